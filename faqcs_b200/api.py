@@ -1,0 +1,387 @@
+"""ctypes binding of include/faqcs_b200.h -- the host-side mirror of the FaQCs
+``trim()`` seam (FaQCs.h:245-248) in Python.
+
+The structures below are field-for-field copies of the C header.  The binding
+is prefix-parametrised (``fq_`` for the CUDA library) so that the test-only
+oracle, which deliberately exports the same shapes under ``fqo_``, can be
+driven by the same ``Engine`` class from ``tests/``; this module itself never
+loads anything under ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+NUM_STAT = 25
+NUM_QUAL = 42
+NUM_BASE = 5
+NUM_COMPOSITION_BIN = 10001
+NUM_COMPOSITION = 6
+REF_BATCH = 32768
+OFFSET_AUTO = -128
+NUM_STREAM = 4
+OUT_R1, OUT_R2, OUT_UNPAIRED, OUT_DISCARD = range(4)
+MODE_HARD, MODE_BWA, MODE_BWA_PLUS = range(3)
+
+FILTER_STAT_NAMES = [
+    "TOTAL_COUNT", "TOTAL_NUMBER", "TOTAL_LENGTH", "TOTAL_TRIMMED_NUMBER", "TOTAL_TRIMMED_LENGTH",
+    "PAIRED_READ_NUMBER", "PAIRED_BASE_LENGTH", "READ_LENGTH", "BASE_LENGTH", "READ_NN", "BASE_NN",
+    "READ_PHIX", "BASE_PHIX", "READ_ADAPTER", "BASE_ADAPTER", "READ_AVG_Q", "BASE_AVG_Q",
+    "READ_QUAL_TRIM", "BASE_QUAL_TRIM", "READ_LOW_COMPLEXITY", "BASE_LOW_COMPLEXITY",
+    "N_TO_A", "N_TO_T", "N_TO_G", "N_TO_C",
+]
+STAT = {n: i for i, n in enumerate(FILTER_STAT_NAMES)}
+
+RR_VALID, RR_F_LENGTH, RR_F_NN, RR_F_AVGQ, RR_F_LOWCOMP, RR_QUAL_TRIMMED, RR_ADAPTER = (
+    0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40)
+
+STATUS_NAMES = {0: "FQ_OK", 1: "FQ_ERR_ARG", 2: "FQ_ERR_CUDA", 3: "FQ_ERR_NO_DEVICE", 4: "FQ_ERR_FORMAT",
+                5: "FQ_ERR_QUALITY", 6: "FQ_ERR_OFFSET", 7: "FQ_ERR_BASE", 8: "FQ_ERR_STATE"}
+
+# Built-in adapter table, in reference order (options.cpp:576-625).  Sequence data.
+BUILTIN_ADAPTERS: List[Tuple[str, str]] = [
+    ("cre-loxp-forward", "TCGTATAACTTCGTATAATGTATGCTATACGAAGTTATTACG"),
+    ("cre-loxp-reverse", "AGCATATTGAAGCATATTACATACGATATGCTTCAATAATGC"),
+    ("TruSeq-adapter-1", "GGGGTAGTGTGGATCCTCCTCTAGGCAGTTGGGTTATTCTAGAAGCAGATGTGTTGGCTGTTTCTGAAACTCTGGAAAA"),
+    ("TruSeq-adapter-3", "CAACAGCCGGTCAAAACATCTGGAGGGTAAGCCATAAACACCTCAACAGAAAA"),
+    ("PCR-primer-1", "CGATAACTTCGTATAATGTATGCTATACGAAGTTATTACG"),
+    ("PCR-primer-2", "GCATAACTTCGTATAGCATACATTATACGAAGTTATACGA"),
+    ("Nextera-primer-adapter-1", "GATCGGAAGAGCACACGTCTGAACTCCAGTCAC"),
+    ("Nextera-primer-adapter-2", "GATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"),
+    ("Nextera-junction-adapter-1", "CTGTCTCTTATACACATCTAGATGTGTATAAGAGACAG"),
+]
+POLYA_ADAPTER = ("polyA", "A" * 20)
+
+
+class CAdapter(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("seq", C.c_char_p)]
+
+
+class COptions(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("quality", C.c_int32), ("trim_5", C.c_uint32), ("trim_3", C.c_uint32),
+        ("min_read_length", C.c_uint32), ("max_num_poly_N", C.c_uint32),
+        ("average_quality", C.c_float), ("low_complexity_cutoff_ratio", C.c_float),
+        ("adapter_mismatch_rate", C.c_float),
+        ("input_quality_offset", C.c_int32), ("output_quality_offset", C.c_int32),
+        ("replace_to_N_q", C.c_uint32), ("qc_only", C.c_int32), ("protect_5", C.c_int32),
+        ("filter_adapter", C.c_int32), ("discard_output", C.c_int32),
+        ("num_thread", C.c_uint32), ("n_adapters", C.c_uint32), ("adapters", C.POINTER(CAdapter)),
+    ]
+
+
+class CReadResult(C.Structure):
+    _fields_ = [("offset_5", C.c_uint32), ("length", C.c_uint32), ("flags", C.c_uint16),
+                ("adapter", C.c_int16), ("avg_q", C.c_float)]
+
+
+READ_RESULT_DTYPE = np.dtype([("offset_5", "<u4"), ("length", "<u4"), ("flags", "<u2"),
+                              ("adapter", "<i2"), ("avg_q", "<f4")])
+
+
+class CBatchOut(C.Structure):
+    _fields_ = [
+        ("data", C.POINTER(C.c_uint8) * NUM_STREAM), ("bytes", C.c_uint64 * NUM_STREAM),
+        ("n_records", C.c_uint64), ("n_valid", C.c_uint64 * 2),
+        ("paired_read_number", C.c_uint64), ("paired_base_length", C.c_uint64),
+        ("results", C.POINTER(CReadResult) * 2),
+    ]
+
+
+U64P = C.POINTER(C.c_uint64)
+
+
+class CStatsView(C.Structure):
+    _fields_ = [
+        ("filter_stats", C.c_uint64 * NUM_STAT), ("n_adapters", C.c_uint32),
+        ("adapter_reads", U64P), ("adapter_bases", U64P),
+        ("pre_rows", C.c_uint32), ("post_rows", C.c_uint32),
+        ("pre_len_size", C.c_uint32), ("post_len_size", C.c_uint32),
+        ("pre_quality_matrix", U64P), ("post_quality_matrix", U64P),
+        ("pre_base_matrix", U64P), ("post_base_matrix", U64P),
+        ("pre_read_quality_hist", U64P), ("pre_base_quality_hist", U64P),
+        ("post_read_quality_hist", U64P), ("post_base_quality_hist", U64P),
+        ("pre_composition", U64P), ("post_composition", U64P),
+        ("pre_length_hist", U64P), ("post_length_hist", U64P),
+    ]
+
+
+@dataclass
+class Options:
+    """Python view of the fields of ``struct Options`` (FaQCs.h:77-144) that ``trim()`` reads.
+    Defaults are the reference's (options.cpp:98-133)."""
+    mode: int = MODE_BWA_PLUS
+    quality: int = 5
+    trim_5: int = 0
+    trim_3: int = 0
+    min_read_length: int = 50
+    max_num_poly_N: int = 2
+    average_quality: float = 0.0
+    low_complexity_cutoff_ratio: float = 0.85
+    adapter_mismatch_rate: float = 0.2
+    input_quality_offset: int = OFFSET_AUTO
+    output_quality_offset: int = 33
+    replace_to_N_q: int = 0
+    qc_only: bool = False
+    protect_5: bool = False
+    filter_adapter: bool = False
+    discard_output: bool = False
+    num_thread: int = 0
+    adapters: List[Tuple[str, str]] = field(default_factory=list)
+
+    def to_c(self):
+        n = len(self.adapters)
+        arr = (CAdapter * max(n, 1))()
+        keep = []
+        for i, (name, seq) in enumerate(self.adapters):
+            bn, bs = name.encode(), seq.encode()
+            keep += [bn, bs]
+            arr[i].name, arr[i].seq = bn, bs
+        c = COptions(self.mode, self.quality, self.trim_5, self.trim_3, self.min_read_length,
+                     self.max_num_poly_N, self.average_quality, self.low_complexity_cutoff_ratio,
+                     self.adapter_mismatch_rate, self.input_quality_offset, self.output_quality_offset,
+                     self.replace_to_N_q, int(self.qc_only), int(self.protect_5), int(self.filter_adapter),
+                     int(self.discard_output), self.num_thread, n, arr)
+        return c, (arr, keep)
+
+
+@dataclass
+class BatchResult:
+    streams: List[bytes]
+    n_records: int
+    n_valid: Tuple[int, int]
+    paired_read_number: int
+    paired_base_length: int
+    results: List[Optional[np.ndarray]]
+
+
+@dataclass
+class Stats:
+    filter_stats: np.ndarray
+    adapter_reads: np.ndarray
+    adapter_bases: np.ndarray
+    pre_quality_matrix: np.ndarray
+    post_quality_matrix: np.ndarray
+    pre_base_matrix: np.ndarray
+    post_base_matrix: np.ndarray
+    pre_read_quality_hist: np.ndarray
+    pre_base_quality_hist: np.ndarray
+    post_read_quality_hist: np.ndarray
+    post_base_quality_hist: np.ndarray
+    pre_composition: np.ndarray
+    post_composition: np.ndarray
+    pre_length_hist: np.ndarray
+    post_length_hist: np.ndarray
+
+    FIELDS = ("filter_stats", "adapter_reads", "adapter_bases", "pre_quality_matrix", "post_quality_matrix",
+              "pre_base_matrix", "post_base_matrix", "pre_read_quality_hist", "pre_base_quality_hist",
+              "post_read_quality_hist", "post_base_quality_hist", "pre_composition", "post_composition",
+              "pre_length_hist", "post_length_hist")
+
+    def diff(self, other: "Stats") -> List[str]:
+        out = []
+        for f in self.FIELDS:
+            a, b = getattr(self, f), getattr(other, f)
+            if a.shape != b.shape:
+                out.append(f"{f}: shape {a.shape} != {b.shape}")
+            elif not np.array_equal(a, b):
+                idx = np.argwhere(a != b)
+                out.append(f"{f}: {len(idx)} cells differ, first {tuple(idx[0])}: {a[tuple(idx[0])]} != {b[tuple(idx[0])]}")
+        return out
+
+
+class FaqcsError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+        self.message = message
+
+
+def _np_from(ptr, n, dtype=np.uint64):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+
+def default_library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfaqcs_b200.so")
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """Load the CUDA C-ABI library.  Fails loudly if it has not been built: there is no fallback."""
+    path = path or default_library_path()
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  faqcs_b200 has no CPU fallback.")
+    return C.CDLL(path)
+
+
+class Engine:
+    """One context of the C ABI (``fq_ctx``) -- the stand-in for the accumulators
+    ``main`` owns (filter_stats, adaptor_stats, PlotInfo; FaQCs.cpp:67-69) plus the
+    ``trim()`` + routing loop applied batch by batch."""
+
+    def __init__(self, options: Options, device: int = 0, lib: Optional[C.CDLL] = None, prefix: str = "fq_"):
+        self.lib = lib if lib is not None else load_library()
+        self.p = prefix
+        self._bind()
+        self.options = options
+        copt, self._keep = options.to_c()
+        self.ctx = C.c_void_p()
+        if prefix == "fq_":
+            st = self._f("create")(C.byref(copt), C.c_int(device), C.byref(self.ctx))
+        else:
+            st = self._f("create")(C.byref(copt), C.byref(self.ctx))
+        if st != 0:
+            raise FaqcsError(st, self._f("last_error")(None).decode(errors="replace"))
+
+    def _f(self, name):
+        return getattr(self.lib, self.p + name)
+
+    def _bind(self):
+        L = self.lib
+        p = self.p
+        getattr(L, p + "last_error").restype = C.c_char_p
+        getattr(L, p + "last_error").argtypes = [C.c_void_p]
+        getattr(L, p + "destroy").argtypes = [C.c_void_p]
+        getattr(L, p + "destroy").restype = None
+        getattr(L, p + "set_debug_results").argtypes = [C.c_void_p, C.c_int]
+        getattr(L, p + "autodetect").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        getattr(L, p + "process_host").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                   C.c_uint64, C.c_int, C.POINTER(CBatchOut)]
+        getattr(L, p + "stats").argtypes = [C.c_void_p, C.POINTER(CStatsView)]
+        if p == "fq_":
+            L.fq_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                            C.c_uint64, C.c_int, C.c_int, C.POINTER(CBatchOut)]
+            L.fq_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+            L.fq_launch_count.argtypes = [C.c_void_p]
+            L.fq_launch_count.restype = C.c_uint64
+            L.fq_stream.argtypes = [C.c_void_p]
+            L.fq_stream.restype = C.c_void_p
+            L.fq_stats_device_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                                 C.POINTER(C.c_void_p)]
+            L.fq_stats_commit.argtypes = [C.c_void_p]
+            L.fq_reset_stats.argtypes = [C.c_void_p]
+            L.fq_device_outputs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p * NUM_STREAM)]
+            L.fq_build_info.restype = C.c_char_p
+
+    def _check(self, st):
+        if st != 0:
+            raise FaqcsError(st, self._f("last_error")(self.ctx).decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self._f("destroy")(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- API -------------------------------------------------------------
+    def set_debug_results(self, enable: bool = True):
+        self._check(self._f("set_debug_results")(self.ctx, int(enable)))
+
+    @staticmethod
+    def _buf(b):
+        if b is None:
+            return None, 0, None
+        if isinstance(b, (bytes, bytearray)):
+            a = np.frombuffer(b, dtype=np.uint8)
+        else:
+            a = np.ascontiguousarray(b, dtype=np.uint8)
+        return C.c_void_p(a.ctypes.data) if a.size else C.c_void_p(0), a.size, a
+
+    def autodetect(self, r1, r2=None) -> Tuple[int, int]:
+        p1, n1, k1 = self._buf(r1)
+        p2, n2, k2 = self._buf(r2)
+        off, q = C.c_int32(), C.c_int32()
+        self._check(self._f("autodetect")(self.ctx, p1, n1, p2, n2, C.byref(off), C.byref(q)))
+        return off.value, q.value
+
+    def _collect(self, out: CBatchOut, paired: bool, want_data: bool = True) -> BatchResult:
+        streams = []
+        for s in range(NUM_STREAM):
+            n = int(out.bytes[s])
+            streams.append(C.string_at(out.data[s], n) if (n and want_data and out.data[s]) else b"")
+        results: List[Optional[np.ndarray]] = [None, None]
+        for m in range(2 if paired else 1):
+            if out.results[m]:
+                raw = C.string_at(out.results[m], int(out.n_records) * C.sizeof(CReadResult))
+                results[m] = np.frombuffer(raw, dtype=READ_RESULT_DTYPE).copy()
+        return BatchResult(streams, int(out.n_records), (int(out.n_valid[0]), int(out.n_valid[1])),
+                           int(out.paired_read_number), int(out.paired_base_length), results)
+
+    def process(self, r1, r2=None, first_record_index: int = 0, is_final: bool = True) -> BatchResult:
+        """Host buffers in, host buffers out (fq_process_host)."""
+        p1, n1, k1 = self._buf(r1)
+        p2, n2, k2 = self._buf(r2)
+        out = CBatchOut()
+        self._check(self._f("process_host")(self.ctx, p1, n1, p2, n2, first_record_index, int(is_final),
+                                            C.byref(out)))
+        return self._collect(out, r2 is not None)
+
+    def process_device(self, d_r1: int, n1: int, d_r2: Optional[int] = None, n2: int = 0,
+                       first_record_index: int = 0, is_final: bool = True, copy_out: bool = False) -> BatchResult:
+        """Device pointers in (fq_process_device); outputs stay in HBM unless copy_out."""
+        out = CBatchOut()
+        self._check(self.lib.fq_process_device(self.ctx, C.c_void_p(d_r1), n1,
+                                               C.c_void_p(d_r2) if d_r2 else None, n2,
+                                               first_record_index, int(is_final), int(copy_out), C.byref(out)))
+        return self._collect(out, d_r2 is not None, want_data=copy_out)
+
+    def last_timing(self) -> Tuple[float, float]:
+        a, b = C.c_float(), C.c_float()
+        self._check(self.lib.fq_last_timing(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.fq_launch_count(self.ctx))
+
+    def stream(self) -> int:
+        return int(self.lib.fq_stream(self.ctx) or 0)
+
+    def stats_device_buffer(self) -> Tuple[int, int, int]:
+        d, n, r = C.c_void_p(), C.c_size_t(), C.c_void_p()
+        self._check(self.lib.fq_stats_device_buffer(self.ctx, C.byref(d), C.byref(n), C.byref(r)))
+        return int(d.value), int(n.value), int(r.value)
+
+    def stats_commit(self):
+        self._check(self.lib.fq_stats_commit(self.ctx))
+
+    def stats(self) -> Stats:
+        v = CStatsView()
+        self._check(self._f("stats")(self.ctx, C.byref(v)))
+        na = v.n_adapters
+        return Stats(
+            filter_stats=np.array(list(v.filter_stats), dtype=np.uint64),
+            adapter_reads=_np_from(v.adapter_reads, na), adapter_bases=_np_from(v.adapter_bases, na),
+            pre_quality_matrix=_np_from(v.pre_quality_matrix, v.pre_rows * NUM_QUAL).reshape(-1, NUM_QUAL),
+            post_quality_matrix=_np_from(v.post_quality_matrix, v.post_rows * NUM_QUAL).reshape(-1, NUM_QUAL),
+            pre_base_matrix=_np_from(v.pre_base_matrix, v.pre_rows * NUM_BASE).reshape(-1, NUM_BASE),
+            post_base_matrix=_np_from(v.post_base_matrix, v.post_rows * NUM_BASE).reshape(-1, NUM_BASE),
+            pre_read_quality_hist=_np_from(v.pre_read_quality_hist, NUM_QUAL),
+            pre_base_quality_hist=_np_from(v.pre_base_quality_hist, NUM_QUAL),
+            post_read_quality_hist=_np_from(v.post_read_quality_hist, NUM_QUAL),
+            post_base_quality_hist=_np_from(v.post_base_quality_hist, NUM_QUAL),
+            pre_composition=_np_from(v.pre_composition, NUM_COMPOSITION * NUM_COMPOSITION_BIN).reshape(
+                NUM_COMPOSITION, NUM_COMPOSITION_BIN),
+            post_composition=_np_from(v.post_composition, NUM_COMPOSITION * NUM_COMPOSITION_BIN).reshape(
+                NUM_COMPOSITION, NUM_COMPOSITION_BIN),
+            pre_length_hist=_np_from(v.pre_length_hist, v.pre_len_size),
+            post_length_hist=_np_from(v.post_length_hist, v.post_len_size),
+        )

@@ -1,0 +1,67 @@
+"""Pin the CPU oracle against the UNMODIFIED reference binary (oracle/_ref/FaQCs).
+
+These tests are what makes the oracle trustworthy: emitted FASTQ bytes, every
+integer in QC.stats.txt and the ten --debug matrix / histogram files must agree.
+They run only where oracle/_ref/FaQCs exists (this container and, because the
+binary travels with the snapshot, the GPU box)."""
+import numpy as np
+import pytest
+
+import refcli
+from faqcs_b200 import synth
+from faqcs_b200.api import MODE_BWA, MODE_HARD, Options
+from oracle_binding import OracleEngine
+from parity import assert_matches_reference, run_engine
+
+pytestmark = [pytest.mark.ref, pytest.mark.skipif(not refcli.have_ref(), reason="reference binary not built")]
+
+
+def check(w, opt, threads=1, polyA=False, artifacts=None, extra_flags=(), batch_records=None):
+    flags = refcli.flags_for(opt, polyA=polyA) + list(extra_flags)
+    if w.r2 is not None:
+        ref = refcli.run_reference(w.r1, w.r2, flags=flags, threads=threads, artifacts=artifacts)
+    else:
+        ref = refcli.run_reference(unpaired=w.r1, flags=flags, threads=threads, artifacts=artifacts)
+    opt.adapters = refcli.adapters_for(opt.filter_adapter, polyA, artifacts)
+    if artifacts:
+        opt.filter_adapter = True
+    with OracleEngine(opt) as eng:
+        streams, _ = run_engine(eng, w.r1, w.r2, batch_records)
+        assert_matches_reference(ref, streams, eng.stats(), opt, opt.adapters)
+
+
+def test_c2_defaults():
+    check(synth.c2(20000), Options())
+
+
+def test_c2_defaults_multibatch_t4():
+    check(synth.c2(40000), Options(), threads=4, batch_records=32768)
+
+
+def test_c2_discard_5end_3end():
+    check(synth.c2(5000), Options(trim_5=7, trim_3=11, discard_output=True))
+
+
+def test_c2_bwa_and_hard_modes():
+    check(synth.c2(5000), Options(mode=MODE_BWA, quality=15, discard_output=True))
+    check(synth.c2(5000), Options(mode=MODE_HARD, quality=25, discard_output=True))
+    check(synth.c2(5000), Options(quality=20, protect_5=True, average_quality=30.0))
+
+
+def test_c4_qc_only():
+    check(synth.c4(30000), Options(qc_only=True))
+
+
+def test_c5_mixed_ascii64_hard():
+    check(synth.c5(20000), Options(mode=MODE_HARD, quality=20, average_quality=25.0, replace_to_N_q=10,
+                                   discard_output=True))
+
+
+def test_c3_adapters_polya_artifacts_t1():
+    w = synth.c3(1500)
+    check(w, Options(filter_adapter=True, num_thread=1), threads=1, polyA=True, artifacts=w.artifacts)
+
+
+def test_c3_adapters_qc_only():
+    w = synth.c3(1000)
+    check(w, Options(filter_adapter=True, qc_only=True, num_thread=2), threads=2, polyA=True)
