@@ -2,10 +2,10 @@
 ``trim()`` seam (FaQCs.h:245-248) in Python.
 
 The structures below are field-for-field copies of the C header.  The binding
-is prefix-parametrised (``fq_`` for the CUDA library) so that the test-only
-oracle, which deliberately exports the same shapes under ``fqo_``, can be
-driven by the same ``Engine`` class from ``tests/``; this module itself never
-loads anything under ``oracle/``.
+is prefix-parametrised (``fq_`` for the CUDA library) so that the test-only CPU
+checker, which deliberately exports the same shapes under another prefix, can
+be driven by the same ``Engine`` class from ``tests/``; this module itself only
+ever loads ``libfaqcs_b200.so``.
 """
 from __future__ import annotations
 
@@ -266,7 +266,12 @@ class Engine:
             L.fq_stream.restype = C.c_void_p
             L.fq_stats_device_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                                  C.POINTER(C.c_void_p)]
-            L.fq_stats_commit.argtypes = [C.c_void_p]
+            L.fq_stats_reserve_rows.argtypes = [C.c_void_p, C.c_uint32]
+            L.fq_set_check_pair_ids.argtypes = [C.c_void_p, C.c_int]
+            L.fq_host_alloc.argtypes = [C.c_size_t]
+            L.fq_host_alloc.restype = C.c_void_p
+            L.fq_host_free.argtypes = [C.c_void_p]
+            L.fq_host_free.restype = None
             L.fq_reset_stats.argtypes = [C.c_void_p]
             L.fq_device_outputs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p * NUM_STREAM)]
             L.fq_build_info.restype = C.c_char_p
@@ -360,8 +365,11 @@ class Engine:
         self._check(self.lib.fq_stats_device_buffer(self.ctx, C.byref(d), C.byref(n), C.byref(r)))
         return int(d.value), int(n.value), int(r.value)
 
-    def stats_commit(self):
-        self._check(self.lib.fq_stats_commit(self.ctx))
+    def stats_reserve_rows(self, rows: int):
+        self._check(self.lib.fq_stats_reserve_rows(self.ctx, rows))
+
+    def reset_stats(self):
+        self._check(self.lib.fq_reset_stats(self.ctx))
 
     def stats(self) -> Stats:
         v = CStatsView()

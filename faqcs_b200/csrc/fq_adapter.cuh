@@ -1,0 +1,225 @@
+// fq_adapter.cuh -- adapter / artifact matching (trim_adapters_and_phiX, trim.cpp:961-1142;
+// SeqOverlap::align_smith_waterman, seq_overlap.cpp:46-370; find_mask_range, trim.cpp:1144-1189).
+//
+// The reference's "Smith-Waterman" has gaps compiled out, so every diagonal of
+// the read x adapter matrix is an independent recurrence
+//     M_k = max(M_{k-1}, 0) + (match ? +1 : -1),   start_k = (M_{k-1} < 0) ? i_k : start_{k-1}
+// and the reported alignment is the cell with the largest M, ties going to the
+// LAST cell in (i outer, j inner) order (seq_overlap.cpp:342 uses >=).  Here one
+// warp owns a read, lanes own diagonals (32 at a time), the adapter set lives in
+// shared memory for the whole CTA, and the winner is picked with a warp max over
+// the key (M, i, j).  Integer ALU bound, not HBM bound.
+#pragma once
+#include "fq_common.cuh"
+#include "fq_trim.cuh"
+
+namespace fq {
+
+struct AdapterSet {
+    const uint8_t *codes;     // concatenated NA bit codes (seq_overlap.h:133-150)
+    const uint32_t *offset;   // [n + 1]
+    uint32_t n;
+    uint32_t total;           // bytes in codes
+    uint32_t any_bits;        // per-adapter OR of codes is in or_bits
+    const uint8_t *or_bits;   // [n]
+};
+
+struct AdapterArgs {
+    const uint8_t *raw[2];
+    const Rec *rec[2];
+    uint2 *adp[2];
+    int32_t *adp_best[2];
+    uint32_t n_rec, n_mates;
+    uint32_t max_len;            // longest read in the batch (sizes the per-warp buffers)
+    unsigned long long *stats;
+    StatsLayout L;
+    BatchInfo *info;
+    unsigned long long first_index;   // global index of record 0 (Q3 emulation)
+    unsigned long long end_index;     // first_index + n_rec if this is the final batch, else ~0
+};
+
+// seq_overlap.cpp:372-411; 0xff = unknown base (the reference throws)
+__device__ __forceinline__ uint32_t na_to_bits(uint32_t c)
+{
+    switch (c | 0x20u) {
+        case 'a': return 1;  case 'c': return 2;  case 'g': return 4;  case 't': return 8;
+        case 'm': return 3;  case 'r': return 5;  case 's': return 6;  case 'v': return 7;
+        case 'w': return 9;  case 'y': return 10; case 'h': return 11; case 'k': return 12;
+        case 'd': return 13; case 'b': return 14; case 'n': return 15;
+        default: return c == '-' ? 16u : 0xffu;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevOpts o, const AdapterSet A)
+{
+    extern __shared__ uint32_t smem_u32[];
+    // layout: [adapter offsets n+1][adapter codes, padded to 4][per-warp: read codes (max_len padded to 4) + mask words]
+    uint32_t *s_off = smem_u32;
+    uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_off + A.n + 1);
+    const uint32_t codes_pad = (A.total + 3) & ~3u;
+    const uint32_t read_pad = (a.max_len + 3) & ~3u;
+    const uint32_t mask_words = (a.max_len + 31) >> 5;
+    const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *warp_base = s_codes + codes_pad + (size_t)warp_in_cta * (read_pad + 4 * mask_words);
+    uint8_t *s_read = warp_base;
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(warp_base + read_pad);
+
+    for (uint32_t i = threadIdx.x; i <= A.n; i += blockDim.x) s_off[i] = A.offset[i];
+    for (uint32_t i = threadIdx.x; i < A.total; i += blockDim.x) s_codes[i] = A.codes[i];
+    __syncthreads();
+
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t total = a.n_rec * a.n_mates;
+
+    for (uint32_t g = warp_global; g < total; g += n_warps) {
+        const uint32_t mate = g >= a.n_rec ? 1 : 0;
+        const uint32_t r = g - mate * a.n_rec;
+        const Rec rc = a.rec[mate][r];
+        const uint32_t L = rc.len;
+        const uint8_t *sp = a.raw[mate] + rc.seq;
+
+        // pack_query (seq_overlap.h:370-411)
+        bool unknown = false;
+        uint32_t read_or = 0;
+        for (uint32_t p = lane; p < L; p += 32) {
+            const uint32_t b = na_to_bits(sp[p]);
+            unknown |= (b == 0xffu);
+            read_or |= b;
+            s_read[p] = (uint8_t)b;
+        }
+        for (uint32_t w = lane; w < mask_words; w += 32) s_mask[w] = 0;     // 1 = masked
+        if (__any_sync(0xffffffffu, unknown)) {
+            if (lane == 0) { atomicOr(&a.info->err, kErrUnknownBase); atomicMin(&a.info->err_record, r); }
+        }
+#pragma unroll
+        for (int k = 16; k; k >>= 1) read_or |= __shfl_xor_sync(0xffffffffu, read_or, k);
+        __syncwarp();
+
+        // Q3: which length feeds the match threshold (trim.cpp:985,996-1008,1074-1082)
+        uint32_t thr_len = L;
+        bool thr_min = true;            // threshold uses min(thr_len, T); false: T alone (tail group)
+        if (o.num_thread) {
+            const unsigned long long gidx = a.first_index + r;
+            const unsigned long long bstart = gidx - (gidx % FQ_REF_BATCH);
+            unsigned long long N = FQ_REF_BATCH;
+            if (a.end_index != ~0ull && a.end_index - bstart < N) N = a.end_index - bstart;
+            const uint32_t ib = (uint32_t)(gidx - bstart), nt = o.num_thread;
+            const uint32_t q = (uint32_t)N / nt, rr = (uint32_t)N % nt;
+            uint32_t cs, sz;
+            if (ib < rr * (q + 1)) { const uint32_t t = ib / (q + 1); cs = t * (q + 1); sz = q + 1; }
+            else { const uint32_t t = rr + (q ? (ib - rr * (q + 1)) / q : 0); cs = rr * (q + 1) + (t - rr) * q; sz = q; }
+            const uint32_t pc = ib - cs, grp = pc >> 3;
+            if (grp * 8 + 8 <= sz) thr_len = a.rec[mate][r + (grp * 8 + 7 - pc)].len;
+            else thr_min = false;
+        }
+
+        int best_score = 0, best_adapter = -1;
+        int st_start = 0, st_stop = 0;            // max_elem.M_start_i / stop_i survive across align() calls (Q5)
+        bool any_pass = false;
+
+        for (uint32_t j = 0; j < A.n; ++j) {
+            const uint32_t T = s_off[j + 1] - s_off[j];
+            const uint8_t *t = s_codes + s_off[j];
+            int score = 0;
+            if ((read_or & A.or_bits[j]) && L && T) {
+                // per-lane best over the diagonals this lane walks: (M, i, jj) lexicographic max
+                int bM = 0, bi = 0, bj = 0, bst = 0;
+                for (int d0 = -(int)(L - 1); d0 <= (int)T - 1; d0 += 32) {
+                    const int d = d0 + (int)lane;
+                    const int i_lo = max(0, -(d0 + 31));
+                    const int i_hi = min((int)L - 1, (int)T - 1 - d0);
+                    int M = 0, st = i_lo, gM = 0, gi = 0, gst = 0;
+                    for (int i = i_lo; i <= i_hi; ++i) {
+                        const int jj = i + d;
+                        const uint32_t qi = s_read[i];
+                        if ((unsigned)jj < T) {
+                            const bool match = (qi & t[jj]) != 0;
+                            st = (M < 0) ? i : st;
+                            M = max(M, 0) + (match ? 1 : -1);
+                            if (M >= gM && M > 0) { gM = M; gi = i; gst = st; }
+                        } else {
+                            M = 0;
+                            st = i + 1;
+                        }
+                    }
+                    const int gj = gi + d;
+                    if (gM > bM || (gM == bM && gM > 0 && (gi > bi || (gi == bi && gj > bj)))) { bM = gM; bi = gi; bj = gj; bst = gst; }
+                }
+                unsigned long long key = bM > 0 ? (((unsigned long long)bM << 48) | ((unsigned long long)bi << 24) | (unsigned long long)bj) : 0ull;
+                unsigned long long kmax = key;
+#pragma unroll
+                for (int k = 16; k; k >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, kmax, k);
+                    kmax = other > kmax ? other : kmax;
+                }
+                if (kmax) {
+                    const uint32_t win = __ballot_sync(0xffffffffu, key == kmax);
+                    const int src = __ffs(win) - 1;
+                    score = (int)(kmax >> 48);
+                    st_stop = (int)((kmax >> 24) & 0xffffffu);
+                    st_start = __shfl_sync(0xffffffffu, bst, src);
+                }
+            }
+            // trim.cpp:1021-1041
+            const uint32_t tl = thr_min ? min(thr_len, T) : T;
+            const int threshold = __float2int_rz(__fmul_rn(o.match_rate, (float)tl));
+            const int match_length = st_stop - st_start + 1;
+            const int num_match = (match_length + score) / 2;
+            if (num_match >= threshold) {
+                any_pass = true;
+                for (uint32_t w = lane; w < mask_words; w += 32) {
+                    const int lo_b = max(st_start, (int)(w << 5)), hi_b = min(st_stop, (int)(w << 5) + 31);
+                    if (lo_b <= hi_b) {
+                        const uint32_t nb = (uint32_t)(hi_b - lo_b + 1);
+                        const uint32_t bits = (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u)) << (lo_b & 31);
+                        s_mask[w] |= bits;
+                    }
+                }
+                if (score > best_score) { best_score = score; best_adapter = (int)j; }
+            }
+        }
+        __syncwarp();
+
+        uint32_t out_start = 0, out_len = L;
+        if (best_score > 0) {
+            // find_mask_range (trim.cpp:1144-1189) over runs instead of bits; every lane runs it redundantly
+            uint32_t run_start = 0, run_len = 0, longest = 0, longest_start = 0;
+            for (uint32_t w = 0; w < mask_words; ++w) {
+                const uint32_t nbits = min(32u, L - (w << 5));
+                uint32_t keep = ~s_mask[w];
+                if (nbits < 32) keep &= (1u << nbits) - 1u;
+                uint32_t bp = 0;
+                while (bp < nbits) {
+                    const uint32_t x = keep >> bp;
+                    if (x & 1u) {
+                        const uint32_t ones = min((uint32_t)(__ffs(~x) ? __ffs(~x) - 1 : 32), nbits - bp);
+                        if (run_len == 0) run_start = (w << 5) + bp;
+                        run_len += ones;
+                        bp += ones;
+                    } else {
+                        const uint32_t zeros = x ? (uint32_t)(__ffs(x) - 1) : (nbits - bp);
+                        if (run_len > longest) { longest = run_len; longest_start = run_start; run_len = 0; }
+                        bp += zeros;
+                    }
+                }
+            }
+            if (run_len > longest) { longest = run_len; longest_start = run_start; }
+            if (longest == 0) longest_start = 0;
+            out_start = longest_start;
+            out_len = longest;
+            if (lane == 0) {
+                atomicAdd(&a.stats[a.L.adapter_reads + best_adapter], 1ull);
+                atomicAdd(&a.stats[a.L.adapter_bases + best_adapter], (unsigned long long)(L - longest));
+            }
+        }
+        (void)any_pass;
+        if (lane == 0) {
+            a.adp[mate][r] = make_uint2(out_start, out_len);
+            a.adp_best[mate][r] = best_score > 0 ? best_adapter : -1;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace fq

@@ -1,0 +1,749 @@
+// fq_api.cu -- C ABI (include/faqcs_b200.h) over the sm_100a kernels.
+//
+// One fq_ctx = one CUDA device + one stream + the run's accumulators (the
+// filter_stats / adaptor_stats / PlotInfo trio main() owns, FaQCs.cpp:67-69).
+// A batch goes through: frame -> [pair-id check] -> [adapter pass] -> trim ->
+// route -> scan -> emit.  There is no CPU implementation of any of these steps
+// in this library: without a CUDA device fq_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fq_adapter.cuh"
+#include "fq_common.cuh"
+#include "fq_emit.cuh"
+#include "fq_frame.cuh"
+#include "fq_trim.cuh"
+
+using namespace fq;
+
+#define FQ_STR2(x) #x
+#define FQ_STR(x) FQ_STR2(x)
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+const char *kPhiX = "__PhiX174_NC_001422__";                       // FaQCs.h:29-30
+const char *kPhiXComplement = "__PhiX174_NC_001422_complement__";
+
+int na_bits_host(char c)
+{
+    switch (c | 0x20) {
+        case 'a': return 1;  case 'c': return 2;  case 'g': return 4;  case 't': return 8;
+        case 'm': return 3;  case 'r': return 5;  case 's': return 6;  case 'v': return 7;
+        case 'w': return 9;  case 'y': return 10; case 'h': return 11; case 'k': return 12;
+        case 'd': return 13; case 'b': return 14; case 'n': return 15;
+        default: return c == '-' ? 16 : -1;
+    }
+}
+
+}  // namespace
+
+struct fq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    fq_options opt{};
+    DevOpts dopt{};
+    std::vector<std::string> adapter_names, adapter_seqs;
+    AdapterSet aset{};
+    DevBuf d_adp_codes, d_adp_off, d_adp_or;
+
+    DevBuf d_raw[2], d_chunk[2], d_nl[2], d_rec[2], d_adp[2], d_adp_best[2], d_res[2], d_dbg[2], d_tile, d_out[4];
+    DevBuf d_info, d_stats, d_rows;
+    BatchInfo *h_info = nullptr;       // pinned
+    StatsLayout L{};
+    PinnedBuf h_out[4], h_dbg[2], h_stats;
+    bool debug_results = false;
+    bool check_pair_ids = true;
+
+    // host-side stats views handed out by fq_stats
+    std::vector<uint64_t> v_adapter_reads, v_adapter_bases, v_pre_q, v_post_q, v_pre_b, v_post_b, v_hist[4], v_pre_comp,
+        v_post_comp, v_pre_len, v_post_len;
+
+    std::string error;
+    uint64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float t_all = 0, t_trim = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    const void *last_dev_out[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+fq_status fail(fq_ctx *c, fq_status code, const std::string &msg)
+{
+    if (c) c->error = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(ctx, FQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+
+uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+// (Re)allocate the stats block for at least `rows` position rows, keeping the contents.
+fq_status ensure_stats_rows(fq_ctx *ctx, uint32_t rows)
+{
+    rows = std::max(64u, round_up(rows, 64));
+    if (ctx->d_stats.p && rows <= ctx->L.rows) return FQ_OK;
+    const StatsLayout oldL = ctx->L;
+    const StatsLayout newL = StatsLayout::make(rows, ctx->opt.n_adapters);
+    std::vector<unsigned long long> oldv, newv(newL.total, 0);
+    if (ctx->d_stats.p) {
+        oldv.resize(oldL.total);
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpy(oldv.data(), ctx->d_stats.p, oldL.total * 8, cudaMemcpyDeviceToHost));
+        auto copy = [&](size_t so, size_t dso, size_t n) { std::copy(oldv.begin() + so, oldv.begin() + so + n, newv.begin() + dso); };
+        copy(oldL.filter, newL.filter, 32);
+        copy(oldL.adapter_reads, newL.adapter_reads, oldL.n_adapters);
+        copy(oldL.adapter_bases, newL.adapter_bases, oldL.n_adapters);
+        copy(oldL.pre_rq, newL.pre_rq, 4 * kQualCols);
+        copy(oldL.pre_comp, newL.pre_comp, 12 * (size_t)kCompBins);
+        for (int c = 0; c < kQualCols; ++c) {
+            copy(oldL.pre_q + (size_t)c * oldL.rows, newL.pre_q + (size_t)c * newL.rows, oldL.rows);
+            copy(oldL.rem_q + (size_t)c * oldL.rows, newL.rem_q + (size_t)c * newL.rows, oldL.rows);
+        }
+        for (int c = 0; c < kBaseCols; ++c) {
+            copy(oldL.pre_b + (size_t)c * oldL.rows, newL.pre_b + (size_t)c * newL.rows, oldL.rows);
+            copy(oldL.rem_b + (size_t)c * oldL.rows, newL.rem_b + (size_t)c * newL.rows, oldL.rows);
+        }
+        copy(oldL.g2n, newL.g2n, oldL.rows);
+        copy(oldL.pre_len, newL.pre_len, oldL.rows + 1);
+        copy(oldL.post_len, newL.post_len, oldL.rows + 1);
+    }
+    DevBuf nb;
+    CK(nb.ensure(newL.total * 8));
+    CK(cudaMemcpy(nb.p, newv.data(), newL.total * 8, cudaMemcpyHostToDevice));
+    ctx->d_stats.release();
+    ctx->d_stats = nb;
+    ctx->L = newL;
+    return FQ_OK;
+}
+
+fq_status upload_adapters(fq_ctx *ctx)
+{
+    const uint32_t n = ctx->opt.n_adapters;
+    std::vector<uint8_t> codes, orb(n ? n : 1, 0);
+    std::vector<uint32_t> off(n + 1, 0);
+    for (uint32_t j = 0; j < n; ++j) {
+        off[j] = (uint32_t)codes.size();
+        for (char ch : ctx->adapter_seqs[j]) {
+            const int b = na_bits_host(ch);
+            if (b < 0) return fail(ctx, FQ_ERR_BASE, "seq_overlap.cpp:na_to_bits: Unknown base!");
+            codes.push_back((uint8_t)b);
+            orb[j] |= (uint8_t)b;
+        }
+    }
+    off[n] = (uint32_t)codes.size();
+    CK(ctx->d_adp_codes.ensure(codes.size() + 16));
+    CK(ctx->d_adp_off.ensure(off.size() * 4));
+    CK(ctx->d_adp_or.ensure(orb.size()));
+    if (!codes.empty()) CK(cudaMemcpy(ctx->d_adp_codes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_adp_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_adp_or.p, orb.data(), orb.size(), cudaMemcpyHostToDevice));
+    ctx->aset.codes = ctx->d_adp_codes.as<uint8_t>();
+    ctx->aset.offset = ctx->d_adp_off.as<uint32_t>();
+    ctx->aset.or_bits = ctx->d_adp_or.as<uint8_t>();
+    ctx->aset.n = n;
+    ctx->aset.total = (uint32_t)codes.size();
+    ctx->aset.any_bits = 0;
+    return FQ_OK;
+}
+
+void refresh_dev_opts(fq_ctx *ctx)
+{
+    const fq_options &o = ctx->opt;
+    DevOpts &d = ctx->dopt;
+    d.mode = o.mode;
+    d.quality = (int)(signed char)o.quality;
+    d.trim_5 = o.trim_5;
+    d.trim_3 = o.trim_3;
+    d.min_len = o.min_read_length;
+    d.max_poly_n = o.max_num_poly_N;
+    d.avg_q = o.average_quality;
+    d.lc = o.low_complexity_cutoff_ratio;
+    d.match_rate = (float)(1.0 - (double)o.adapter_mismatch_rate);     // trim.cpp:969
+    d.in_off = (int)(signed char)o.input_quality_offset;
+    d.out_off = (int)(signed char)o.output_quality_offset;
+    d.replace_q = o.replace_to_N_q;
+    d.qc_only = o.qc_only;
+    d.protect_5 = o.protect_5;
+    d.filter_adapter = o.filter_adapter && o.n_adapters > 0;
+    d.discard = o.discard_output;
+    d.num_thread = o.num_thread;
+    d.n_adapters = o.n_adapters;
+}
+
+// Framing of one mate: count -> scan -> (sync) -> scatter -> records.
+fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_t *n_rec_out)
+{
+    *n_rec_out = 0;
+    if (n == 0) return FQ_OK;
+    if (n >= (1ull << 32)) return fail(ctx, FQ_ERR_ARG, "batch larger than 4 GiB per mate: split it");
+    if ((reinterpret_cast<uintptr_t>(d_raw) & 15) != 0) return fail(ctx, FQ_ERR_ARG, "device input must be 16-byte aligned");
+    BatchInfo *info = ctx->d_info.as<BatchInfo>();
+    const uint32_t n_chunks = (uint32_t)((n + kChunkBytes - 1) / kChunkBytes);
+    CK(ctx->d_chunk[m].ensure((size_t)n_chunks * 4));
+    const int grid = std::max(1, std::min<int>((n_chunks + 7) / 8, ctx->sm_count * 8));
+    k_count_lines<<<grid, 256, 0, ctx->stream>>>(d_raw, n, ctx->d_chunk[m].as<uint32_t>(), n_chunks, info, m);
+    k_scan_chunks<<<1, 1024, 0, ctx->stream>>>(ctx->d_chunk[m].as<uint32_t>(), n_chunks, info, m);
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t n_lines = ctx->h_info->n_lines[m];
+    if (n_lines % 4 != 0) {
+        static const char *msg[4] = {"", "fastq.cpp:next_read: Unable to read sequence", "fastq.cpp:next_read: Unable to read '+'",
+                                     "fastq.cpp:next_read: Unable to read quality"};
+        return fail(ctx, FQ_ERR_FORMAT, msg[n_lines % 4]);
+    }
+    const uint32_t n_rec = n_lines / 4;
+    if (n_rec == 0) return FQ_OK;
+    CK(ctx->d_nl[m].ensure((size_t)n_lines * 4));
+    CK(ctx->d_rec[m].ensure((size_t)n_rec * sizeof(Rec)));
+    k_scatter_lines<<<grid, 256, 0, ctx->stream>>>(d_raw, n, ctx->d_chunk[m].as<uint32_t>(), n_chunks, ctx->d_nl[m].as<uint32_t>());
+    k_build_records<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(d_raw, ctx->d_nl[m].as<uint32_t>(), n_rec, ctx->d_rec[m].as<Rec>(), info, m);
+    ctx->launches += 2;
+    *n_rec_out = n_rec;
+    return FQ_OK;
+}
+
+fq_status map_device_error(fq_ctx *ctx, const BatchInfo &hi)
+{
+    if (!hi.err) return FQ_OK;
+    char where[64];
+    snprintf(where, sizeof where, " (record %u)", hi.err_record);
+    if (hi.err & kErrLenMismatch) return fail(ctx, FQ_ERR_FORMAT, std::string("fastq.cpp:next_read: |Sequence| != |Quality|") + where);
+    if (hi.err & kErrLoneCR) return fail(ctx, FQ_ERR_FORMAT, std::string("carriage return inside a line is not supported") + where);
+    if (hi.err & kErrPairId) return fail(ctx, FQ_ERR_FORMAT, std::string("FaQCs.cpp:trim: I/O error") + where);
+    if (hi.err & kErrUnknownBase) return fail(ctx, FQ_ERR_BASE, std::string("seq_overlap.cpp:na_to_bits: Unknown base!") + where);
+    if (hi.err & kErrQualGt41)
+        return fail(ctx, FQ_ERR_QUALITY,
+                    std::string("fastq.h:quality_score: Found a quality score value that is greater than the maximum allowed quality score") + where);
+    if (hi.err & kErrReencode) return fail(ctx, FQ_ERR_QUALITY, std::string("trim.cpp: quality error!") + where);
+    return fail(ctx, FQ_ERR_STATE, "unknown device error");
+}
+
+fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint8_t *d_r2, size_t n2, bool paired,
+                         uint64_t first_record_index, int is_final, int copy_out, fq_batch_out *out)
+{
+    memset(out, 0, sizeof(*out));
+    for (auto &p : ctx->last_dev_out) p = nullptr;
+    if (ctx->opt.input_quality_offset == FQ_OFFSET_AUTO)
+        return fail(ctx, FQ_ERR_STATE, "quality offset not set; call fq_autodetect on the first batch");
+    refresh_dev_opts(ctx);
+    ctx->dopt.paired = paired ? 1 : 0;
+    const DevOpts o = ctx->dopt;
+    if (o.filter_adapter && o.num_thread && (first_record_index % FQ_REF_BATCH) != 0)
+        return fail(ctx, FQ_ERR_ARG, "thread-count emulation needs batches that start on a 32768-record boundary");
+    BatchInfo *info = ctx->d_info.as<BatchInfo>();
+    BatchInfo init{};
+    init.err_record = 0xffffffffu;
+    init.detect_key = ~0ull;
+    *ctx->h_info = init;
+    CK(cudaMemcpyAsync(info, ctx->h_info, sizeof(BatchInfo), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+
+    uint32_t n_rec[2] = {0, 0};
+    fq_status st = frame_mate(ctx, 0, d_r1, n1, &n_rec[0]);
+    if (st != FQ_OK) return st;
+    if (paired) {
+        st = frame_mate(ctx, 1, d_r2, n2, &n_rec[1]);
+        if (st != FQ_OK) return st;
+        if (n_rec[0] != n_rec[1]) return fail(ctx, FQ_ERR_FORMAT, "FaQCs.cppI/O error");   // FaQCs.cpp:370-380 (sic)
+    }
+    const uint32_t n = n_rec[0];
+    const int n_mates = paired ? 2 : 1;
+    out->n_records = n;
+    if (o.filter_adapter && o.num_thread && !is_final && (n % FQ_REF_BATCH) != 0)
+        return fail(ctx, FQ_ERR_ARG, "thread-count emulation needs non-final batches of a multiple of 32768 records");
+    if (n == 0) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        return FQ_OK;
+    }
+    // second look at the framing scalars: max length, CR accounting, |seq| != |qual|
+    CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    {
+        BatchInfo hi = *ctx->h_info;
+        for (int m = 0; m < n_mates; ++m)
+            if (hi.n_cr[m] != hi.n_cr_eol[m]) hi.err |= kErrLoneCR;
+        st = map_device_error(ctx, hi);
+        if (st != FQ_OK) return st;
+    }
+    const uint32_t max_len = std::max(ctx->h_info->max_len[0], ctx->h_info->max_len[1]);
+    if (max_len > kResLenMask) return fail(ctx, FQ_ERR_ARG, "read longer than 16 Mi bases");
+    st = ensure_stats_rows(ctx, max_len);
+    if (st != FQ_OK) return st;
+    unsigned long long *S = ctx->d_stats.as<unsigned long long>();
+
+    if (paired && ctx->check_pair_ids) {
+        k_check_pair_ids<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_r1, ctx->d_rec[0].as<Rec>(), d_r2, ctx->d_rec[1].as<Rec>(), n, info);
+        ctx->launches++;
+    }
+    for (int m = 0; m < n_mates; ++m) {
+        CK(ctx->d_res[m].ensure((size_t)n * sizeof(uint2)));
+        if (ctx->debug_results) CK(ctx->d_dbg[m].ensure((size_t)n * sizeof(fq_read_result)));
+    }
+
+    // ---- adapter pass
+    if (o.filter_adapter) {
+        AdapterArgs aa{};
+        for (int m = 0; m < n_mates; ++m) {
+            CK(ctx->d_adp[m].ensure((size_t)n * sizeof(uint2)));
+            CK(ctx->d_adp_best[m].ensure((size_t)n * sizeof(int32_t)));
+            aa.raw[m] = m ? d_r2 : d_r1;
+            aa.rec[m] = ctx->d_rec[m].as<Rec>();
+            aa.adp[m] = ctx->d_adp[m].as<uint2>();
+            aa.adp_best[m] = ctx->d_adp_best[m].as<int32_t>();
+        }
+        aa.n_rec = n;
+        aa.n_mates = n_mates;
+        aa.max_len = max_len;
+        aa.stats = S;
+        aa.L = ctx->L;
+        aa.info = info;
+        aa.first_index = first_record_index;
+        aa.end_index = is_final ? first_record_index + n : ~0ull;
+        const size_t fixed = (size_t)(ctx->aset.n + 1) * 4 + ((ctx->aset.total + 3) & ~3u);
+        const size_t per_warp = ((max_len + 3) & ~3u) + 4 * (size_t)((max_len + 31) >> 5);
+        int warps = 8;
+        while (warps > 1 && fixed + warps * per_warp > ctx->smem_optin) warps >>= 1;
+        const size_t smem = fixed + warps * per_warp;
+        if (smem > ctx->smem_optin) return fail(ctx, FQ_ERR_ARG, "adapter set + read length exceed shared memory");
+        CK(cudaFuncSetAttribute(k_adapter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = std::max(1, std::min<int>((n * n_mates + warps - 1) / warps, ctx->sm_count * 8));
+        k_adapter<<<grid, warps * 32, smem, ctx->stream>>>(aa, o, ctx->aset);
+        ctx->launches++;
+    }
+
+    // ---- trim / filter / statistics
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    {
+        TrimArgs ta{};
+        for (int m = 0; m < n_mates; ++m) {
+            ta.raw[m] = m ? d_r2 : d_r1;
+            ta.rec[m] = ctx->d_rec[m].as<Rec>();
+            ta.adp[m] = o.filter_adapter ? ctx->d_adp[m].as<uint2>() : nullptr;
+            ta.adp_best[m] = o.filter_adapter ? ctx->d_adp_best[m].as<int32_t>() : nullptr;
+            ta.res[m] = ctx->d_res[m].as<uint2>();
+            ta.dbg[m] = ctx->debug_results ? ctx->d_dbg[m].as<fq_read_result>() : nullptr;
+        }
+        ta.n_rec = n;
+        ta.n_mates = n_mates;
+        ta.stats = S;
+        ta.L = ctx->L;
+        ta.rows = ctx->d_rows.as<StatsRows>();
+        ta.info = info;
+        const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+        uint32_t rows = round_up(std::max(max_len, 1u), 32);
+        auto words = [](uint32_t r) { return (size_t)r * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)r + 1) + 4 * kQualCols + 32; };
+        while (rows > 32 && words(rows) * 4 > budget) rows -= 32;
+        rows = std::min(rows, ctx->L.rows);
+        ta.smem_rows = rows;
+        const size_t smem = words(rows) * 4;
+        CK(cudaFuncSetAttribute(k_trim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int threads = 512;
+        const int grid = std::max(1, std::min<int>((n * n_mates + 15) / 16, ctx->sm_count));
+        k_trim<<<grid, threads, smem, ctx->stream>>>(ta, o);
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    // ---- route / scan / emit
+    EmitArgs ea{};
+    ea.n_rec = n;
+    ea.n_tiles = (n + kTile - 1) / kTile;
+    CK(ctx->d_tile.ensure((size_t)ea.n_tiles * 4 * 4));
+    ea.tile_sum = ctx->d_tile.as<uint32_t>();
+    ea.info = info;
+    ea.stats = S;
+    ea.filter_off = ctx->L.filter;
+    for (int m = 0; m < n_mates; ++m) {
+        ea.raw[m] = m ? d_r2 : d_r1;
+        ea.rec[m] = ctx->d_rec[m].as<Rec>();
+        ea.res[m] = ctx->d_res[m].as<uint2>();
+    }
+    if (!o.qc_only) {
+        // a trimmed record is never longer than its raw record, so the inputs bound the outputs
+        const size_t cap[4] = {paired ? n1 : 0, paired ? n2 : 0, paired ? std::max(n1, n2) : n1, o.discard ? n1 + n2 : 0};
+        for (int s = 0; s < 4; ++s) {
+            if (cap[s]) CK(ctx->d_out[s].ensure(cap[s] + 16));
+            ea.out[s] = ctx->d_out[s].as<uint8_t>();
+        }
+    }
+    k_route<<<ea.n_tiles, kTile, 0, ctx->stream>>>(ea, o);
+    k_scan_tiles<<<1, 128, 0, ctx->stream>>>(ea.tile_sum, ea.n_tiles, info);
+    ctx->launches += 2;
+    if (!o.qc_only) {
+        k_emit<<<ea.n_tiles, kTile, 0, ctx->stream>>>(ea, o);
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    cudaEventElapsedTime(&ctx->t_all, ctx->ev[0], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->t_trim, ctx->ev[1], ctx->ev[2]);
+    const BatchInfo hi = *ctx->h_info;
+    st = map_device_error(ctx, hi);
+    if (st != FQ_OK) return st;
+    out->n_valid[0] = hi.n_valid[0];
+    out->n_valid[1] = hi.n_valid[1];
+    out->paired_read_number = hi.paired_reads;
+    out->paired_base_length = hi.paired_bases;
+    for (int s = 0; s < 4; ++s) {
+        out->bytes[s] = o.qc_only ? 0 : hi.out_bytes[s];
+        ctx->last_dev_out[s] = out->bytes[s] ? ctx->d_out[s].p : nullptr;
+    }
+    if (copy_out) {
+        for (int s = 0; s < 4; ++s) {
+            if (!out->bytes[s]) continue;
+            CK(ctx->h_out[s].ensure(out->bytes[s]));
+            CK(cudaMemcpyAsync(ctx->h_out[s].p, ctx->d_out[s].p, out->bytes[s], cudaMemcpyDeviceToHost, ctx->stream));
+            out->data[s] = static_cast<const uint8_t *>(ctx->h_out[s].p);
+        }
+    }
+    if (ctx->debug_results) {
+        for (int m = 0; m < n_mates; ++m) {
+            CK(ctx->h_dbg[m].ensure((size_t)n * sizeof(fq_read_result)));
+            CK(cudaMemcpyAsync(ctx->h_dbg[m].p, ctx->d_dbg[m].p, (size_t)n * sizeof(fq_read_result), cudaMemcpyDeviceToHost, ctx->stream));
+            out->results[m] = static_cast<const fq_read_result *>(ctx->h_dbg[m].p);
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fq_abi_version(void) { return FQ_ABI_VERSION; }
+
+const char *fq_build_info(void) { return "faqcs_b200 " __DATE__ " sm_100a (nvcc " FQ_STR(__CUDACC_VER_MAJOR__) "." FQ_STR(__CUDACC_VER_MINOR__) ")"; }
+
+fq_status fq_create(const fq_options *opt, int device, fq_ctx **out)
+{
+    fq_ctx *ctx = nullptr;
+    if (!opt || !out) return fail(nullptr, FQ_ERR_ARG, "fq_create: null argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(nullptr, FQ_ERR_NO_DEVICE, "no CUDA device: faqcs_b200 has no CPU fallback");
+    if (device < 0 || device >= n_dev) return fail(nullptr, FQ_ERR_ARG, "fq_create: bad device index");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, FQ_ERR_CUDA, "cudaSetDevice failed");
+    ctx = new fq_ctx();
+    ctx->device = device;
+    ctx->opt = *opt;
+    for (uint32_t i = 0; i < opt->n_adapters; ++i) {
+        ctx->adapter_names.push_back(opt->adapters[i].name ? opt->adapters[i].name : "");
+        ctx->adapter_seqs.push_back(opt->adapters[i].seq ? opt->adapters[i].seq : "");
+    }
+    ctx->opt.adapters = nullptr;
+    cudaDeviceProp prop{};
+    fq_status st = FQ_OK;
+    auto boot = [&]() -> fq_status {
+        CK(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->smem_optin = prop.sharedMemPerBlockOptin;
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
+        CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_info), sizeof(BatchInfo)));
+        CK(ctx->d_info.ensure(sizeof(BatchInfo)));
+        CK(ctx->d_rows.ensure(sizeof(StatsRows)));
+        CK(cudaMemset(ctx->d_rows.p, 0, sizeof(StatsRows)));
+        fq_status s2 = upload_adapters(ctx);
+        if (s2 != FQ_OK) return s2;
+        return ensure_stats_rows(ctx, 320);
+    };
+    st = boot();
+    if (st != FQ_OK) {
+        g_create_error = ctx->error;
+        fq_destroy(ctx);
+        return st;
+    }
+    refresh_dev_opts(ctx);
+    *out = ctx;
+    return FQ_OK;
+}
+
+void fq_destroy(fq_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int m = 0; m < 2; ++m) {
+        ctx->d_raw[m].release(); ctx->d_chunk[m].release(); ctx->d_nl[m].release(); ctx->d_rec[m].release();
+        ctx->d_adp[m].release(); ctx->d_adp_best[m].release(); ctx->d_res[m].release(); ctx->d_dbg[m].release();
+        ctx->h_dbg[m].release();
+    }
+    for (int s = 0; s < 4; ++s) { ctx->d_out[s].release(); ctx->h_out[s].release(); }
+    ctx->d_tile.release(); ctx->d_info.release(); ctx->d_stats.release(); ctx->d_rows.release();
+    ctx->d_adp_codes.release(); ctx->d_adp_off.release(); ctx->d_adp_or.release();
+    ctx->h_stats.release();
+    if (ctx->h_info) cudaFreeHost(ctx->h_info);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *fq_last_error(const fq_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+fq_status fq_set_debug_results(fq_ctx *ctx, int enable)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    ctx->debug_results = enable != 0;
+    return FQ_OK;
+}
+
+fq_status fq_set_check_pair_ids(fq_ctx *ctx, int enable)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    ctx->check_pair_ids = enable != 0;
+    return FQ_OK;
+}
+
+void *fq_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void fq_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+fq_status fq_autodetect(fq_ctx *ctx, const uint8_t *r1, size_t n1, const uint8_t *r2, size_t n2,
+                        int32_t *input_quality_offset, int32_t *quality)
+{
+    if (!ctx || (!r1 && n1) || (!r2 && n2)) return FQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const bool paired = r2 != nullptr;
+    if (ctx->opt.input_quality_offset == FQ_OFFSET_AUTO) {
+        int detected[2] = {0, 0};
+        for (int m = 0; m < (paired ? 2 : 1); ++m) {
+            const uint8_t *h = m ? r2 : r1;
+            const size_t n = m ? n2 : n1;
+            BatchInfo init{};
+            init.err_record = 0xffffffffu;
+            init.detect_key = ~0ull;
+            *ctx->h_info = init;
+            CK(cudaMemcpyAsync(ctx->d_info.p, ctx->h_info, sizeof(BatchInfo), cudaMemcpyHostToDevice, ctx->stream));
+            uint32_t n_rec = 0;
+            if (n) {
+                CK(ctx->d_raw[m].ensure(n + 16));
+                CK(cudaMemcpyAsync(ctx->d_raw[m].p, h, n, cudaMemcpyHostToDevice, ctx->stream));
+                fq_status st = frame_mate(ctx, m, ctx->d_raw[m].as<uint8_t>(), n, &n_rec);
+                if (st != FQ_OK) return st;
+            }
+            const uint32_t look = std::min<uint32_t>(n_rec, FQ_REF_BATCH);
+            if (look) {
+                k_detect_offset<<<(look * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_raw[m].as<uint8_t>(), ctx->d_rec[m].as<Rec>(), look,
+                                                                                 ctx->d_info.as<BatchInfo>());
+                ctx->launches++;
+            }
+            CK(cudaMemcpyAsync(ctx->h_info, ctx->d_info.p, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            fq_status st = map_device_error(ctx, *ctx->h_info);
+            if (st != FQ_OK) return st;
+            if (ctx->h_info->detect_key == ~0ull)
+                return fail(ctx, FQ_ERR_OFFSET, "trim.cpp:auto_detect_quality_offset: Unknown quality format!");
+            detected[m] = (int)(ctx->h_info->detect_key & 0xff);
+        }
+        if (paired && detected[0] != detected[1])
+            return fail(ctx, FQ_ERR_OFFSET, "FaQCs.cpp:process_paired: I/O Error (inconsistent quality offset detection between reads one and two)");
+        ctx->opt.input_quality_offset = detected[0];
+    }
+    // auto_detect_next_seq (trim.cpp:619-626): header of the first read starts with "@NS"
+    if (ctx->opt.quality < 20 && n1 >= 3 && r1[0] == '@' && r1[1] == 'N' && r1[2] == 'S') {
+        bool first_line = true;     // "@NS" must sit inside the first header line
+        for (int i = 0; i < 3; ++i) first_line &= (r1[i] != '\n' && r1[i] != '\r');
+        if (first_line) ctx->opt.quality = 20;
+    }
+    refresh_dev_opts(ctx);
+    if (input_quality_offset) *input_quality_offset = ctx->opt.input_quality_offset;
+    if (quality) *quality = ctx->opt.quality;
+    return FQ_OK;
+}
+
+fq_status fq_process_host(fq_ctx *ctx, const uint8_t *r1, size_t n1, const uint8_t *r2, size_t n2,
+                          uint64_t first_record_index, int is_final, fq_batch_out *out)
+{
+    if (!ctx || !out || (!r1 && n1) || (!r2 && n2)) return FQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const bool paired = r2 != nullptr;
+    CK(ctx->d_raw[0].ensure(n1 + 16));
+    if (n1) CK(cudaMemcpyAsync(ctx->d_raw[0].p, r1, n1, cudaMemcpyHostToDevice, ctx->stream));
+    if (paired) {
+        CK(ctx->d_raw[1].ensure(n2 + 16));
+        if (n2) CK(cudaMemcpyAsync(ctx->d_raw[1].p, r2, n2, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return process_common(ctx, ctx->d_raw[0].as<uint8_t>(), n1, paired ? ctx->d_raw[1].as<uint8_t>() : nullptr, n2, paired,
+                          first_record_index, is_final, 1, out);
+}
+
+fq_status fq_process_device(fq_ctx *ctx, const void *d_r1, size_t n1, const void *d_r2, size_t n2,
+                            uint64_t first_record_index, int is_final, int copy_out, fq_batch_out *out)
+{
+    if (!ctx || !out || (!d_r1 && n1) || (!d_r2 && n2)) return FQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return process_common(ctx, static_cast<const uint8_t *>(d_r1), n1, static_cast<const uint8_t *>(d_r2), n2, d_r2 != nullptr,
+                          first_record_index, is_final, copy_out, out);
+}
+
+fq_status fq_device_outputs(fq_ctx *ctx, const void *d_out[FQ_NUM_STREAM])
+{
+    if (!ctx || !d_out) return FQ_ERR_ARG;
+    for (int s = 0; s < 4; ++s) d_out[s] = ctx->last_dev_out[s];
+    return FQ_OK;
+}
+
+fq_status fq_last_timing(fq_ctx *ctx, float *all_kernels_ms, float *trim_kernel_ms)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    if (all_kernels_ms) *all_kernels_ms = ctx->t_all;
+    if (trim_kernel_ms) *trim_kernel_ms = ctx->t_trim;
+    return FQ_OK;
+}
+
+uint64_t fq_launch_count(const fq_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void *fq_stream(fq_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+fq_status fq_stats_reserve_rows(fq_ctx *ctx, uint32_t rows)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return ensure_stats_rows(ctx, rows);
+}
+
+fq_status fq_stats_device_buffer(fq_ctx *ctx, void **d_u64, size_t *n_u64, void **d_rows_u32x4)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (d_u64) *d_u64 = ctx->d_stats.p;
+    if (n_u64) *n_u64 = ctx->L.total;
+    if (d_rows_u32x4) *d_rows_u32x4 = ctx->d_rows.p;
+    return FQ_OK;
+}
+
+fq_status fq_reset_stats(fq_ctx *ctx)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemset(ctx->d_stats.p, 0, ctx->L.total * 8));
+    CK(cudaMemset(ctx->d_rows.p, 0, sizeof(StatsRows)));
+    return FQ_OK;
+}
+
+fq_status fq_stats(fq_ctx *ctx, fq_stats_view *v)
+{
+    if (!ctx || !v) return FQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const StatsLayout &L = ctx->L;
+    CK(ctx->h_stats.ensure(L.total * 8 + sizeof(StatsRows)));
+    uint64_t *S = static_cast<uint64_t *>(ctx->h_stats.p);
+    StatsRows rows{};
+    CK(cudaMemcpy(S, ctx->d_stats.p, L.total * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&rows, ctx->d_rows.p, sizeof(StatsRows), cudaMemcpyDeviceToHost));
+    memset(v, 0, sizeof(*v));
+    for (int i = 0; i < FQ_NUM_STAT; ++i) v->filter_stats[i] = S[L.filter + i];
+    const uint32_t na = L.n_adapters;
+    ctx->v_adapter_reads.assign(S + L.adapter_reads, S + L.adapter_reads + na);
+    ctx->v_adapter_bases.assign(S + L.adapter_bases, S + L.adapter_bases + na);
+    // main(): phiX pseudo-adapters -> READ_PHIX/BASE_PHIX, the rest -> READ_ADAPTER/BASE_ADAPTER (FaQCs.cpp:92-127)
+    for (uint32_t j = 0; j < na; ++j) {
+        const bool phix = ctx->adapter_names[j] == kPhiX || ctx->adapter_names[j] == kPhiXComplement;
+        v->filter_stats[phix ? FQ_READ_PHIX : FQ_READ_ADAPTER] += ctx->v_adapter_reads[j];
+        v->filter_stats[phix ? FQ_BASE_PHIX : FQ_BASE_ADAPTER] += ctx->v_adapter_bases[j];
+    }
+    v->n_adapters = na;
+    v->adapter_reads = ctx->v_adapter_reads.data();
+    v->adapter_bases = ctx->v_adapter_bases.data();
+    const uint32_t pr = std::min(rows.pre_rows, L.rows), qr = std::min(rows.post_rows, L.rows);
+    v->pre_rows = pr;
+    v->post_rows = qr;
+    ctx->v_pre_q.assign((size_t)pr * kQualCols, 0);
+    ctx->v_post_q.assign((size_t)qr * kQualCols, 0);
+    ctx->v_pre_b.assign((size_t)pr * kBaseCols, 0);
+    ctx->v_post_b.assign((size_t)qr * kBaseCols, 0);
+    for (uint32_t p = 0; p < pr; ++p) {
+        for (int c = 0; c < kQualCols; ++c) ctx->v_pre_q[(size_t)p * kQualCols + c] = S[L.pre_q + (size_t)c * L.rows + p];
+        for (int c = 0; c < kBaseCols; ++c) ctx->v_pre_b[(size_t)p * kBaseCols + c] = S[L.pre_b + (size_t)c * L.rows + p];
+    }
+    for (uint32_t p = 0; p < qr; ++p) {          // post = pre - removed (+ G->N into column N)
+        for (int c = 0; c < kQualCols; ++c)
+            ctx->v_post_q[(size_t)p * kQualCols + c] = S[L.pre_q + (size_t)c * L.rows + p] - S[L.rem_q + (size_t)c * L.rows + p];
+        for (int c = 0; c < kBaseCols; ++c)
+            ctx->v_post_b[(size_t)p * kBaseCols + c] = S[L.pre_b + (size_t)c * L.rows + p] - S[L.rem_b + (size_t)c * L.rows + p] +
+                                                       (c == 4 ? S[L.g2n + p] : 0);
+    }
+    v->pre_quality_matrix = ctx->v_pre_q.data();
+    v->post_quality_matrix = ctx->v_post_q.data();
+    v->pre_base_matrix = ctx->v_pre_b.data();
+    v->post_base_matrix = ctx->v_post_b.data();
+    const size_t hist_off[4] = {L.pre_rq, L.pre_bq, L.post_rq, L.post_bq};
+    for (int h = 0; h < 4; ++h) ctx->v_hist[h].assign(S + hist_off[h], S + hist_off[h] + kQualCols);
+    v->pre_read_quality_hist = ctx->v_hist[0].data();
+    v->pre_base_quality_hist = ctx->v_hist[1].data();
+    v->post_read_quality_hist = ctx->v_hist[2].data();
+    v->post_base_quality_hist = ctx->v_hist[3].data();
+    ctx->v_pre_comp.assign(S + L.pre_comp, S + L.pre_comp + 6 * (size_t)kCompBins);
+    ctx->v_post_comp.assign(S + L.post_comp, S + L.post_comp + 6 * (size_t)kCompBins);
+    v->pre_composition = ctx->v_pre_comp.data();
+    v->post_composition = ctx->v_post_comp.data();
+    v->pre_len_size = std::min(rows.pre_len_size, L.rows + 1);
+    v->post_len_size = std::min(rows.post_len_size, L.rows + 1);
+    ctx->v_pre_len.assign(S + L.pre_len, S + L.pre_len + v->pre_len_size);
+    ctx->v_post_len.assign(S + L.post_len, S + L.post_len + v->post_len_size);
+    v->pre_length_hist = ctx->v_pre_len.data();
+    v->post_length_hist = ctx->v_post_len.data();
+    return FQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+// fq_emit.cuh -- pair routing and in-order stream compaction
+// (FaQCs.cpp:296-361,431-496 paired; :634-659,696-720 unpaired; write_read, fastq.cpp:127-138).
+//
+// Three steps: k_route sums the emitted bytes of each 256-record tile for the
+// four streams, k_scan_tiles turns the tile sums into tile bases, k_emit
+// recomputes the per-record sizes, scans them inside the tile and has one warp
+// per record copy `def\nseq\n+\nqual\n` to its final position, applying the
+// mutations trim_read leaves in the read (terminal-N quality mask, G->N
+// replacement, quality re-encoding).  Discarded reads are copied raw.
+#pragma once
+#include "fq_common.cuh"
+#include "fq_trim.cuh"
+
+namespace fq {
+
+constexpr uint32_t kTile = 256;     // records per route/emit tile
+
+struct EmitArgs {
+    const uint8_t *raw[2];
+    const Rec *rec[2];
+    const uint2 *res[2];
+    uint32_t n_rec;
+    uint32_t n_tiles;
+    uint32_t *tile_sum;          // [4][n_tiles] -> exclusive bases after k_scan_tiles (u32: < 4 GiB per stream per batch)
+    uint8_t *out[4];
+    BatchInfo *info;
+    unsigned long long *stats;   // global stats block (PAIRED_* counters are added here too)
+    size_t filter_off;
+};
+
+__device__ __forceinline__ uint32_t header_len(const uint8_t *raw, const Rec &rc)
+{
+    uint32_t n = rc.seq - rc.hdr - 1;
+    if (n && raw[rc.hdr + n - 1] == '\r') --n;
+    return n;
+}
+
+// Sizes of what record r contributes to each stream.
+__device__ __forceinline__ void route_sizes(const EmitArgs &a, const DevOpts &o, uint32_t r, uint32_t sz[4], bool valid[2],
+                                            uint32_t wl[2])
+{
+    sz[0] = sz[1] = sz[2] = sz[3] = 0;
+    valid[0] = valid[1] = false;
+    wl[0] = wl[1] = 0;
+    if (r >= a.n_rec) return;
+    uint32_t trimmed[2] = {0, 0}, rawsz[2] = {0, 0};
+    const int n_mates = o.paired ? 2 : 1;
+    for (int m = 0; m < n_mates; ++m) {
+        const Rec rc = a.rec[m][r];
+        const uint2 v = a.res[m][r];
+        const uint32_t hl = header_len(a.raw[m], rc);
+        wl[m] = v.y & kResLenMask;
+        valid[m] = ((v.y >> kResLenBits) & FQ_RR_VALID) != 0;
+        trimmed[m] = hl + 2 * wl[m] + 5;
+        rawsz[m] = hl + 2 * rc.len + 5;
+    }
+    if (o.qc_only) return;
+    if (o.paired) {
+        if (valid[0] && valid[1]) { sz[0] = trimmed[0]; sz[1] = trimmed[1]; }
+        else {
+            if (valid[0]) sz[2] = trimmed[0];
+            else if (valid[1]) sz[2] = trimmed[1];
+            if (o.discard) sz[3] = (valid[0] ? 0 : rawsz[0]) + (valid[1] ? 0 : rawsz[1]);
+        }
+    } else {
+        if (valid[0]) sz[2] = trimmed[0];
+        else if (o.discard) sz[3] = rawsz[0];
+    }
+}
+
+__global__ void __launch_bounds__(kTile) k_route(const EmitArgs a, const DevOpts o)
+{
+    __shared__ uint32_t s_sum[8][8];
+    const uint32_t r = blockIdx.x * kTile + threadIdx.x;
+    uint32_t sz[4], wl[2];
+    bool valid[2];
+    route_sizes(a, o, r, sz, valid, wl);
+    uint32_t v[8];
+    v[0] = sz[0]; v[1] = sz[1]; v[2] = sz[2]; v[3] = sz[3];
+    v[4] = valid[0]; v[5] = valid[1];
+    const bool both = o.paired && valid[0] && valid[1];
+    v[6] = both ? 2u : 0u;                       // PAIRED_READ_NUMBER (FaQCs.cpp:304-308)
+    v[7] = both ? wl[0] + wl[1] : 0u;            // PAIRED_BASE_LENGTH
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = warp_sum(v[k]);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_sum[wid][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        uint32_t t = 0;
+        for (int w = 0; w < (int)(kTile / 32); ++w) t += s_sum[w][threadIdx.x];
+        if (threadIdx.x < 4) a.tile_sum[threadIdx.x * a.n_tiles + blockIdx.x] = t;
+        else if (t) {
+            unsigned long long *dst = threadIdx.x == 4 ? &a.info->n_valid[0] : threadIdx.x == 5 ? &a.info->n_valid[1]
+                                    : threadIdx.x == 6 ? &a.info->paired_reads : &a.info->paired_bases;
+            atomicAdd(dst, (unsigned long long)t);
+            if (threadIdx.x == 6) atomicAdd(&a.stats[a.filter_off + FQ_PAIRED_READ_NUMBER], (unsigned long long)t);
+            if (threadIdx.x == 7) atomicAdd(&a.stats[a.filter_off + FQ_PAIRED_BASE_LENGTH], (unsigned long long)t);
+        }
+    }
+}
+
+// Exclusive scan of the four tile-sum rows; totals go to info->out_bytes.  One CTA, warp w scans stream w.
+__global__ void __launch_bounds__(128) k_scan_tiles(uint32_t *tile_sum, uint32_t n_tiles, BatchInfo *info)
+{
+    const uint32_t lane = threadIdx.x & 31, s = threadIdx.x >> 5;
+    uint32_t *row = tile_sum + (size_t)s * n_tiles;
+    unsigned long long carry = 0;
+    for (uint32_t base = 0; base < n_tiles; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = i < n_tiles ? row[i] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, k);
+            if (lane >= (uint32_t)k) x += y;
+        }
+        if (i < n_tiles) row[i] = (uint32_t)(carry + x - v);
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) info->out_bytes[s] = carry;
+}
+
+// Copy one trimmed record.  All 32 lanes cooperate, byte-striped.
+__device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, const Rec &rc, uint32_t lo, uint32_t wl,
+                                              const DevOpts &o, uint32_t lane)
+{
+    const uint32_t hl = header_len(raw, rc);
+    const uint8_t *hp = raw + rc.hdr;
+    const uint8_t *sp = raw + rc.seq;
+    const signed char *qp = reinterpret_cast<const signed char *>(raw + rc.qual);
+    // terminal-N mask bounds (only matter when an end of the read is 'N')
+    uint32_t lead = 0, trail = rc.len;
+    if (rc.len && (sp[0] == 'N' || sp[rc.len - 1] == 'N')) {
+        while (lead < rc.len && sp[lead] == 'N') ++lead;
+        while (trail > 0 && sp[trail - 1] == 'N') --trail;
+    }
+    const uint32_t s0 = hl + 1, s1 = s0 + wl, q0 = s1 + 3, q1 = q0 + wl, total = q1 + 1;
+    for (uint32_t i = lane; i < total; i += 32) {
+        uint32_t ch;
+        if (i < hl) ch = hp[i];
+        else if (i < s0) ch = '\n';
+        else if (i < s1) {
+            const uint32_t p = lo + (i - s0);
+            ch = sp[p];
+            if (o.replace_q > 0 && ch == 'G') {
+                int qc = (p < lead || p >= trail) ? o.in_off : (int)qp[p];
+                if (max(0, qc - o.in_off) < (int)o.replace_q) ch = 'N';
+            }
+        } else if (i < q0) ch = (i == s1 + 1) ? '+' : '\n';
+        else if (i < q1) {
+            const uint32_t p = lo + (i - q0);
+            int qc = (p < lead || p >= trail) ? o.in_off : (int)qp[p];
+            if (o.in_off != o.out_off) qc = max(0, qc - o.in_off) + o.out_off;      // trim.cpp:516-525
+            ch = (uint32_t)qc & 0xffu;
+        } else ch = '\n';
+        dst[i] = (uint8_t)ch;
+    }
+}
+
+// Copy one raw (discarded) record: def \n seq \n + \n qual \n with the original, unmasked bytes.
+__device__ __forceinline__ void write_raw(uint8_t *dst, const uint8_t *raw, const Rec &rc, uint32_t lane)
+{
+    const uint32_t hl = header_len(raw, rc);
+    const uint32_t s0 = hl + 1, s1 = s0 + rc.len, q0 = s1 + 3, q1 = q0 + rc.len, total = q1 + 1;
+    for (uint32_t i = lane; i < total; i += 32) {
+        uint32_t ch;
+        if (i < hl) ch = raw[rc.hdr + i];
+        else if (i < s0) ch = '\n';
+        else if (i < s1) ch = raw[rc.seq + (i - s0)];
+        else if (i < q0) ch = (i == s1 + 1) ? '+' : '\n';
+        else if (i < q1) ch = raw[rc.qual + (i - q0)];
+        else ch = '\n';
+        dst[i] = (uint8_t)ch;
+    }
+}
+
+__global__ void __launch_bounds__(kTile) k_emit(const EmitArgs a, const DevOpts o)
+{
+    __shared__ uint32_t s_off[4][kTile];
+    __shared__ uint32_t s_wsum[4][kTile / 32];
+    __shared__ uint8_t s_valid[kTile];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * kTile + threadIdx.x;
+    uint32_t sz[4], wl[2];
+    bool valid[2];
+    route_sizes(a, o, r, sz, valid, wl);
+    uint32_t inc[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        uint32_t x = sz[s];
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, k);
+            if (lane >= (uint32_t)k) x += y;
+        }
+        inc[s] = x;
+        if (lane == 31) s_wsum[s][wid] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        uint32_t before = a.tile_sum[(size_t)s * a.n_tiles + blockIdx.x];
+        for (uint32_t w = 0; w < wid; ++w) before += s_wsum[s][w];
+        s_off[s][threadIdx.x] = before + inc[s] - sz[s];
+    }
+    s_valid[threadIdx.x] = (uint8_t)((valid[0] ? 1 : 0) | (valid[1] ? 2 : 0));
+    __syncthreads();
+    if (o.qc_only) return;
+
+    // warp w copies records w*32 .. w*32+31 of the tile, one after the other
+    for (uint32_t k = 0; k < 32; ++k) {
+        const uint32_t t = wid * 32 + k;
+        const uint32_t rr = blockIdx.x * kTile + t;
+        if (rr >= a.n_rec) break;
+        const uint32_t vm = s_valid[t];
+        const bool v0 = vm & 1, v1 = (vm & 2) != 0;
+        if (o.paired) {
+            const Rec r0 = a.rec[0][rr], r1 = a.rec[1][rr];
+            const uint2 e0 = a.res[0][rr], e1 = a.res[1][rr];
+            if (v0 && v1) {
+                write_trimmed(a.out[0] + s_off[0][t], a.raw[0], r0, e0.x, e0.y & kResLenMask, o, lane);
+                write_trimmed(a.out[1] + s_off[1][t], a.raw[1], r1, e1.x, e1.y & kResLenMask, o, lane);
+            } else {
+                if (v0) write_trimmed(a.out[2] + s_off[2][t], a.raw[0], r0, e0.x, e0.y & kResLenMask, o, lane);
+                else if (v1) write_trimmed(a.out[2] + s_off[2][t], a.raw[1], r1, e1.x, e1.y & kResLenMask, o, lane);
+                if (o.discard) {
+                    uint32_t off = s_off[3][t];
+                    if (!v0) { write_raw(a.out[3] + off, a.raw[0], r0, lane); off += header_len(a.raw[0], r0) + 2 * r0.len + 5; }
+                    if (!v1) write_raw(a.out[3] + off, a.raw[1], r1, lane);
+                }
+            }
+        } else {
+            const Rec r0 = a.rec[0][rr];
+            const uint2 e0 = a.res[0][rr];
+            if (v0) write_trimmed(a.out[2] + s_off[2][t], a.raw[0], r0, e0.x, e0.y & kResLenMask, o, lane);
+            else if (o.discard) write_raw(a.out[3] + s_off[3][t], a.raw[0], r0, lane);
+        }
+    }
+}
+
+}  // namespace fq

@@ -199,6 +199,13 @@ const char *fq_last_error(const fq_ctx *ctx);   /* ctx may be NULL: last create 
 
 /* Ask for per-read verdicts in fq_batch_out.results (off by default). */
 fq_status fq_set_debug_results(fq_ctx *ctx, int enable);
+/* parse_id(r1.def) == parse_id(r2.def) check of FaQCs.cpp:383-389 (on by default). */
+fq_status fq_set_check_pair_ids(fq_ctx *ctx, int enable);
+
+/* Pinned host memory for the buffers handed to fq_process_host (pageable memory
+ * works too, but the copies then cannot overlap and run at a fraction of PCIe speed). */
+void *fq_host_alloc(size_t bytes);
+void  fq_host_free(void *p);
 
 /* Quality-offset auto-detection on the first batch (auto_detect_quality_offset,
  * trim.cpp:599-617, call sites FaQCs.cpp:261-270,393-402,609-611,669-671) and
@@ -247,16 +254,18 @@ void     *fq_stream(fq_ctx *ctx);
  * loop (FaQCs.cpp:92-133). */
 fq_status fq_stats(fq_ctx *ctx, fq_stats_view *view);
 
-/* Flattened u64 view of the same statistics in DEVICE memory, with fixed
- * capacity rows so that the layout is identical on every rank: this is the
- * buffer a multi-GPU run all-reduces (sum) with NCCL.  `max_rows_out` (rows
- * actually used) must be all-reduced with MAX.  After the all-reduce call
- * fq_stats_commit to make fq_stats return the reduced values. */
+/* Multi-GPU merge (the reference's `omp critical` merge, trim.cpp:120-154, across
+ * devices): the accumulators live in one flat u64 block in DEVICE memory whose
+ * layout depends only on (row capacity, n_adapters).  Every rank first calls
+ * fq_stats_reserve_rows with the same capacity (>= the longest read of any
+ * rank), then all-reduces the block with SUM and the 4 x u32 row counters with
+ * MAX (ncclAllReduce over NVLink; the only collective of the path).  fq_stats
+ * afterwards returns the merged statistics on every rank. */
+fq_status fq_stats_reserve_rows(fq_ctx *ctx, uint32_t rows);
 fq_status fq_stats_device_buffer(fq_ctx *ctx, void **d_u64, size_t *n_u64,
                                  void **d_rows_u32x4);
-fq_status fq_stats_commit(fq_ctx *ctx);
 
-/* Add caller-side counters (PAIRED_* are folded in automatically). */
+/* Zero the accumulators (new run on the same context). */
 fq_status fq_reset_stats(fq_ctx *ctx);
 
 #ifdef __cplusplus

@@ -127,8 +127,8 @@ def assert_matches_reference(ref: Dict, streams: Sequence[bytes], stats: Stats, 
     if "pre_quality_matrix" in ref:
         for f in MATRIX_FIELDS:
             a, b = getattr(stats, f), ref[f]
-            if f.endswith("length_hist") and a.size == 1 and b.size <= 1:
-                continue
+            if f.endswith("length_hist") and a.size <= 1 and b.size <= 1:
+                continue          # the file format cannot tell an empty histogram from one with only bin 0
             assert a.shape == b.shape, f"{f}: shape {a.shape} != reference {b.shape}"
             if not np.array_equal(a, b):
                 idx = np.argwhere(a != b)[0]

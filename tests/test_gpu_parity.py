@@ -1,0 +1,200 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on seeded inputs:
+emitted FASTQ bytes, every statistic, per-read verdicts.  Bit-exact; the only floats
+(average quality) are compared bit for bit as well."""
+import numpy as np
+import pytest
+
+import refcli
+from faqcs_b200 import synth
+from faqcs_b200.api import (BUILTIN_ADAPTERS, MODE_BWA, MODE_HARD, OFFSET_AUTO, POLYA_ADAPTER, Engine, FaqcsError,
+                            Options)
+from faqcs_b200.synth import fastq_bytes
+from oracle_binding import OracleEngine
+from parity import assert_engines_equal, assert_matches_reference, run_engine
+
+pytestmark = pytest.mark.gpu
+AD = dict(BUILTIN_ADAPTERS)
+
+
+def both(r1, r2, opt_factory, batch_records=None, check_results=True):
+    with OracleEngine(opt_factory()) as ora, Engine(opt_factory()) as gpu:
+        ora.set_debug_results(True)
+        gpu.set_debug_results(True)
+        so, ro = run_engine(ora, r1, r2, batch_records)
+        sg, rg = run_engine(gpu, r1, r2, batch_records)
+        # avg_q of invalid reads is not defined on the GPU side (never computed)
+        for a, b in zip(ro, rg):
+            for m in range(2):
+                if a.results[m] is not None and b.results[m] is not None:
+                    inv = (a.results[m]["flags"] & 1) == 0
+                    a.results[m]["avg_q"][inv] = 0
+                    b.results[m]["avg_q"][inv] = 0
+        assert_engines_equal(sg, gpu.stats(), so, ora.stats(), rg if check_results else None, ro if check_results else None)
+        return sg, gpu.stats()
+
+
+def test_c2_defaults():
+    w = synth.c2(30000)
+    both(w.r1, w.r2, lambda: Options())
+
+
+def test_c2_multibatch_equals_single():
+    w = synth.c2(20000)
+    s1, st1 = both(w.r1, w.r2, lambda: Options(discard_output=True))
+    s2, st2 = both(w.r1, w.r2, lambda: Options(discard_output=True), batch_records=3000)
+    assert [bytes(x) for x in s1] == [bytes(x) for x in s2]
+    assert not st1.diff(st2)
+
+
+def test_c2_modes_and_clips():
+    w = synth.c2(8000)
+    both(w.r1, w.r2, lambda: Options(trim_5=7, trim_3=11, discard_output=True))
+    both(w.r1, w.r2, lambda: Options(mode=MODE_BWA, quality=15, discard_output=True))
+    both(w.r1, w.r2, lambda: Options(mode=MODE_HARD, quality=25, discard_output=True))
+    both(w.r1, w.r2, lambda: Options(quality=20, protect_5=True, average_quality=30.0))
+    both(w.r1, w.r2, lambda: Options(quality=20, min_read_length=100, max_num_poly_N=1, low_complexity_cutoff_ratio=0.4))
+
+
+def test_c4_qc_only():
+    w = synth.c4(40000)
+    both(w.r1, None, lambda: Options(qc_only=True))
+
+
+def test_c5_mixed_ascii64_hard():
+    w = synth.c5(30000)
+    both(w.r1, None, lambda: Options(mode=MODE_HARD, quality=20, average_quality=25.0, replace_to_N_q=10,
+                                     discard_output=True))
+
+
+def test_c3_adapters():
+    w = synth.c3(3000)
+    ads = BUILTIN_ADAPTERS + [POLYA_ADAPTER] + w.artifacts
+    both(w.r1, w.r2, lambda: Options(filter_adapter=True, adapters=list(ads)))
+    both(w.r1, w.r2, lambda: Options(filter_adapter=True, adapters=list(ads), qc_only=True))
+
+
+def test_short_reads_thread_emulation():
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(2000):
+        L = int(rng.integers(26, 120))
+        k = int(rng.integers(18, 30))
+        s = "".join(rng.choice(list("ACGT"), size=max(L - k, 1))) + AD["Nextera-primer-adapter-1"][:k]
+        recs.append((f"@q3_{i}", s, "I" * (len(s) - 1) + "5"))
+    r1 = np.frombuffer(fastq_bytes(recs), dtype=np.uint8)
+    for t in (1, 2, 4, 7):
+        both(r1, None, lambda: Options(filter_adapter=True, adapters=list(BUILTIN_ADAPTERS), min_read_length=1,
+                                       num_thread=t, input_quality_offset=33))
+
+
+def test_micro_cases_vs_oracle():
+    rng = np.random.default_rng(11)
+    rnd = lambda n, al="ACGT": "".join(rng.choice(list(al), size=n))
+    recs = [("@r0", "A" * 30 + "C" * 30, "#" * 60), ("@r1", "ACGT" * 15, "I" * 30 + "#" * 30),
+            ("@r2", "ACGT" * 15, "I" + "#" * 59), ("@n0", "NN" + rnd(70) + "TNN", "I" * 75),
+            ("@n1", "N" * 64, "I" * 64), ("@n2", "N" * 33 + "ACGT" * 10 + "N", "I" * 74),
+            ("@lc0", "A" * 86 + "CGTCGTCGTCGTCG", "I" * 100), ("@lc1", "AC" * 50, "I" * 100),
+            ("@lc2", "ac" * 50, "I" * 100), ("@lc3", "AC" * 20 + "N" + "AC" * 29 + "G", "I" * 100),
+            ("@nn", rnd(40) + "NN" + rnd(40), "I" * 82), ("@nnn", rnd(31) + "NNN" + rnd(40), "I" * 74),
+            ("@cross", rnd(30) + "NNNN" + rnd(40), "I" * 74), ("@one", "A", "I"), ("@two", "AC", "I#")]
+    for L in range(1, 40):
+        q = "".join(chr(33 + int(x)) for x in rng.choice([2, 2, 2, 8, 20, 30, 40], size=L))
+        recs.append((f"@s{L}", rnd(L, "ACGTN"), q))
+    r1 = np.frombuffer(fastq_bytes(recs), dtype=np.uint8)
+    for mode in (MODE_HARD, MODE_BWA, 2):
+        for protect in (False, True):
+            both(r1, None, lambda: Options(mode=mode, quality=10, min_read_length=1, protect_5=protect,
+                                           input_quality_offset=33, discard_output=True, max_num_poly_N=3))
+    both(r1, None, lambda: Options(input_quality_offset=33, discard_output=True, max_num_poly_N=4, min_read_length=30))
+
+
+def test_crlf_and_ragged_headers():
+    recs = [("@c0 x", "GGACGTACGTNA" * 6, "h" * 30 + "D" * 42), ("@c1", "NAAGGT" * 12, "hE" * 36),
+            ("@a_very_long_header_" + "z" * 150, "ACGT" * 20, "h" * 80), ("@", "ACGTTGCA" * 9, "g" * 72)]
+    r1 = np.frombuffer(fastq_bytes(recs, "\r\n"), dtype=np.uint8)
+    both(r1, None, lambda: Options(replace_to_N_q=10, min_read_length=10, discard_output=True))
+
+
+def test_pairs_routing_with_discard():
+    rng = np.random.default_rng(7)
+    rnd = lambda n, al="ACGT": "".join(rng.choice(list(al), size=n))
+    r1, r2 = [], []
+    for i in range(3000):
+        L = int(rng.integers(30, 130))
+        s1 = "NN" + rnd(L) + "TNN" if i % 3 == 0 else rnd(L, "ACGTN" if i % 5 == 0 else "ACGT")
+        s2 = rnd(L) if i % 4 else "A" * L
+        q1 = "".join(chr(int(x)) for x in rng.integers(35, 74, size=len(s1)))
+        q2 = "".join(chr(int(x)) for x in rng.integers(33, 74, size=len(s2)))
+        r1.append((f"@p{i}/1", s1, q1))
+        r2.append((f"@p{i}/2", s2, q2))
+    a = np.frombuffer(fastq_bytes(r1), dtype=np.uint8)
+    b = np.frombuffer(fastq_bytes(r2), dtype=np.uint8)
+    both(a, b, lambda: Options(discard_output=True, quality=12, input_quality_offset=33))
+    both(a, b, lambda: Options(discard_output=True, quality=12, input_quality_offset=33), batch_records=700)
+
+
+def test_long_reads_beyond_shared_rows():
+    rng = np.random.default_rng(12)
+    recs = []
+    for i in range(60):
+        L = int(rng.integers(500, 2500))
+        s = "".join(rng.choice(list("ACGTN"), p=[.24, .25, .25, .25, .01], size=L))
+        q = "".join(chr(33 + int(x)) for x in np.clip(rng.normal(25, 10, size=L), 0, 41).astype(int))
+        recs.append((f"@long{i}", s, q))
+    r1 = np.frombuffer(fastq_bytes(recs), dtype=np.uint8)
+    both(r1, None, lambda: Options(quality=15, max_num_poly_N=3, discard_output=True))
+
+
+def test_errors_match_reference_text():
+    ok = fastq_bytes([("@a", "ACGT" * 20, "I" * 79 + "#")])
+    with Engine(Options()) as e:                                     # Q > 41
+        bad = fastq_bytes([("@a", "ACGT" * 20, "K" * 79 + "#")])
+        e.autodetect(bad)
+        with pytest.raises(FaqcsError) as ei:
+            e.process(bad)
+        assert "greater than the maximum allowed quality score" in str(ei.value)
+    with Engine(Options()) as e:                                     # Q10: nothing decisive
+        with pytest.raises(FaqcsError) as ei:
+            e.autodetect(fastq_bytes([("@a", "ACGT" * 20, "I" * 80)]))
+        assert "Unknown quality format!" in str(ei.value)
+    with Engine(Options()) as e:                                     # |seq| != |qual|
+        with pytest.raises(FaqcsError) as ei:
+            e.autodetect(ok + b"@b\nACGT\n+\nII#\n")
+        assert "|Sequence| != |Quality|" in str(ei.value)
+    with Engine(Options(input_quality_offset=33)) as e:              # truncated record
+        with pytest.raises(FaqcsError) as ei:
+            e.process(ok + b"@b\nACGT\n")
+        assert "Unable to read '+'" in str(ei.value)
+    with Engine(Options(input_quality_offset=33)) as e:              # pair id mismatch
+        with pytest.raises(FaqcsError) as ei:
+            e.process(ok, fastq_bytes([("@zzz", "ACGT" * 20, "I" * 79 + "#")]))
+        assert "FaQCs.cpp:trim: I/O error" in str(ei.value)
+    with Engine(Options()) as e:                                     # NextSeq bumps -q to 20
+        off, q = e.autodetect(fastq_bytes([("@NS500:1", "ACGT" * 20, "I" * 79 + "#")]))
+        assert (off, q) == (33, 20)
+
+
+@pytest.mark.skipif(not refcli.have_ref(), reason="reference binary not present")
+def test_c2_against_reference_binary_directly():
+    w = synth.c2(20000)
+    opt = Options(discard_output=True)
+    ref = refcli.run_reference(w.r1, w.r2, flags=refcli.flags_for(opt), threads=4)
+    with Engine(opt) as gpu:
+        streams, _ = run_engine(gpu, w.r1, w.r2, batch_records=7000)
+        assert_matches_reference(ref, streams, gpu.stats(), opt)
+
+
+@pytest.mark.skipif(not refcli.have_ref(), reason="reference binary not present")
+def test_c5_and_c3_against_reference_binary_directly():
+    w = synth.c5(15000)
+    opt = Options(mode=MODE_HARD, quality=20, average_quality=25.0, replace_to_N_q=10, discard_output=True)
+    ref = refcli.run_reference(unpaired=w.r1, flags=refcli.flags_for(opt), threads=2)
+    with Engine(opt) as gpu:
+        streams, _ = run_engine(gpu, w.r1, None)
+        assert_matches_reference(ref, streams, gpu.stats(), opt)
+    w = synth.c3(1500)
+    opt = Options(filter_adapter=True, adapters=refcli.adapters_for(True, True, w.artifacts))
+    ref = refcli.run_reference(w.r1, w.r2, flags=refcli.flags_for(opt, polyA=True), threads=3, artifacts=w.artifacts)
+    with Engine(opt) as gpu:
+        streams, _ = run_engine(gpu, w.r1, w.r2)
+        assert_matches_reference(ref, streams, gpu.stats(), opt, opt.adapters)
