@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the FaQCs trim + filter + statistics hot path on B200.
+
+One "step" = one pass of the hot path (frame -> trim/filter/stats -> route/emit)
+over one batch of synthetic Illumina-like reads (BASELINE.json configs[1]:
+2x150 PE, ASCII-33, default BWA_plus trim + filters + full statistics).
+
+  python bench.py --gpus N --steps K --warmup W          # this implementation
+  python bench.py --impl reference ...                    # the reference's CPU path (oracle/_ref/FaQCs)
+
+Prints ONE JSON line (rank 0).  `value` = reads/s with the batch resident in HBM
+(CUDA events on the launching stream, max over ranks); `e2e` = the same metric
+through fq_process_host with pinned HOST buffers (H2D + kernels + D2H inside the
+timed region); `roofline` = algorithmic bytes of the dominant kernel / its
+device time against the measured HBM copy peak; `cpu_baseline` = the reference
+binary timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "reads/s trim+filter+stats (2x150 PE, default BWA_plus -q 5 --min_L 50 -n 2 --lc 0.85, full stats)"
+UNIT = "reads/s"
+WORKLOAD = "C2: synthetic Illumina 2x150 PE, ASCII-33, default trim + filters + full stats matrices"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "FaQCs")
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.sm, self.sm_max, self.reasons = [], 0, set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+                f = [x.strip() for x in out.split(",")]
+                self.sm.append(float(f[0]))
+                self.sm_max = max(self.sm_max, float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+
+    def result(self):
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max or None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def time_reference_binary(w, threads: int, tmp_root: str):
+    """Wall-clock of the unmodified reference on (r1, r2) with -t threads, --trim_only (skips only R)."""
+    d = tempfile.mkdtemp(prefix="faqcs_bench_", dir=tmp_root)
+    try:
+        p1, p2 = os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq")
+        w.r1.tofile(p1)
+        w.r2.tofile(p2)
+        t0 = time.perf_counter()
+        p = subprocess.run([REF_BIN, "-1", p1, "-2", p2, "-d", os.path.join(d, "out"), "-t", str(threads), "--trim_only"],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        dt = time.perf_counter() - t0
+        if p.returncode != 0:
+            raise RuntimeError("reference failed: " + p.stderr.decode(errors="replace")[-300:])
+        return dt
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def tmp_root():
+    return "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+
+
+def cpu_baseline(sample_pairs: int):
+    from faqcs_b200 import synth
+    cores = os.cpu_count() or 1
+    w = synth.c2(sample_pairs, start=7_000_000)
+    if os.path.exists(REF_BIN):
+        dt = time_reference_binary(w, cores, tmp_root())
+        kind = "reference"
+        sample = f"{sample_pairs} pairs (2x150) of the same workload, FaQCs v2.10 -t {cores} --trim_only, files on tmpfs, wall clock of the process"
+    else:                                   # the reference binary did not travel: time the oracle port
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from faqcs_b200.api import Options
+        from oracle_binding import OracleEngine
+        with OracleEngine(Options(input_quality_offset=33)) as eng:
+            t0 = time.perf_counter()
+            eng.process(w.r1, w.r2)
+            dt = time.perf_counter() - t0
+        kind, cores = "port", 1
+        sample = f"{sample_pairs} pairs (2x150), single-thread oracle port, in-memory"
+    return {"value": 2 * sample_pairs / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+            "gbases_per_s": 2 * sample_pairs * 150 / dt / 1e9}
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on this box's cores."""
+    if rank != 0:
+        return
+    from faqcs_b200 import synth
+    cores = os.cpu_count() or 1
+    pairs = args.ref_pairs
+    times = []
+    for i in range(args.warmup + args.steps):
+        w = synth.c2(pairs, start=9_000_000 + i * pairs)
+        if os.path.exists(REF_BIN):
+            dt = time_reference_binary(w, cores, tmp_root())
+            kind = "reference"
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from faqcs_b200.api import Options
+            from oracle_binding import OracleEngine
+            with OracleEngine(Options(input_quality_offset=33)) as eng:
+                t0 = time.perf_counter()
+                eng.process(w.r1, w.r2)
+                dt = time.perf_counter() - t0
+            kind, cores = "port", 1
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = 2 * pairs * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": pairs, "read_length": 150,
+                       "gbases_per_s": value * 150 / 1e9},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{pairs} pairs per step, FaQCs v2.10 -t {cores} --trim_only, tmpfs, process wall clock"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+class _DevPtr:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--block-pairs", type=int, default=250_000, help="pairs generated on the host (numpy)")
+    ap.add_argument("--batch-pairs", type=int, default=2_000_000, help="pairs per step (block replicated in HBM)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-pairs", type=int, default=500_000, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs per step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from faqcs_b200 import synth
+    from faqcs_b200.api import Engine, Options
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: faqcs_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: each rank owns its own slice of the read stream (weak scaling, no data-path collective)
+    reps = max(1, args.batch_pairs // args.block_pairs)
+    batch_pairs = reps * args.block_pairs
+    w = synth.c2(args.block_pairs, start=rank * args.block_pairs)
+    d_r1 = torch.from_numpy(w.r1).to(dev).repeat(reps)
+    d_r2 = torch.from_numpy(w.r2).to(dev).repeat(reps)
+    n1, n2 = d_r1.numel(), d_r2.numel()
+    reads_per_step = 2 * batch_pairs
+
+    eng = Engine(Options(), device=local_rank)
+    eng.autodetect(w.r1, w.r2)
+    ext = torch.cuda.ExternalStream(eng.stream(), device=dev)
+
+    def step():
+        return eng.process_device(d_r1.data_ptr(), n1, d_r2.data_ptr(), n2, 0, True, copy_out=False)
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launch_count()
+    seg = {k: 0.0 for k in ("all", "frame", "adapter", "trim", "emit")}
+    torch.cuda.synchronize()
+    e0.record(ext)
+    for _ in range(args.steps):
+        step()
+        t = eng.last_timing()
+        for k in seg:
+            seg[k] += t[k]
+    e1.record(ext)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    launches = eng.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = world * reads_per_step * args.steps / (total_ms / 1e3)
+
+    # emitted bytes of one step (needed for the algorithmic byte count)
+    import ctypes as C
+    from faqcs_b200.api import CBatchOut
+    out_bytes = list(res.stream_bytes)
+    alg_bytes = n1 + n2 + sum(out_bytes)
+
+    # ---- multi-GPU merge of the statistics: the path's only collective (NCCL all-reduce over NVLink)
+    allreduce_ms = None
+    if world > 1:
+        rows_needed = torch.tensor([320], device=dev, dtype=torch.int32)
+        dist.all_reduce(rows_needed, op=dist.ReduceOp.MAX)
+        eng.stats_reserve_rows(int(rows_needed.item()))
+        d, n, r = eng.stats_device_buffer()
+        t_stats = torch.as_tensor(_DevPtr(d, n, "<i8"), device=dev)
+        t_rows = torch.as_tensor(_DevPtr(r, 4, "<i4"), device=dev)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        dist.all_reduce(t_stats, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t_rows, op=dist.ReduceOp.MAX)
+        a1.record()
+        torch.cuda.synchronize()
+        allreduce_ms = a0.elapsed_time(a1)
+    st = eng.stats()
+
+    # ---- end-to-end: pinned host buffers in, host buffers out (fq_process_host)
+    e2e = None
+    if args.e2e_steps > 0:
+        h1, h2 = eng.host_alloc(n1), eng.host_alloc(n2)
+        for k in range(reps):
+            h1[k * w.r1.size:(k + 1) * w.r1.size] = w.r1
+            h2[k * w.r2.size:(k + 1) * w.r2.size] = w.r2
+        cb2 = CBatchOut()
+
+        def host_step():
+            eng._check(eng.lib.fq_process_host(eng.ctx, C.c_void_p(h1.ctypes.data), n1, C.c_void_p(h2.ctypes.data), n2, 0, 1, C.byref(cb2)))
+
+        host_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(ext)
+        for _ in range(args.e2e_steps):
+            host_step()
+        f1.record(ext)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ems = torch.tensor([max(f0.elapsed_time(f1), wall * 1e3)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * reads_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": n1 + n2, "d2h_bytes_per_step": int(sum(int(cb2.bytes[i]) for i in range(4))),
+               "ms_per_step": float(ems.item()) / args.e2e_steps,
+               "api": "fq_process_host (pinned host buffers, synchronous H2D -> kernels -> D2H)"}
+        eng.host_free(h1)
+        eng.host_free(h2)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        dom = max(("frame", "trim", "emit"), key=lambda k: seg[k])
+        dom_ms = seg[dom] / args.steps
+        # algorithmic bytes of each segment: framing reads B_in, trim reads the seq+qual lines,
+        # emit reads B_in and writes B_out; the headline figure charges the whole B_in + B_out to the dominant kernel
+        achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": batch_pairs, "read_length": 150,
+                       "bytes_in_per_step_per_gpu": n1 + n2, "bytes_out_per_step_per_gpu": sum(out_bytes),
+                       "gbases_per_s": value * 150 / 1e9, "l2": "inputs (%.0f MB per step) exceed the 126 MB L2" % ((n1 + n2) / 1e6),
+                       "reads_total": int(st.filter_stats[1]), "reads_kept": int(st.filter_stats[3]),
+                       "stats_allreduce_ms": allreduce_ms,
+                       "whole_job_hbm_frac": (alg_bytes / (total_ms / args.steps / 1e3) / 1e9) / peak},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": {"frame": "k_count_lines+k_scatter_lines+k_build_records", "trim": "k_trim",
+                                                     "emit": "k_route+k_scan_tiles+k_emit"}[dom],
+                         "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                         "segments_ms": {k: v / args.steps for k, v in seg.items()}},
+            "clocks": sampler.result(),
+            "gpu_launches": int(launches),
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_pairs)
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,7 @@ class Options:
 @dataclass
 class BatchResult:
     streams: List[bytes]
+    stream_bytes: List[int]
     n_records: int
     n_valid: Tuple[int, int]
     paired_read_number: int
@@ -259,7 +260,7 @@ class Engine:
         if p == "fq_":
             L.fq_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                             C.c_uint64, C.c_int, C.c_int, C.POINTER(CBatchOut)]
-            L.fq_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+            L.fq_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
             L.fq_launch_count.argtypes = [C.c_void_p]
             L.fq_launch_count.restype = C.c_uint64
             L.fq_stream.argtypes = [C.c_void_p]
@@ -328,7 +329,7 @@ class Engine:
             if out.results[m]:
                 raw = C.string_at(out.results[m], int(out.n_records) * C.sizeof(CReadResult))
                 results[m] = np.frombuffer(raw, dtype=READ_RESULT_DTYPE).copy()
-        return BatchResult(streams, int(out.n_records), (int(out.n_valid[0]), int(out.n_valid[1])),
+        return BatchResult(streams, [int(out.bytes[s]) for s in range(NUM_STREAM)], int(out.n_records), (int(out.n_valid[0]), int(out.n_valid[1])),
                            int(out.paired_read_number), int(out.paired_base_length), results)
 
     def process(self, r1, r2=None, first_record_index: int = 0, is_final: bool = True) -> BatchResult:
@@ -349,10 +350,22 @@ class Engine:
                                                first_record_index, int(is_final), int(copy_out), C.byref(out)))
         return self._collect(out, d_r2 is not None, want_data=copy_out)
 
-    def last_timing(self) -> Tuple[float, float]:
-        a, b = C.c_float(), C.c_float()
-        self._check(self.lib.fq_last_timing(self.ctx, C.byref(a), C.byref(b)))
-        return a.value, b.value
+    def last_timing(self) -> dict:
+        """Device ms of the last batch by segment (CUDA events on the context's stream)."""
+        ms = (C.c_float * 5)()
+        self._check(self.lib.fq_last_timing(self.ctx, ms, 5))
+        return dict(zip(("all", "frame", "adapter", "trim", "emit"), [float(x) for x in ms]))
+
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """Pinned host buffer (fq_host_alloc) viewed as a uint8 array; free with host_free."""
+        p = self.lib.fq_host_alloc(nbytes)
+        if not p:
+            raise MemoryError("fq_host_alloc failed")
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        self.lib.fq_host_free(C.c_void_p(arr.ctypes.data))
 
     def launch_count(self) -> int:
         return int(self.lib.fq_launch_count(self.ctx))

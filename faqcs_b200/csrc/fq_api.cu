@@ -102,8 +102,8 @@ struct fq_ctx {
 
     std::string error;
     uint64_t launches = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float t_all = 0, t_trim = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float t_seg[5] = {0, 0, 0, 0, 0};
     int sm_count = 0;
     size_t smem_optin = 0;
     const void *last_dev_out[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -315,6 +315,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         st = map_device_error(ctx, hi);
         if (st != FQ_OK) return st;
     }
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     const uint32_t max_len = std::max(ctx->h_info->max_len[0], ctx->h_info->max_len[1]);
     if (max_len > kResLenMask) return fail(ctx, FQ_ERR_ARG, "read longer than 16 Mi bases");
     st = ensure_stats_rows(ctx, max_len);
@@ -427,8 +428,11 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    cudaEventElapsedTime(&ctx->t_all, ctx->ev[0], ctx->ev[3]);
-    cudaEventElapsedTime(&ctx->t_trim, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->t_seg[0], ctx->ev[0], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->t_seg[1], ctx->ev[0], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->t_seg[2], ctx->ev[4], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->t_seg[3], ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->t_seg[4], ctx->ev[2], ctx->ev[3]);
     const BatchInfo hi = *ctx->h_info;
     st = map_device_error(ctx, hi);
     if (st != FQ_OK) return st;
@@ -641,11 +645,10 @@ fq_status fq_device_outputs(fq_ctx *ctx, const void *d_out[FQ_NUM_STREAM])
     return FQ_OK;
 }
 
-fq_status fq_last_timing(fq_ctx *ctx, float *all_kernels_ms, float *trim_kernel_ms)
+fq_status fq_last_timing(fq_ctx *ctx, float *ms, int n)
 {
-    if (!ctx) return FQ_ERR_ARG;
-    if (all_kernels_ms) *all_kernels_ms = ctx->t_all;
-    if (trim_kernel_ms) *trim_kernel_ms = ctx->t_trim;
+    if (!ctx || !ms) return FQ_ERR_ARG;
+    for (int i = 0; i < n && i < 5; ++i) ms[i] = ctx->t_seg[i];
     return FQ_OK;
 }
 

@@ -240,9 +240,11 @@ fq_status fq_process_device(fq_ctx *ctx, const void *d_r1, size_t n1,
                             int copy_out, fq_batch_out *out);
 fq_status fq_device_outputs(fq_ctx *ctx, const void *d_out[FQ_NUM_STREAM]);
 
-/* Elapsed device time (ms, CUDA events on the context's stream) of the kernels
- * of the last fq_process_* call, and of its dominant kernel alone. */
-fq_status fq_last_timing(fq_ctx *ctx, float *all_kernels_ms, float *trim_kernel_ms);
+/* Device time (ms, CUDA events on the context's stream) of the last fq_process_*
+ * call, by segment: ms[0] all kernels, ms[1] framing, ms[2] pair-id check +
+ * adapter pass, ms[3] trim/filter/statistics kernel, ms[4] route + scan + emit.
+ * Fills min(n, 5) entries. */
+fq_status fq_last_timing(fq_ctx *ctx, float *ms, int n);
 /* Number of kernel launches issued by the context so far. */
 uint64_t  fq_launch_count(const fq_ctx *ctx);
 /* CUDA stream of the context as a void* (cudaStream_t), for event timing by the caller. */

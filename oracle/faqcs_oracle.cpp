@@ -861,6 +861,13 @@ fq_status fqo_stats(fqo_ctx *ctx, fq_stats_view *v)
     Stats &s = ctx->st;
     memset(v, 0, sizeof(*v));
     memcpy(v->filter_stats, s.filter, sizeof(s.filter));
+    // main(): phiX pseudo-adapters -> READ/BASE_PHIX, the others -> READ/BASE_ADAPTER (FaQCs.cpp:92-127)
+    for (size_t j = 0; j < s.adapter_reads.size(); ++j) {
+        const bool phix = ctx->adapter_names[j] == "__PhiX174_NC_001422__" ||
+                          ctx->adapter_names[j] == "__PhiX174_NC_001422_complement__";
+        v->filter_stats[phix ? FQ_READ_PHIX : FQ_READ_ADAPTER] += s.adapter_reads[j];
+        v->filter_stats[phix ? FQ_BASE_PHIX : FQ_BASE_ADAPTER] += s.adapter_bases[j];
+    }
     v->n_adapters = (uint32_t)s.adapter_reads.size();
     v->adapter_reads = s.adapter_reads.data();
     v->adapter_bases = s.adapter_bases.data();

@@ -110,10 +110,7 @@ def assert_matches_reference(ref: Dict, streams: Sequence[bytes], stats: Stats, 
                                      f"{a[max(0,k-60):k+60]!r} vs {b[max(0,k-60):k+60]!r}")
     parsed = parse_stats_txt(ref["stats_txt"], opt.qc_only)
     for name, val in parsed.items():
-        if name in ("READ_ADAPTER", "BASE_ADAPTER"):
-            got = int(stats.adapter_reads.sum()) if name == "READ_ADAPTER" else int(stats.adapter_bases.sum())
-        else:
-            got = int(stats.filter_stats[STAT[name]])
+        got = int(stats.filter_stats[STAT[name]])
         assert got == val, f"{name}: {got} != reference {val}"
     if adapters:
         want = parse_adapter_lines(ref["stats_txt"])
