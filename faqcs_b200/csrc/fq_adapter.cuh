@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
         if (best_score > 0) {
             // find_mask_range (trim.cpp:1144-1189) over runs instead of bits; every lane runs it redundantly
             uint32_t run_start = 0, run_len = 0, longest = 0, longest_start = 0;
-            for (uint32_t w = 0; w < mask_words; ++w) {
+            const uint32_t read_words = (L + 31) >> 5;          // only the words this read owns
+            for (uint32_t w = 0; w < read_words; ++w) {
                 const uint32_t nbits = min(32u, L - (w << 5));
                 uint32_t keep = ~s_mask[w];
                 if (nbits < 32) keep &= (1u << nbits) - 1u;

@@ -380,16 +380,20 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         ta.L = ctx->L;
         ta.rows = ctx->d_rows.as<StatsRows>();
         ta.info = info;
+        // shared histogram rows: cover the longest read if it fits next to the composition tables
+        ta.comp_key_len = max_len <= 1023 ? max_len : 0xffffffffu;
         const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
         uint32_t rows = round_up(std::max(max_len, 1u), 32);
-        auto words = [](uint32_t r) { return (size_t)r * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)r + 1) + 4 * kQualCols + 32; };
-        while (rows > 32 && words(rows) * 4 > budget) rows -= 32;
+        while (rows > 32 && SmemHist::words(rows, ta.comp_key_len) * 4 > budget) rows -= 32;
         rows = std::min(rows, ctx->L.rows);
         ta.smem_rows = rows;
-        const size_t smem = words(rows) * 4;
+        const size_t smem = SmemHist::words(rows, ta.comp_key_len) * 4;
         CK(cudaFuncSetAttribute(k_trim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int threads = 512;
-        const int grid = std::max(1, std::min<int>((n * n_mates + 15) / 16, ctx->sm_count));
+        const int threads = kTrimThreads;
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trim, threads, smem));
+        per_sm = std::max(per_sm, 1);
+        const int grid = std::max(1, std::min<int>((n * n_mates + 15) / 16, ctx->sm_count * per_sm));
         k_trim<<<grid, threads, smem, ctx->stream>>>(ta, o);
         ctx->launches++;
     }

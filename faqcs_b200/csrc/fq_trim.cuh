@@ -1,11 +1,18 @@
 // fq_trim.cuh -- the per-read trim / filter / statistics kernel (trim_read, trim.cpp:225-551).
 //
-// One warp per read, lanes striped over consecutive base positions, persistent
-// grid.  Statistics go to shared-memory privatised histograms stored transposed
+// One warp per read, lanes striped over consecutive base positions (lane l holds
+// positions l, l+32, ...), persistent grid.  Reads of up to 320 bases take a
+// register-resident fast path (process_fast<K>: the whole read is loaded once,
+// byte-striped, and every later phase works from registers); longer reads take
+// process_generic, which re-reads global memory chunk by chunk.
+//
+// Statistics go to shared-memory privatised histograms stored transposed
 // ([column][position], rows % 32 == 0) so that a warp's 32 consecutive positions
 // always fall into 32 distinct banks; they are merged into the global u64 block
-// once per CTA.  post-trim matrices are accumulated as "pre minus removed" (see
-// StatsLayout), so an untrimmed surviving read costs one histogram update per base.
+// once per CTA.  The post-trim matrices are accumulated as "pre minus removed"
+// (see StatsLayout), so an untrimmed surviving read costs one histogram update
+// per base.  Base letters are classified through a 256-entry shared-memory LUT,
+// per-read base counts are 5-bit packed per lane and reduced with REDUX.
 #pragma once
 #include "fq_common.cuh"
 
@@ -25,26 +32,24 @@ struct TrimArgs {
     StatsRows *rows;
     BatchInfo *info;
     uint32_t smem_rows;         // rows held in shared memory (multiple of 32, <= L.rows)
+    uint32_t comp_key_len;      // reads of exactly this length use the shared composition tables (0xffffffff: none)
 };
 
-__device__ __forceinline__ int base_code(uint32_t c)
+// Base classes: A/a 0, T/t 1, C/c 2, G/g 3, N/n 4 (FaQCs.h:35-42), anything else 5.
+__host__ __device__ __forceinline__ int base_code_slow(uint32_t c)
 {
     c |= 0x20u;
     return c == 'a' ? 0 : c == 't' ? 1 : c == 'c' ? 2 : c == 'g' ? 3 : c == 'n' ? 4 : 5;
 }
+// LUT entry: bits 28..31 = class, bits 0..24 = 1 << (5 * class) for classes 0..4 (packed per-lane counters).
+__host__ __device__ __forceinline__ uint32_t lut_entry(uint32_t c)
+{
+    const int code = base_code_slow(c);
+    return ((uint32_t)code << 28) | (code < 5 ? (1u << (5 * code)) : 0u);
+}
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ int warp_sum_i(int v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
 // trim.cpp:553-576 with the reference's C types: float(int)/float(size_t) - float(char), clamped at 0.
 __device__ __forceinline__ float average_quality(int total, uint32_t len, int offset)
@@ -54,11 +59,8 @@ __device__ __forceinline__ float average_quality(int total, uint32_t len, int of
 }
 
 // trim.cpp:860-874: bin = size_t(float(10000)/len * count), float arithmetic.
-__device__ __forceinline__ uint32_t composition_bin(uint32_t len, uint32_t count)
-{
-    const float norm = len ? __fdiv_rn(10000.0f, (float)len) : 0.0f;
-    return __float2uint_rz(__fmul_rn(norm, (float)count));
-}
+__device__ __forceinline__ float composition_norm(uint32_t len) { return len ? __fdiv_rn(10000.0f, (float)len) : 0.0f; }
+__device__ __forceinline__ uint32_t composition_bin_n(float norm, uint32_t count) { return __float2uint_rz(__fmul_rn(norm, (float)count)); }
 
 // Quality value of absolute position p with terminal-N masking applied
 // (mask_quality_terminal_N, trim.cpp:1191-1216; quality_score, fastq.h:17-36).
@@ -135,40 +137,615 @@ __device__ __forceinline__ uint32_t bwa_plus_trim(const QualAt &qa, uint32_t lo,
     return (uint32_t)(final_pos_3 - final_pos_5 + 1);
 }
 
-// Shared-memory histogram block of one CTA.
+// Shared-memory block of one CTA, addressed by word offsets from the dynamic shared base
+// (offsets are functions of `rows` alone, so the layout costs two registers, not twelve pointers).
+extern __shared__ uint32_t g_smem[];
 struct SmemHist {
-    uint32_t *preq, *remq;   // [42][rows]
-    uint32_t *preb, *remb;   // [5][rows]
-    uint32_t *g2n;           // [rows]
-    uint32_t *prelen, *postlen;   // [rows + 1]
-    uint32_t *qh;            // [4][42]: pre_rq, pre_bq, post_rq, post_bq
-    uint32_t *filt;          // [32]
-    uint32_t rows;
-    __device__ static size_t words(uint32_t rows) { return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * (rows + 1) + 4 * kQualCols + 32; }
-    __device__ void carve(uint32_t *base, uint32_t r)
+    uint32_t rows, key;
+    // [42][rows] pre / removed quality, [5][rows] pre / removed base, [rows] g2n, [rows+1] x2 length,
+    // [4][42] avg-Q hists, [32] filter counters, [256] LUT, [12] composition bin 0, [2][7][key+1] composition by count
+    __host__ __device__ static size_t words(uint32_t rows, uint32_t key)
     {
-        rows = r;
-        preq = base; base += (size_t)kQualCols * r;
-        remq = base; base += (size_t)kQualCols * r;
-        preb = base; base += (size_t)kBaseCols * r;
-        remb = base; base += (size_t)kBaseCols * r;
-        g2n = base; base += r;
-        prelen = base; base += r + 1;
-        postlen = base; base += r + 1;
-        qh = base; base += 4 * kQualCols;
-        filt = base;
+        return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + 4 * kQualCols + 32 + 256 + 12 +
+               (key == 0xffffffffu ? 0 : 14 * ((size_t)key + 1));
     }
+    __device__ __forceinline__ uint32_t *preq() const { return g_smem; }
+    __device__ __forceinline__ uint32_t *remq() const { return g_smem + kQualCols * rows; }
+    __device__ __forceinline__ uint32_t *preb() const { return g_smem + 2 * kQualCols * rows; }
+    __device__ __forceinline__ uint32_t *remb() const { return g_smem + (2 * kQualCols + kBaseCols) * rows; }
+    __device__ __forceinline__ uint32_t *g2n() const { return g_smem + (2 * kQualCols + 2 * kBaseCols) * rows; }
+    __device__ __forceinline__ uint32_t *prelen() const { return g_smem + (2 * kQualCols + 2 * kBaseCols + 1) * rows; }
+    __device__ __forceinline__ uint32_t *postlen() const { return prelen() + rows + 1; }
+    __device__ __forceinline__ uint32_t *qh() const { return postlen() + rows + 1; }
+    __device__ __forceinline__ uint32_t *filt() const { return qh() + 4 * kQualCols; }
+    __device__ __forceinline__ uint32_t *lut() const { return filt() + 32; }
+    __device__ __forceinline__ uint32_t *zero() const { return lut() + 256; }
+    __device__ __forceinline__ uint32_t *compk() const { return zero() + 12; }
 };
 
 __device__ __forceinline__ void gadd(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 
-__global__ void __launch_bounds__(512, 1) k_trim(const TrimArgs a, const DevOpts o)
+// Warp-uniform state carried across the reads a warp processes.
+struct WarpState {
+    uint32_t acc_reads = 0, acc_trimmed = 0;
+    unsigned long long acc_len = 0, acc_trimmed_len = 0;
+    uint32_t max_pre_rows = 0, max_post_rows = 0, max_post_len1 = 0;
+    uint32_t err = 0, err_rec = 0xffffffffu;
+    uint32_t c_len = 0xffffffffu;   // cached divisions (most runs have one read length)
+    float c_norm = 0.0f;
+    uint32_t c_wl = 0xffffffffu;
+    float c_lcnorm = 0.0f;
+    __device__ __forceinline__ float norm_for(uint32_t len)
+    {
+        if (len != c_len) { c_len = len; c_norm = composition_norm(len); }
+        return c_norm;
+    }
+    __device__ __forceinline__ float lcnorm_for(uint32_t wl)
+    {
+        if (wl != c_wl) { c_wl = wl; c_lcnorm = (float)(1.0 / (double)wl); }   // trim.cpp:483
+        return c_lcnorm;
+    }
+};
+
+struct KernelCtx {
+    const TrimArgs &a;
+    const DevOpts &o;
+    const SmemHist &H;
+    unsigned long long *S;
+    uint32_t lane;
+};
+
+// One increment in each of the six composition histograms (trim.cpp:860-874).  `cnt` holds the
+// count of class `lane` in lanes 0..4.  which = 0 (pre) / 1 (post).
+__device__ __forceinline__ void composition_update(const KernelCtx &kc, WarpState &ws, int which, uint32_t len, uint32_t cnt)
 {
-    extern __shared__ uint32_t smem[];
-    SmemHist H;
-    H.carve(smem, a.smem_rows);
-    const size_t n_words = SmemHist::words(a.smem_rows);
-    for (size_t i = threadIdx.x; i < n_words; i += blockDim.x) smem[i] = 0;
+    const uint32_t lane = kc.lane;
+    const float norm = ws.norm_for(len);
+    const uint32_t bin = composition_bin_n(norm, cnt);
+    const uint32_t iC = __shfl_sync(0xffffffffu, bin, 2), iG = __shfl_sync(0xffffffffu, bin, 3);
+    const size_t comp = which ? kc.a.L.post_comp : kc.a.L.pre_comp;
+    if (len == kc.H.key) {
+        const uint32_t cC = __shfl_sync(0xffffffffu, cnt, 2), cG = __shfl_sync(0xffffffffu, cnt, 3);
+        uint32_t *tab = kc.H.compk() + (size_t)which * 7 * (kc.H.key + 1);
+        if (lane < 5) atomicAdd(&tab[lane * (kc.H.key + 1) + cnt], 1u);
+        else if (lane == 5) {
+            const uint32_t s = cC + cG;
+            const uint32_t delta = composition_bin_n(norm, s) - (iC + iG);      // bin(G)+bin(C) vs bin(G+C): 0 or 1
+            if (delta < 2) atomicAdd(&tab[(5 + delta) * (kc.H.key + 1) + s], 1u);
+            else gadd(&kc.S[comp + 5 * (size_t)kCompBins + iC + iG], 1);
+        }
+    } else if (lane < 6) {
+        const uint32_t b = lane < 5 ? bin : iC + iG;
+        if (b == 0) atomicAdd(&kc.H.zero()[which * 6 + lane], 1u);
+        else gadd(&kc.S[comp + (size_t)lane * kCompBins + b], 1);
+    }
+}
+
+// Lane-parallel scalar statistics of one read: composition, length histogram, avg-Q histograms.
+__device__ __forceinline__ void scalar_stats(const KernelCtx &kc, WarpState &ws, int which, uint32_t len, uint32_t cnt, int qbin)
+{
+    composition_update(kc, ws, which, len, cnt);
+    const uint32_t lane = kc.lane;
+    qbin = min(max(qbin, 0), 41);
+    if (lane == 6) {
+        uint32_t *h = which ? kc.H.postlen() : kc.H.prelen();
+        if (len <= kc.H.rows) atomicAdd(&h[len], 1u);
+        else gadd(&kc.S[(which ? kc.a.L.post_len : kc.a.L.pre_len) + len], 1);
+    } else if (lane == 7) atomicAdd(&kc.H.qh()[(2 * which) * kQualCols + qbin], 1u);
+    else if (lane == 8) atomicAdd(&kc.H.qh()[(2 * which + 1) * kQualCols + qbin], len);
+}
+
+// Window after adapter clip, 5'/3' clip, length filter and quality trim (trim.cpp:270-360).
+struct Window {
+    uint32_t lo, wl, off5, flags;
+    bool ret;
+    int best_adapter;
+};
+
+__device__ __forceinline__ Window determine_window(const KernelCtx &kc, uint32_t mate, uint32_t r, uint32_t len, const QualAt &qa)
+{
+    const DevOpts &o = kc.o;
+    const SmemHist &H = kc.H;
+    const uint32_t lane = kc.lane;
+    Window w{0, len, 0, 0, true, -1};
+    if (o.filter_adapter && kc.a.adp[mate]) {
+        const uint2 v = kc.a.adp[mate][r];
+        w.best_adapter = kc.a.adp_best[mate][r];
+        if (w.best_adapter >= 0) w.flags |= FQ_RR_ADAPTER;
+        if (len != v.y) {
+            w.lo = v.x;
+            w.wl = v.y;
+            w.off5 += (v.y == 0) ? len : v.x;
+        }
+    }
+    if (o.trim_5 && !o.qc_only) {
+        if (o.trim_5 > w.wl) w.wl = 0;                          // offset_5 += len after len = 0 (Q14)
+        else { w.lo += o.trim_5; w.wl -= o.trim_5; w.off5 += o.trim_5; }
+    }
+    if (o.trim_3 && !o.qc_only) {
+        if (o.trim_3 > w.wl) w.wl = 0;
+        else w.wl -= o.trim_3;
+    }
+    if (w.wl < o.min_len || w.wl == 0) {                        // trim.cpp:317-323
+        if (lane == 0) { atomicAdd(&H.filt()[FQ_READ_LENGTH], 1u); atomicAdd(&H.filt()[FQ_BASE_LENGTH], w.wl); }
+        w.flags |= FQ_RR_F_LENGTH;
+        w.ret = false;
+    }
+    if (!o.qc_only && w.ret) {                                  // trim.cpp:325-360
+        const uint32_t init_len = w.wl;
+        uint32_t f5 = 0;
+        if (o.mode == FQ_MODE_HARD) w.wl = hard_trim(qa, w.lo, (int)w.wl, o.quality, o.protect_5 != 0, f5);
+        else if (o.mode == FQ_MODE_BWA) w.wl = bwa_trim(qa, w.lo, (int)w.wl, o.quality, f5);
+        else w.wl = bwa_plus_trim(qa, w.lo, (int)w.wl, o.quality, o.protect_5 != 0, f5);
+        w.off5 += f5;
+        w.lo += f5;
+        if (init_len != w.wl) {
+            if (lane == 0) { atomicAdd(&H.filt()[FQ_READ_QUAL_TRIM], 1u); atomicAdd(&H.filt()[FQ_BASE_QUAL_TRIM], init_len - w.wl); }
+            w.flags |= FQ_RR_QUAL_TRIMMED;
+        }
+        if (w.wl < o.min_len || w.wl == 0) {
+            if (lane == 0) { atomicAdd(&H.filt()[FQ_READ_LENGTH], 1u); atomicAdd(&H.filt()[FQ_BASE_LENGTH], w.wl); }
+            w.flags |= FQ_RR_F_LENGTH;
+            w.ret = false;
+        }
+    }
+    return w;
+}
+
+// Dinucleotide counts of the window straight from global memory (rare path, trim.cpp:426-481).
+__device__ __forceinline__ bool dinucleotide_low_complexity(const KernelCtx &kc, const uint8_t *sp, const QualAt &qa, uint32_t lo, uint32_t wl, float norm2)
+{
+    const DevOpts &o = kc.o;
+    const uint32_t lane = kc.lane;
+    uint32_t dc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dc[k] = 0;
+    int prev_carry = 4;
+    for (uint32_t b = 0; b < wl; b += 32) {
+        const uint32_t i = b + lane;
+        const bool in = i < wl;
+        const uint32_t p = lo + i;
+        const uint32_t c = in ? sp[p] : 0;
+        int cur = in ? (int)(kc.H.lut()[c] >> 28) : 4;
+        if (cur > 3) cur = 4;
+        if (in && o.replace_q > 0 && c == 'G' && qa(p) < (int)o.replace_q) cur = 4;
+        int prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        if (lane == 0) prev = prev_carry;
+        prev_carry = __shfl_sync(0xffffffffu, cur, 31);
+        const int code = (in && cur != 4 && prev != 4 && cur != prev) ? ((prev << 2) | cur) : -1;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dc[k] += __popc(__ballot_sync(0xffffffffu, code == k));
+    }
+    bool lowc = false;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) lowc |= __fmul_rn((float)dc[k], norm2) > o.lc;
+    return lowc;
+}
+
+// Filters on the window (trim.cpp:363-513).  Counts are of the window after G->N replacement.
+__device__ __forceinline__ void apply_filters(const KernelCtx &kc, WarpState &ws, Window &w, uint32_t r, uint32_t max_run, int sum_w,
+                                              uint32_t wA, uint32_t wT, uint32_t wC, uint32_t wG, int max_qv, const uint8_t *sp,
+                                              const QualAt &qa, float &ave_q)
+{
+    const DevOpts &o = kc.o;
+    const SmemHist &H = kc.H;
+    const uint32_t lane = kc.lane;
+    if (max_run >= o.max_poly_n) {                              // trim.cpp:363-371
+        if (lane == 0) { atomicAdd(&H.filt()[FQ_READ_NN], 1u); atomicAdd(&H.filt()[FQ_BASE_NN], w.wl); }
+        w.flags |= FQ_RR_F_NN;
+        if (!o.qc_only) w.ret = false;
+    }
+    ave_q = average_quality(sum_w, w.wl, o.in_off);
+    if (w.ret && ave_q < o.avg_q) {                             // trim.cpp:374-382
+        if (lane == 0) { atomicAdd(&H.filt()[FQ_READ_AVG_Q], 1u); atomicAdd(&H.filt()[FQ_BASE_AVG_Q], w.wl); }
+        w.flags |= FQ_RR_F_AVGQ;
+        w.ret = false;
+    }
+    if (w.ret) {                                                // low complexity, trim.cpp:405-513
+        const float norm = ws.lcnorm_for(w.wl);
+        bool lowc = __fmul_rn((float)wA, norm) > o.lc || __fmul_rn((float)wT, norm) > o.lc ||
+                    __fmul_rn((float)wG, norm) > o.lc || __fmul_rn((float)wC, norm) > o.lc;
+        if (!lowc) {
+            const float norm2 = norm * 2.0f;                    // trim.cpp:499
+            // a dinucleotide count can not exceed the second largest base count
+            const uint32_t second = max(max(min(wA, wT), min(wC, wG)), min(max(wA, wT), max(wC, wG)));
+            if (__fmul_rn((float)second, norm2) > o.lc) lowc = dinucleotide_low_complexity(kc, sp, qa, w.lo, w.wl, norm2);
+        }
+        if (lowc) {
+            if (lane == 0) { atomicAdd(&H.filt()[FQ_READ_LOW_COMPLEXITY], 1u); atomicAdd(&H.filt()[FQ_BASE_LOW_COMPLEXITY], w.wl); }
+            w.flags |= FQ_RR_F_LOWCOMP;
+            w.ret = false;
+        }
+    }
+    if (w.ret && o.in_off != o.out_off && max_qv + o.out_off > 127) {      // trim.cpp:516-525
+        ws.err |= kErrReencode;
+        ws.err_rec = min(ws.err_rec, r);
+    }
+}
+
+// Longest run of set bits in a multi-word bitmap fed word by word (count_poly_n, trim.cpp:578-597).
+struct RunTracker {
+    uint32_t carry = 0, best = 0;
+    __device__ __forceinline__ void feed(uint32_t m)
+    {
+        if (m) {
+            uint32_t x = m;
+            const int f = __ffs(~x);
+            const uint32_t head = f ? (uint32_t)(f - 1) : 32u;
+            best = max(best, carry + head);
+            uint32_t k = 0;
+            while (x) { x &= x >> 1; ++k; }
+            best = max(best, k);
+            carry = (m == 0xffffffffu) ? carry + 32 : (uint32_t)__clz(~m);
+        } else carry = 0;
+    }
+};
+
+__device__ __forceinline__ uint32_t unpack5(uint32_t packed, int field) { return (packed >> (5 * field)) & 31u; }
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: reads of up to 32 * K bases, everything from registers.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void process_fast(const KernelCtx &kc, WarpState &ws, uint32_t mate, uint32_t r, const Rec &rc)
+{
+    const DevOpts &o = kc.o;
+    const SmemHist &H = kc.H;
+    const uint32_t lane = kc.lane, R = H.rows;
+    const uint8_t *sp = kc.a.raw[mate] + rc.seq;
+    const signed char *qp = reinterpret_cast<const signed char *>(kc.a.raw[mate] + rc.qual);
+    const uint32_t len = rc.len;
+
+    // ---- load the read once, byte-striped
+    uint32_t c[K];
+    int q[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t p = k * 32 + lane;
+        c[k] = 0;
+        q[k] = o.in_off;
+        if (p < len) { c[k] = sp[p]; q[k] = (int)qp[p]; }
+    }
+    // ---- terminal 'N' runs (trim.cpp:1191-1216), uppercase only
+    uint32_t nm[K], any_n = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { nm[k] = __ballot_sync(0xffffffffu, c[k] == 'N'); any_n |= nm[k]; }
+    uint32_t lead = 0, trail = len;
+    if (any_n) {
+        bool last_n = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if ((uint32_t)k == ((len - 1) >> 5)) last_n = (nm[k] >> ((len - 1) & 31)) & 1u;
+        if ((nm[0] & 1u) || last_n) {
+            // ones from position 0 / zeros back from position len-1
+            bool open = true;
+            lead = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (open && (uint32_t)(k * 32) < len) {
+                    const uint32_t nb = min(32u, len - k * 32);
+                    const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+                    const uint32_t inv = ~nm[k] & valid;
+                    if (inv) { lead += __ffs(inv) - 1; open = false; }
+                    else lead += nb;
+                }
+            }
+            open = true;
+            trail = len;
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) {
+                if (open && (uint32_t)(k * 32) < len) {
+                    const uint32_t nb = min(32u, len - k * 32);
+                    const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+                    const uint32_t inv = ~nm[k] & valid;
+                    if (inv) { trail = k * 32 + (31 - __clz(inv)) + 1; open = false; }
+                    else trail = k * 32;
+                }
+            }
+            if (lead >= len) trail = 0;     // all 'N'
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint32_t p = k * 32 + lane;
+                if (p < lead || p >= trail) q[k] = o.in_off;
+            }
+        }
+    }
+    const QualAt qa{qp, lead, trail, o.in_off};
+
+    // ---- PRE statistics (trim.cpp:247-258)
+    int sum_q = 0;
+    uint32_t packed = 0, codes = 0;
+    bool bad_q = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if ((uint32_t)(k * 32) < len) {
+            const uint32_t p = k * 32 + lane;
+            const bool in = p < len;
+            const uint32_t e = H.lut()[c[k]];
+            const uint32_t code = e >> 28;
+            const int qv = max(0, q[k] - o.in_off);
+            if (in) {
+                sum_q += q[k];
+                packed += e & 0x1ffffffu;
+                bad_q |= qv > FQ_MAX_QUALITY_SCORE;
+                if (qv <= FQ_MAX_QUALITY_SCORE) atomicAdd(&H.preq()[qv * R + p], 1u);
+                if (code < 5) atomicAdd(&H.preb()[code * R + p], 1u);
+            }
+            codes |= code << (3 * k);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad_q)) { ws.err |= kErrQualGt41; ws.err_rec = min(ws.err_rec, r); }
+    sum_q = warp_sum_i(sum_q);
+    // per-class totals: 10-bit fields (A,T,C) and (G,N); a read has at most 320 bases
+    const uint32_t tATC = warp_sum(unpack5(packed, 0) | (unpack5(packed, 1) << 10) | (unpack5(packed, 2) << 20));
+    const uint32_t tGN = warp_sum(unpack5(packed, 3) | (unpack5(packed, 4) << 10));
+    const uint32_t nA = tATC & 1023u, nT = (tATC >> 10) & 1023u, nC = tATC >> 20, nG = tGN & 1023u, nN = tGN >> 10;
+    {
+        const uint32_t mine = lane == 0 ? nA : lane == 1 ? nT : lane == 2 ? nC : lane == 3 ? nG : nN;
+        scalar_stats(kc, ws, 0, len, mine, (int)average_quality(sum_q, len, o.in_off));
+    }
+    ws.acc_reads += 1;
+    ws.acc_len += len;
+    ws.max_pre_rows = max(ws.max_pre_rows, len);
+
+    // ---- window
+    Window w = determine_window(kc, mate, r, len, qa);
+
+    // ---- window statistics and filters
+    float ave_q = 0.0f;
+    uint32_t wA = nA, wT = nT, wC = nC, wG = nG, wN = nN, n_lowg = 0;
+    if (w.ret) {
+        int sum_w = sum_q, max_qv = 0;
+        const bool whole = (w.lo == 0 && w.wl == len);
+        const bool need_max = o.in_off != o.out_off && o.out_off + FQ_MAX_QUALITY_SCORE > 127;   // re-encode can overflow
+        if (!whole || o.replace_q > 0 || need_max) {
+            uint32_t pk = 0;
+            int sw = 0, mq = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if ((uint32_t)(k * 32) < len) {
+                    const uint32_t p = k * 32 + lane;
+                    const bool inw = p >= w.lo && p < w.lo + w.wl;
+                    uint32_t code = (codes >> (3 * k)) & 7u;
+                    const int qv = max(0, q[k] - o.in_off);
+                    const bool lowg = inw && o.replace_q > 0 && c[k] == 'G' && qv < (int)o.replace_q;
+                    if (lowg) code = 4;
+                    if (inw) {
+                        sw += q[k];               // raw quality chars (terminal-N positions hold the offset char)
+                        mq = max(mq, qv);
+                        if (code < 5) pk += 1u << (5 * code);
+                    }
+                    n_lowg += __popc(__ballot_sync(0xffffffffu, lowg));
+                }
+            }
+            sum_w = warp_sum_i(sw);
+            max_qv = __reduce_max_sync(0xffffffffu, mq);
+            const uint32_t uATC = warp_sum(unpack5(pk, 0) | (unpack5(pk, 1) << 10) | (unpack5(pk, 2) << 20));
+            const uint32_t uGN = warp_sum(unpack5(pk, 3) | (unpack5(pk, 4) << 10));
+            wA = uATC & 1023u; wT = (uATC >> 10) & 1023u; wC = uATC >> 20; wG = uGN & 1023u; wN = uGN >> 10;
+        }
+        uint32_t max_run = 0;
+        if (any_n) {                                            // longest 'N' run inside the window
+            RunTracker rt;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if ((uint32_t)(k * 32) < len) {
+                    // window bits of this word
+                    const int lo_b = max((int)w.lo - k * 32, 0), hi_b = min((int)(w.lo + w.wl) - k * 32, 32);
+                    uint32_t wm = 0;
+                    if (lo_b < hi_b) wm = ((hi_b - lo_b) == 32 ? 0xffffffffu : ((1u << (hi_b - lo_b)) - 1u)) << lo_b;
+                    rt.feed(nm[k] & wm);
+                }
+            }
+            max_run = rt.best;
+        }
+        apply_filters(kc, ws, w, r, max_run, sum_w, wA, wT, wC, wG, max_qv, sp, qa, ave_q);
+    }
+
+    // ---- POST statistics (trim.cpp:527-548) as "removed" updates
+    if (w.ret) {
+        w.flags |= FQ_RR_VALID;
+        ws.acc_trimmed += 1;
+        ws.acc_trimmed_len += w.wl;
+        ws.max_post_rows = max(ws.max_post_rows, w.off5 + w.wl);
+        ws.max_post_len1 = max(ws.max_post_len1, w.wl + 1);
+        const uint32_t mine = lane == 0 ? wA : lane == 1 ? wT : lane == 2 ? wC : lane == 3 ? wG : wN;
+        scalar_stats(kc, ws, 1, w.wl, mine, (int)ave_q);
+    }
+    const bool whole_removed = !w.ret;
+    if (whole_removed || w.lo > 0 || w.lo + w.wl < len || n_lowg) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if ((uint32_t)(k * 32) < len) {
+                const uint32_t p = k * 32 + lane;
+                if (p < len) {
+                    const bool inside = !whole_removed && p >= w.lo && p < w.lo + w.wl;
+                    const uint32_t code = (codes >> (3 * k)) & 7u;
+                    const int qv = max(0, q[k] - o.in_off);
+                    if (!inside) {
+                        if (qv <= FQ_MAX_QUALITY_SCORE) atomicAdd(&H.remq()[qv * R + p], 1u);
+                        if (code < 5) atomicAdd(&H.remb()[code * R + p], 1u);
+                    } else if (n_lowg && c[k] == 'G' && qv < (int)o.replace_q) {
+                        atomicAdd(&H.remb()[3 * R + p], 1u);      // surviving G -> N: leaves column G, enters column N
+                        atomicAdd(&H.g2n()[p], 1u);
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        kc.a.res[mate][r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags));
+        if (kc.a.dbg[mate]) {
+            fq_read_result d;
+            d.offset_5 = w.off5;
+            d.length = w.ret ? w.wl : 0;
+            d.flags = (uint16_t)w.flags;
+            d.adapter = (int16_t)w.best_adapter;
+            d.avg_q = ave_q;
+            kc.a.dbg[mate][r] = d;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic path: any length, chunk loops over global memory (L1 resident after the first pass).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void process_generic(const KernelCtx &kc, WarpState &ws, uint32_t mate, uint32_t r, const Rec &rc)
+{
+    const DevOpts &o = kc.o;
+    const SmemHist &H = kc.H;
+    const StatsLayout &L = kc.a.L;
+    unsigned long long *const S = kc.S;
+    const uint32_t lane = kc.lane, R = H.rows;
+    const uint8_t *sp = kc.a.raw[mate] + rc.seq;
+    const signed char *qp = reinterpret_cast<const signed char *>(kc.a.raw[mate] + rc.qual);
+    const uint32_t len = rc.len;
+
+    uint32_t lead = 0, trail = len;
+    if (len) {
+        if (sp[0] == 'N') {
+            lead = len;
+            for (uint32_t b = 0; b < len; b += 32) {
+                const uint32_t p = b + lane;
+                const uint32_t m = __ballot_sync(0xffffffffu, p < len && sp[p] != 'N');
+                if (m) { lead = b + __ffs(m) - 1; break; }
+            }
+        }
+        if (sp[len - 1] == 'N') {
+            trail = 0;
+            for (int b = (int)((len - 1) & ~31u); b >= 0; b -= 32) {
+                const uint32_t p = b + lane;
+                const uint32_t m = __ballot_sync(0xffffffffu, p < len && sp[p] != 'N');
+                if (m) { trail = b + (31 - __clz(m)) + 1; break; }
+            }
+        }
+    }
+    const QualAt qa{qp, lead, trail, o.in_off};
+
+    int sum_q = 0;
+    uint32_t nA = 0, nT = 0, nC = 0, nG = 0, nN = 0;
+    bool bad_q = false;
+    for (uint32_t b = 0; b < len; b += 32) {
+        const uint32_t p = b + lane;
+        const bool in = p < len;
+        const uint32_t c = in ? sp[p] : 0;
+        int qc = in ? (int)qp[p] : o.in_off;
+        if (p < lead || p >= trail) qc = o.in_off;
+        if (in) sum_q += qc;
+        const int qv = max(0, qc - o.in_off);
+        bad_q |= in && (qv > FQ_MAX_QUALITY_SCORE);
+        const int bc = in ? (int)(H.lut()[c] >> 28) : 5;
+        if (in && qv <= FQ_MAX_QUALITY_SCORE) {
+            if (p < R) atomicAdd(&H.preq()[qv * R + p], 1u);
+            else gadd(&S[L.pre_q + (size_t)qv * L.rows + p], 1);
+        }
+        if (bc < 5) {
+            if (p < R) atomicAdd(&H.preb()[bc * R + p], 1u);
+            else gadd(&S[L.pre_b + (size_t)bc * L.rows + p], 1);
+        }
+        nA += __popc(__ballot_sync(0xffffffffu, bc == 0));
+        nT += __popc(__ballot_sync(0xffffffffu, bc == 1));
+        nC += __popc(__ballot_sync(0xffffffffu, bc == 2));
+        nG += __popc(__ballot_sync(0xffffffffu, bc == 3));
+        nN += __popc(__ballot_sync(0xffffffffu, bc == 4));
+    }
+    if (__any_sync(0xffffffffu, bad_q)) { ws.err |= kErrQualGt41; ws.err_rec = min(ws.err_rec, r); }
+    sum_q = warp_sum_i(sum_q);
+    {
+        const uint32_t mine = lane == 0 ? nA : lane == 1 ? nT : lane == 2 ? nC : lane == 3 ? nG : nN;
+        scalar_stats(kc, ws, 0, len, mine, (int)average_quality(sum_q, len, o.in_off));
+    }
+    ws.acc_reads += 1;
+    ws.acc_len += len;
+    ws.max_pre_rows = max(ws.max_pre_rows, len);
+
+    Window w = determine_window(kc, mate, r, len, qa);
+
+    float ave_q = 0.0f;
+    uint32_t wA = 0, wT = 0, wC = 0, wG = 0, wN = 0, n_lowg = 0;
+    if (w.ret) {
+        int sum_w = 0, max_qv = 0;
+        RunTracker rt;
+        for (uint32_t b = 0; b < w.wl; b += 32) {
+            const uint32_t i = b + lane;
+            const bool in = i < w.wl;
+            const uint32_t p = w.lo + i;
+            const uint32_t c = in ? sp[p] : 0;
+            int qc = in ? (int)qp[p] : o.in_off;
+            if (p < lead || p >= trail) qc = o.in_off;
+            if (in) sum_w += qc;
+            const int qv = max(0, qc - o.in_off);
+            max_qv = max(max_qv, in ? qv : 0);
+            const int bc = in ? (int)(H.lut()[c] >> 28) : 5;
+            const bool lowg = in && o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q;
+            rt.feed(__ballot_sync(0xffffffffu, c == 'N'));
+            n_lowg += __popc(__ballot_sync(0xffffffffu, lowg));
+            wA += __popc(__ballot_sync(0xffffffffu, bc == 0));
+            wT += __popc(__ballot_sync(0xffffffffu, bc == 1));
+            wC += __popc(__ballot_sync(0xffffffffu, bc == 2));
+            wG += __popc(__ballot_sync(0xffffffffu, bc == 3 && !lowg));
+            wN += __popc(__ballot_sync(0xffffffffu, bc == 4 || lowg));
+        }
+        sum_w = warp_sum_i(sum_w);
+        max_qv = __reduce_max_sync(0xffffffffu, max_qv);
+        apply_filters(kc, ws, w, r, rt.best, sum_w, wA, wT, wC, wG, max_qv, sp, qa, ave_q);
+    }
+    if (w.ret) {
+        w.flags |= FQ_RR_VALID;
+        ws.acc_trimmed += 1;
+        ws.acc_trimmed_len += w.wl;
+        ws.max_post_rows = max(ws.max_post_rows, w.off5 + w.wl);
+        ws.max_post_len1 = max(ws.max_post_len1, w.wl + 1);
+        const uint32_t mine = lane == 0 ? wA : lane == 1 ? wT : lane == 2 ? wC : lane == 3 ? wG : wN;
+        scalar_stats(kc, ws, 1, w.wl, mine, (int)ave_q);
+    }
+    const bool whole_removed = !w.ret;
+    if (whole_removed || w.lo > 0 || w.lo + w.wl < len || n_lowg) {
+        for (uint32_t b = 0; b < len; b += 32) {
+            const uint32_t p = b + lane;
+            if (p >= len) continue;
+            const bool inside = !whole_removed && p >= w.lo && p < w.lo + w.wl;
+            const uint32_t c = sp[p];
+            const int qv = qa(p);
+            if (!inside) {
+                const int bc = (int)(H.lut()[c] >> 28);
+                if (qv <= FQ_MAX_QUALITY_SCORE) {
+                    if (p < R) atomicAdd(&H.remq()[qv * R + p], 1u);
+                    else gadd(&S[L.rem_q + (size_t)qv * L.rows + p], 1);
+                }
+                if (bc < 5) {
+                    if (p < R) atomicAdd(&H.remb()[bc * R + p], 1u);
+                    else gadd(&S[L.rem_b + (size_t)bc * L.rows + p], 1);
+                }
+            } else if (n_lowg && o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q) {
+                if (p < R) { atomicAdd(&H.remb()[3 * R + p], 1u); atomicAdd(&H.g2n()[p], 1u); }
+                else { gadd(&S[L.rem_b + (size_t)3 * L.rows + p], 1); gadd(&S[L.g2n + p], 1); }
+            }
+        }
+    }
+    if (lane == 0) {
+        kc.a.res[mate][r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags));
+        if (kc.a.dbg[mate]) {
+            fq_read_result d;
+            d.offset_5 = w.off5;
+            d.length = w.ret ? w.wl : 0;
+            d.flags = (uint16_t)w.flags;
+            d.adapter = (int16_t)w.best_adapter;
+            d.avg_q = ave_q;
+            kc.a.dbg[mate][r] = d;
+        }
+    }
+}
+
+constexpr int kTrimThreads = 512;
+
+__global__ void __launch_bounds__(kTrimThreads, 2) k_trim(const TrimArgs a, const DevOpts o)
+{
+    SmemHist H{a.smem_rows, a.comp_key_len};
+    const size_t n_words = SmemHist::words(a.smem_rows, a.comp_key_len);
+    for (size_t i = threadIdx.x; i < n_words; i += blockDim.x) g_smem[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) H.lut()[i] = lut_entry(i);
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
@@ -178,328 +755,36 @@ __global__ void __launch_bounds__(512, 1) k_trim(const TrimArgs a, const DevOpts
     const StatsLayout &L = a.L;
     unsigned long long *const S = a.stats;
     const uint32_t R = H.rows;
-
-    // warp-uniform accumulators for the counters every read touches
-    uint32_t acc_reads = 0, acc_trimmed = 0;
-    unsigned long long acc_len = 0, acc_trimmed_len = 0;
-    uint32_t max_pre_rows = 0, max_post_rows = 0, max_post_len1 = 0;
-    uint32_t err = 0, err_rec = 0xffffffffu;
+    const KernelCtx kc{a, o, H, S, lane};
+    WarpState ws;
 
     for (uint32_t g = warp_global; g < total; g += n_warps) {
         const uint32_t mate = g >= a.n_rec ? 1 : 0;
         const uint32_t r = g - mate * a.n_rec;
         const Rec rc = a.rec[mate][r];
-        const uint8_t *sp = a.raw[mate] + rc.seq;
-        const signed char *qp = reinterpret_cast<const signed char *>(a.raw[mate] + rc.qual);
-        const uint32_t len = rc.len;
-        uint32_t flags = 0;
-
-        // ---- terminal 'N' runs (trim.cpp:1191-1216), uppercase only
-        uint32_t lead = 0, trail = len;
-        if (len) {
-            if (sp[0] == 'N') {
-                lead = len;
-                for (uint32_t b = 0; b < len; b += 32) {
-                    const uint32_t p = b + lane;
-                    const uint32_t m = __ballot_sync(0xffffffffu, p < len && sp[p] != 'N');
-                    if (m) { lead = b + __ffs(m) - 1; break; }
-                }
-            }
-            if (sp[len - 1] == 'N') {
-                trail = 0;
-                for (int b = (int)((len - 1) & ~31u); b >= 0; b -= 32) {
-                    const uint32_t p = b + lane;
-                    const uint32_t m = __ballot_sync(0xffffffffu, p < len && sp[p] != 'N');
-                    if (m) { trail = b + (31 - __clz(m)) + 1; break; }
-                }
-            }
-        }
-        const QualAt qa{qp, lead, trail, o.in_off};
-
-        // ---- PRE statistics over the whole (masked) read (trim.cpp:247-258)
-        int sum_q = 0;
-        uint32_t nA = 0, nT = 0, nC = 0, nG = 0, nN = 0;
-        bool bad_q = false;
-        for (uint32_t b = 0; b < len; b += 32) {
-            const uint32_t p = b + lane;
-            const bool in = p < len;
-            const uint32_t c = in ? sp[p] : 0;
-            int qc = in ? (int)qp[p] : o.in_off;
-            if (p < lead || p >= trail) qc = o.in_off;
-            if (in) sum_q += qc;
-            const int qv = max(0, qc - o.in_off);
-            bad_q |= in && (qv > FQ_MAX_QUALITY_SCORE);
-            const int bc = in ? base_code(c) : 5;
-            if (in && qv <= FQ_MAX_QUALITY_SCORE) {
-                if (p < R) atomicAdd(&H.preq[qv * R + p], 1u);
-                else gadd(&S[L.pre_q + (size_t)qv * L.rows + p], 1);
-            }
-            if (bc < 5) {
-                if (p < R) atomicAdd(&H.preb[bc * R + p], 1u);
-                else gadd(&S[L.pre_b + (size_t)bc * L.rows + p], 1);
-            }
-            nA += __popc(__ballot_sync(0xffffffffu, bc == 0));
-            nT += __popc(__ballot_sync(0xffffffffu, bc == 1));
-            nC += __popc(__ballot_sync(0xffffffffu, bc == 2));
-            nG += __popc(__ballot_sync(0xffffffffu, bc == 3));
-            nN += __popc(__ballot_sync(0xffffffffu, bc == 4));
-        }
-        if (__any_sync(0xffffffffu, bad_q)) { err |= kErrQualGt41; err_rec = min(err_rec, r); }
-        sum_q = warp_sum_i(sum_q);
-        {
-            const int qbin = (int)average_quality(sum_q, len, o.in_off);
-            uint32_t cnt = 0, bin = 0;
-            // lanes 0..5: composition bins (A,T,C,G,N,GC); lane 6: length hist; lanes 7,8: avg-Q hists
-            const uint32_t iC = composition_bin(len, nC), iG = composition_bin(len, nG);
-            if (lane == 0) bin = composition_bin(len, nA);
-            else if (lane == 1) bin = composition_bin(len, nT);
-            else if (lane == 2) bin = iC;
-            else if (lane == 3) bin = iG;
-            else if (lane == 4) bin = composition_bin(len, nN);
-            else if (lane == 5) bin = iG + iC;
-            if (lane < 6) gadd(&S[L.pre_comp + (size_t)lane * kCompBins + bin], 1);
-            else if (lane == 6) {
-                if (len <= R) atomicAdd(&H.prelen[len], 1u);
-                else gadd(&S[L.pre_len + len], 1);
-            } else if (lane == 7) atomicAdd(&H.qh[0 * kQualCols + min(max(qbin, 0), 41)], 1u);
-            else if (lane == 8) atomicAdd(&H.qh[1 * kQualCols + min(max(qbin, 0), 41)], len);
-            (void)cnt;
-        }
-        acc_reads += 1;
-        acc_len += len;
-        max_pre_rows = max(max_pre_rows, len);
-
-        // ---- window after adapter clip, 5'/3' clip (trim.cpp:270-314)
-        uint32_t lo = 0, wl = len, off5 = 0;
-        bool ret = true;
-        int best_adapter = -1;
-        if (o.filter_adapter && a.adp[mate]) {
-            const uint2 v = a.adp[mate][r];
-            best_adapter = a.adp_best[mate][r];
-            if (best_adapter >= 0) flags |= FQ_RR_ADAPTER;
-            if (len != v.y) {
-                lo = v.x;
-                wl = v.y;
-                off5 += (v.y == 0) ? len : v.x;
-            }
-        }
-        if (o.trim_5 && !o.qc_only) {
-            if (o.trim_5 > wl) wl = 0;
-            else { lo += o.trim_5; wl -= o.trim_5; off5 += o.trim_5; }
-        }
-        if (o.trim_3 && !o.qc_only) {
-            if (o.trim_3 > wl) wl = 0;
-            else wl -= o.trim_3;
-        }
-        if (wl < o.min_len || wl == 0) {                       // trim.cpp:317-323
-            if (lane == 0) { atomicAdd(&H.filt[FQ_READ_LENGTH], 1u); atomicAdd(&H.filt[FQ_BASE_LENGTH], wl); }
-            flags |= FQ_RR_F_LENGTH;
-            ret = false;
-        }
-        if (!o.qc_only && ret) {                               // trim.cpp:325-360
-            const uint32_t init_len = wl;
-            uint32_t f5 = 0;
-            if (o.mode == FQ_MODE_HARD) wl = hard_trim(qa, lo, (int)wl, o.quality, o.protect_5 != 0, f5);
-            else if (o.mode == FQ_MODE_BWA) wl = bwa_trim(qa, lo, (int)wl, o.quality, f5);
-            else wl = bwa_plus_trim(qa, lo, (int)wl, o.quality, o.protect_5 != 0, f5);
-            off5 += f5;
-            lo += f5;
-            if (init_len != wl) {
-                if (lane == 0) { atomicAdd(&H.filt[FQ_READ_QUAL_TRIM], 1u); atomicAdd(&H.filt[FQ_BASE_QUAL_TRIM], init_len - wl); }
-                flags |= FQ_RR_QUAL_TRIMMED;
-            }
-            if (wl < o.min_len || wl == 0) {
-                if (lane == 0) { atomicAdd(&H.filt[FQ_READ_LENGTH], 1u); atomicAdd(&H.filt[FQ_BASE_LENGTH], wl); }
-                flags |= FQ_RR_F_LENGTH;
-                ret = false;
-            }
-        }
-
-        // ---- filters on the window (trim.cpp:363-513)
-        float ave_q = 0.0f;
-        uint32_t wA = 0, wT = 0, wC = 0, wG = 0, wN = 0, n_lowg = 0;
-        if (ret) {
-            int sum_w = 0;
-            uint32_t run_carry = 0, max_run = 0;
-            int max_qv = 0;
-            for (uint32_t b = 0; b < wl; b += 32) {
-                const uint32_t i = b + lane;
-                const bool in = i < wl;
-                const uint32_t p = lo + i;
-                const uint32_t c = in ? sp[p] : 0;
-                int qc = in ? (int)qp[p] : o.in_off;
-                if (p < lead || p >= trail) qc = o.in_off;
-                if (in) sum_w += qc;
-                const int qv = max(0, qc - o.in_off);
-                max_qv = max(max_qv, in ? qv : 0);
-                const int bc = in ? base_code(c) : 5;
-                const bool lowg = in && o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q;
-                const uint32_t mN = __ballot_sync(0xffffffffu, c == 'N');
-                if (mN) {                                      // longest run of 'N' (count_poly_n, trim.cpp:578-597)
-                    uint32_t x = mN;
-                    const uint32_t head = __ffs(~x) ? (uint32_t)(__ffs(~x) - 1) : 32u;   // ones from bit 0
-                    max_run = max(max_run, run_carry + head);
-                    uint32_t k = 0;
-                    while (x) { x &= x >> 1; ++k; }
-                    max_run = max(max_run, k);
-                    run_carry = (mN == 0xffffffffu) ? run_carry + 32 : (uint32_t)__clz(~mN);
-                } else run_carry = 0;
-                const uint32_t mLG = __ballot_sync(0xffffffffu, lowg);
-                n_lowg += __popc(mLG);
-                wA += __popc(__ballot_sync(0xffffffffu, bc == 0));
-                wT += __popc(__ballot_sync(0xffffffffu, bc == 1));
-                wC += __popc(__ballot_sync(0xffffffffu, bc == 2));
-                wG += __popc(__ballot_sync(0xffffffffu, bc == 3 && !lowg));
-                wN += __popc(__ballot_sync(0xffffffffu, bc == 4 || lowg));
-            }
-            sum_w = warp_sum_i(sum_w);
-            if (max_run >= o.max_poly_n) {                     // trim.cpp:363-371
-                if (lane == 0) { atomicAdd(&H.filt[FQ_READ_NN], 1u); atomicAdd(&H.filt[FQ_BASE_NN], wl); }
-                flags |= FQ_RR_F_NN;
-                if (!o.qc_only) ret = false;
-            }
-            ave_q = average_quality(sum_w, wl, o.in_off);
-            if (ret && ave_q < o.avg_q) {                      // trim.cpp:374-382
-                if (lane == 0) { atomicAdd(&H.filt[FQ_READ_AVG_Q], 1u); atomicAdd(&H.filt[FQ_BASE_AVG_Q], wl); }
-                flags |= FQ_RR_F_AVGQ;
-                ret = false;
-            }
-            if (ret) {                                         // low complexity, trim.cpp:405-513
-                float norm = (float)(1.0 / (double)wl);
-                bool lowc = __fmul_rn((float)wA, norm) > o.lc || __fmul_rn((float)wT, norm) > o.lc ||
-                            __fmul_rn((float)wG, norm) > o.lc || __fmul_rn((float)wC, norm) > o.lc;
-                if (!lowc) {
-                    norm = norm * 2.0f;
-                    // a dinucleotide count can not exceed the second largest base count
-                    const uint32_t m1 = max(max(wA, wT), max(wC, wG));
-                    const uint32_t second = max(max(min(wA, wT), min(wC, wG)), min(max(wA, wT), max(wC, wG)));
-                    (void)m1;
-                    if (__fmul_rn((float)second, norm) > o.lc) {
-                        uint32_t dc[16];
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) dc[k] = 0;
-                        int prev_carry = 4;
-                        for (uint32_t b = 0; b < wl; b += 32) {
-                            const uint32_t i = b + lane;
-                            const bool in = i < wl;
-                            const uint32_t p = lo + i;
-                            const uint32_t c = in ? sp[p] : 0;
-                            int cur = in ? base_code(c) : 4;
-                            if (cur > 3) cur = 4;
-                            if (in && o.replace_q > 0 && c == 'G' && qa(p) < (int)o.replace_q) cur = 4;
-                            int prev = __shfl_up_sync(0xffffffffu, cur, 1);
-                            if (lane == 0) prev = prev_carry;
-                            prev_carry = __shfl_sync(0xffffffffu, cur, 31);
-                            const int code = (in && cur != 4 && prev != 4 && cur != prev) ? ((prev << 2) | cur) : -1;
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) dc[k] += __popc(__ballot_sync(0xffffffffu, code == k));
-                        }
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) lowc |= __fmul_rn((float)dc[k], norm) > o.lc;
-                    }
-                }
-                if (lowc) {
-                    if (lane == 0) { atomicAdd(&H.filt[FQ_READ_LOW_COMPLEXITY], 1u); atomicAdd(&H.filt[FQ_BASE_LOW_COMPLEXITY], wl); }
-                    flags |= FQ_RR_F_LOWCOMP;
-                    ret = false;
-                }
-            }
-            if (ret && o.in_off != o.out_off) {                // re-encode overflow, trim.cpp:516-525
-                if (o.out_off + 41 > 127) {
-                    max_qv = max(max_qv, __shfl_xor_sync(0xffffffffu, max_qv, 16));
-                    max_qv = max(max_qv, __shfl_xor_sync(0xffffffffu, max_qv, 8));
-                    max_qv = max(max_qv, __shfl_xor_sync(0xffffffffu, max_qv, 4));
-                    max_qv = max(max_qv, __shfl_xor_sync(0xffffffffu, max_qv, 2));
-                    max_qv = max(max_qv, __shfl_xor_sync(0xffffffffu, max_qv, 1));
-                    if (max_qv + o.out_off > 127) { err |= kErrReencode; err_rec = min(err_rec, r); }
-                }
-            }
-        }
-
-        // ---- POST statistics (trim.cpp:527-548) as "removed" updates
-        if (ret) {
-            flags |= FQ_RR_VALID;
-            acc_trimmed += 1;
-            acc_trimmed_len += wl;
-            max_post_rows = max(max_post_rows, off5 + wl);
-            max_post_len1 = max(max_post_len1, wl + 1);
-            const int qbin = min(max((int)ave_q, 0), 41);
-            uint32_t bin = 0;
-            const uint32_t iC = composition_bin(wl, wC), iG = composition_bin(wl, wG);
-            if (lane == 0) bin = composition_bin(wl, wA);
-            else if (lane == 1) bin = composition_bin(wl, wT);
-            else if (lane == 2) bin = iC;
-            else if (lane == 3) bin = iG;
-            else if (lane == 4) bin = composition_bin(wl, wN);
-            else if (lane == 5) bin = iG + iC;
-            if (lane < 6) gadd(&S[L.post_comp + (size_t)lane * kCompBins + bin], 1);
-            else if (lane == 6) {
-                if (wl <= R) atomicAdd(&H.postlen[wl], 1u);
-                else gadd(&S[L.post_len + wl], 1);
-            } else if (lane == 7) atomicAdd(&H.qh[2 * kQualCols + qbin], 1u);
-            else if (lane == 8) atomicAdd(&H.qh[3 * kQualCols + qbin], wl);
-        }
-        const bool whole = !ret;
-        if (whole || lo > 0 || lo + wl < len || n_lowg) {
-            for (uint32_t b = 0; b < len; b += 32) {
-                const uint32_t p = b + lane;
-                if (p >= len) continue;
-                const bool inside = !whole && p >= lo && p < lo + wl;
-                const uint32_t c = sp[p];
-                const int qv = qa(p);
-                if (!inside) {
-                    const int bc = base_code(c);
-                    if (qv <= FQ_MAX_QUALITY_SCORE) {
-                        if (p < R) atomicAdd(&H.remq[qv * R + p], 1u);
-                        else gadd(&S[L.rem_q + (size_t)qv * L.rows + p], 1);
-                    }
-                    if (bc < 5) {
-                        if (p < R) atomicAdd(&H.remb[bc * R + p], 1u);
-                        else gadd(&S[L.rem_b + (size_t)bc * L.rows + p], 1);
-                    }
-                } else if (n_lowg && o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q) {
-                    // surviving G -> N replacement: leaves column G, enters column N
-                    if (p < R) { atomicAdd(&H.remb[3 * R + p], 1u); atomicAdd(&H.g2n[p], 1u); }
-                    else { gadd(&S[L.rem_b + (size_t)3 * L.rows + p], 1); gadd(&S[L.g2n + p], 1); }
-                }
-            }
-        }
-        if (lane == 0) {
-            a.res[mate][r] = make_uint2(off5, pack_len_flags(ret ? wl : 0, flags));
-            if (a.dbg[mate]) {
-                fq_read_result d;
-                d.offset_5 = off5;
-                d.length = ret ? wl : 0;
-                d.flags = (uint16_t)flags;
-                d.adapter = (int16_t)best_adapter;
-                d.avg_q = ave_q;
-                a.dbg[mate][r] = d;
-            }
-        }
+        if (rc.len <= 160 && rc.len <= R) process_fast<5>(kc, ws, mate, r, rc);
+        else if (rc.len <= 320 && rc.len <= R) process_fast<10>(kc, ws, mate, r, rc);
+        else process_generic(kc, ws, mate, r, rc);
     }
 
     // ---- merge: warp accumulators -> shared -> global (matrix.h:111-142 / trim.cpp:120-154)
     if (lane == 0) {
-        if (acc_reads) {
-            gadd(&S[L.filter + FQ_TOTAL_COUNT], acc_reads);
-            gadd(&S[L.filter + FQ_TOTAL_NUMBER], acc_reads);
-            gadd(&S[L.filter + FQ_TOTAL_LENGTH], acc_len);
+        if (ws.acc_reads) {
+            gadd(&S[L.filter + FQ_TOTAL_COUNT], ws.acc_reads);
+            gadd(&S[L.filter + FQ_TOTAL_NUMBER], ws.acc_reads);
+            gadd(&S[L.filter + FQ_TOTAL_LENGTH], ws.acc_len);
+            atomicMax(&a.rows->pre_rows, ws.max_pre_rows);
+            atomicMax(&a.rows->pre_len_size, ws.max_pre_rows + 1);
         }
-        if (acc_trimmed) {
-            gadd(&S[L.filter + FQ_TOTAL_TRIMMED_NUMBER], acc_trimmed);
-            gadd(&S[L.filter + FQ_TOTAL_TRIMMED_LENGTH], acc_trimmed_len);
+        if (ws.acc_trimmed) {
+            gadd(&S[L.filter + FQ_TOTAL_TRIMMED_NUMBER], ws.acc_trimmed);
+            gadd(&S[L.filter + FQ_TOTAL_TRIMMED_LENGTH], ws.acc_trimmed_len);
+            atomicMax(&a.rows->post_rows, ws.max_post_rows);
+            atomicMax(&a.rows->post_len_size, ws.max_post_len1);
         }
-        if (acc_reads) {
-            atomicMax(&a.rows->pre_rows, max_pre_rows);
-            atomicMax(&a.rows->pre_len_size, max_pre_rows + 1);
-        }
-        if (acc_trimmed) {
-            atomicMax(&a.rows->post_rows, max_post_rows);
-            atomicMax(&a.rows->post_len_size, max_post_len1);
-        }
-        if (err) {
-            atomicOr(&a.info->err, err);
-            atomicMin(&a.info->err_record, err_rec);
+        if (ws.err) {
+            atomicOr(&a.info->err, ws.err);
+            atomicMin(&a.info->err_record, ws.err_rec);
         }
     }
     __syncthreads();
@@ -511,20 +796,36 @@ __global__ void __launch_bounds__(512, 1) k_trim(const TrimArgs a, const DevOpts
             if (v) gadd(&S[dst + (i / w) * W + (i % w)], v);
         }
     };
-    flush(H.preq, L.pre_q, kQualCols, false);
-    flush(H.remq, L.rem_q, kQualCols, false);
-    flush(H.preb, L.pre_b, kBaseCols, false);
-    flush(H.remb, L.rem_b, kBaseCols, false);
-    flush(H.g2n, L.g2n, 1, false);
-    flush(H.prelen, L.pre_len, 1, true);
-    flush(H.postlen, L.post_len, 1, true);
+    flush(H.preq(), L.pre_q, kQualCols, false);
+    flush(H.remq(), L.rem_q, kQualCols, false);
+    flush(H.preb(), L.pre_b, kBaseCols, false);
+    flush(H.remb(), L.rem_b, kBaseCols, false);
+    flush(H.g2n(), L.g2n, 1, false);
+    flush(H.prelen(), L.pre_len, 1, true);
+    flush(H.postlen(), L.post_len, 1, true);
     for (uint32_t i = threadIdx.x; i < 4 * kQualCols; i += blockDim.x) {
-        const uint32_t v = H.qh[i];
+        const uint32_t v = H.qh()[i];
         if (v) gadd(&S[(i < kQualCols ? L.pre_rq : i < 2 * kQualCols ? L.pre_bq : i < 3 * kQualCols ? L.post_rq : L.post_bq) + (i % kQualCols)], v);
     }
     for (uint32_t i = threadIdx.x; i < FQ_NUM_STAT; i += blockDim.x) {
-        const uint32_t v = H.filt[i];
+        const uint32_t v = H.filt()[i];
         if (v) gadd(&S[L.filter + i], v);
+    }
+    for (uint32_t i = threadIdx.x; i < 12; i += blockDim.x) {
+        const uint32_t v = H.zero()[i];
+        if (v) gadd(&S[(i < 6 ? L.pre_comp : L.post_comp) + (size_t)(i % 6) * kCompBins], v);
+    }
+    if (H.key != 0xffffffffu) {
+        const uint32_t kw = H.key + 1;
+        const float norm = composition_norm(H.key);
+        for (uint32_t i = threadIdx.x; i < 14 * kw; i += blockDim.x) {
+            const uint32_t v = H.compk()[i];
+            if (!v) continue;
+            const uint32_t which = i / (7 * kw), row = (i / kw) % 7, cnt = i % kw;
+            const uint32_t hist = row < 5 ? row : 5;
+            const uint32_t bin = composition_bin_n(norm, cnt) - (row == 6 ? 1u : 0u);
+            gadd(&S[(which ? L.post_comp : L.pre_comp) + (size_t)hist * kCompBins + bin], v);
+        }
     }
 }
 
