@@ -147,9 +147,8 @@ def test_long_reads_beyond_shared_rows():
 
 def test_errors_match_reference_text():
     ok = fastq_bytes([("@a", "ACGT" * 20, "I" * 79 + "#")])
-    with Engine(Options()) as e:                                     # Q > 41
+    with Engine(Options(input_quality_offset=33)) as e:              # Q > 41 (with autodetect 'K' would mean ASCII-64)
         bad = fastq_bytes([("@a", "ACGT" * 20, "K" * 79 + "#")])
-        e.autodetect(bad)
         with pytest.raises(FaqcsError) as ei:
             e.process(bad)
         assert "greater than the maximum allowed quality score" in str(ei.value)
