@@ -165,28 +165,6 @@ struct SmemHist {
 
 __device__ __forceinline__ void gadd(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 
-// Warp-uniform state carried across the reads a warp processes.
-struct WarpState {
-    uint32_t acc_reads = 0, acc_trimmed = 0;
-    unsigned long long acc_len = 0, acc_trimmed_len = 0;
-    uint32_t max_pre_rows = 0, max_post_rows = 0, max_post_len1 = 0;
-    uint32_t err = 0, err_rec = 0xffffffffu;
-    uint32_t c_len = 0xffffffffu;   // cached divisions (most runs have one read length)
-    float c_norm = 0.0f;
-    uint32_t c_wl = 0xffffffffu;
-    float c_lcnorm = 0.0f;
-    __device__ __forceinline__ float norm_for(uint32_t len)
-    {
-        if (len != c_len) { c_len = len; c_norm = composition_norm(len); }
-        return c_norm;
-    }
-    __device__ __forceinline__ float lcnorm_for(uint32_t wl)
-    {
-        if (wl != c_wl) { c_wl = wl; c_lcnorm = (float)(1.0 / (double)wl); }   // trim.cpp:483
-        return c_lcnorm;
-    }
-};
-
 struct KernelCtx {
     const TrimArgs &a;
     const DevOpts &o;
@@ -197,10 +175,10 @@ struct KernelCtx {
 
 // One increment in each of the six composition histograms (trim.cpp:860-874).  `cnt` holds the
 // count of class `lane` in lanes 0..4.  which = 0 (pre) / 1 (post).
-__device__ __forceinline__ void composition_update(const KernelCtx &kc, WarpState &ws, int which, uint32_t len, uint32_t cnt)
+__device__ __forceinline__ void composition_update(const KernelCtx &kc, int which, uint32_t len, uint32_t cnt)
 {
     const uint32_t lane = kc.lane;
-    const float norm = ws.norm_for(len);
+    const float norm = composition_norm(len);
     const uint32_t bin = composition_bin_n(norm, cnt);
     const uint32_t iC = __shfl_sync(0xffffffffu, bin, 2), iG = __shfl_sync(0xffffffffu, bin, 3);
     const size_t comp = which ? kc.a.L.post_comp : kc.a.L.pre_comp;
@@ -222,9 +200,9 @@ __device__ __forceinline__ void composition_update(const KernelCtx &kc, WarpStat
 }
 
 // Lane-parallel scalar statistics of one read: composition, length histogram, avg-Q histograms.
-__device__ __forceinline__ void scalar_stats(const KernelCtx &kc, WarpState &ws, int which, uint32_t len, uint32_t cnt, int qbin)
+__device__ __forceinline__ void scalar_stats(const KernelCtx &kc, int which, uint32_t len, uint32_t cnt, int qbin)
 {
-    composition_update(kc, ws, which, len, cnt);
+    composition_update(kc, which, len, cnt);
     const uint32_t lane = kc.lane;
     qbin = min(max(qbin, 0), 41);
     if (lane == 6) {
@@ -323,7 +301,7 @@ __device__ __forceinline__ bool dinucleotide_low_complexity(const KernelCtx &kc,
 }
 
 // Filters on the window (trim.cpp:363-513).  Counts are of the window after G->N replacement.
-__device__ __forceinline__ void apply_filters(const KernelCtx &kc, WarpState &ws, Window &w, uint32_t r, uint32_t max_run, int sum_w,
+__device__ __forceinline__ void apply_filters(const KernelCtx &kc, Window &w, uint32_t r, uint32_t max_run, int sum_w,
                                               uint32_t wA, uint32_t wT, uint32_t wC, uint32_t wG, int max_qv, const uint8_t *sp,
                                               const QualAt &qa, float &ave_q)
 {
@@ -342,7 +320,7 @@ __device__ __forceinline__ void apply_filters(const KernelCtx &kc, WarpState &ws
         w.ret = false;
     }
     if (w.ret) {                                                // low complexity, trim.cpp:405-513
-        const float norm = ws.lcnorm_for(w.wl);
+        const float norm = (float)(1.0 / (double)w.wl);          // trim.cpp:483
         bool lowc = __fmul_rn((float)wA, norm) > o.lc || __fmul_rn((float)wT, norm) > o.lc ||
                     __fmul_rn((float)wG, norm) > o.lc || __fmul_rn((float)wC, norm) > o.lc;
         if (!lowc) {
@@ -357,9 +335,9 @@ __device__ __forceinline__ void apply_filters(const KernelCtx &kc, WarpState &ws
             w.ret = false;
         }
     }
-    if (w.ret && o.in_off != o.out_off && max_qv + o.out_off > 127) {      // trim.cpp:516-525
-        ws.err |= kErrReencode;
-        ws.err_rec = min(ws.err_rec, r);
+    if (w.ret && o.in_off != o.out_off && max_qv + o.out_off > 127 && lane == 0) {      // trim.cpp:516-525
+        atomicOr(&kc.a.info->err, kErrReencode);
+        atomicMin(&kc.a.info->err_record, r);
     }
 }
 
@@ -384,19 +362,36 @@ struct RunTracker {
 __device__ __forceinline__ uint32_t unpack5(uint32_t packed, int field) { return (packed >> (5 * field)) & 31u; }
 
 // ---------------------------------------------------------------------------------------------
-// Fast path: reads of up to 32 * K bases, everything from registers.
+// Batched fast path.  A warp takes 32 reads at a time.  Per-BASE work (loads, histogram
+// updates, class counts) is done cooperatively, one read after the other, lanes striped over
+// positions.  Per-READ scalar work (window, quality trim, filters, bins, verdict) is done by one
+// lane per read, so its cost is amortised over 32 reads.  Rare per-base follow-ups (bases that
+// were trimmed away, discarded reads, dinucleotide counts, exact N runs) are cooperative again,
+// driven by ballots.
 // ---------------------------------------------------------------------------------------------
+
+// What phase 1 leaves in the lane that owns the read.
+struct LaneRead {
+    Rec rc;
+    int sum_q;              // sum of (masked) raw quality chars of the whole read
+    uint32_t cnt_atc;       // 10-bit fields A,T,C
+    uint32_t cnt_gn;        // 10-bit fields G,N
+    uint32_t lead, trail;   // terminal-N mask bounds
+    uint32_t run_whole;     // longest 'N' run of the whole read (0 if fewer than -n 'N's)
+    bool done;              // already fully processed (generic path) or out of range
+};
+
+__device__ __forceinline__ uint32_t f10(uint32_t packed, int field) { return (packed >> (10 * field)) & 1023u; }
+
+// Phase 1 for the read owned by lane j: PRE matrices + per-read summaries.
 template <int K>
-__device__ __forceinline__ void process_fast(const KernelCtx &kc, WarpState &ws, uint32_t mate, uint32_t r, const Rec &rc)
+__device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *sp, const signed char *qp, uint32_t len, uint32_t r,
+                                       int &out_sum, uint32_t &out_atc, uint32_t &out_gn, uint32_t &out_lead, uint32_t &out_trail,
+                                       uint32_t &out_run, uint32_t &err, uint32_t &err_rec)
 {
     const DevOpts &o = kc.o;
     const SmemHist &H = kc.H;
     const uint32_t lane = kc.lane, R = H.rows;
-    const uint8_t *sp = kc.a.raw[mate] + rc.seq;
-    const signed char *qp = reinterpret_cast<const signed char *>(kc.a.raw[mate] + rc.qual);
-    const uint32_t len = rc.len;
-
-    // ---- load the read once, byte-striped
     uint32_t c[K];
     int q[K];
 #pragma unroll
@@ -406,18 +401,19 @@ __device__ __forceinline__ void process_fast(const KernelCtx &kc, WarpState &ws,
         q[k] = o.in_off;
         if (p < len) { c[k] = sp[p]; q[k] = (int)qp[p]; }
     }
-    // ---- terminal 'N' runs (trim.cpp:1191-1216), uppercase only
     uint32_t nm[K], any_n = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) { nm[k] = __ballot_sync(0xffffffffu, c[k] == 'N'); any_n |= nm[k]; }
-    uint32_t lead = 0, trail = len;
+    uint32_t lead = 0, trail = len, run = 0;
     if (any_n) {
         bool last_n = false;
+        uint32_t n_count = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k)
+        for (int k = 0; k < K; ++k) {
             if ((uint32_t)k == ((len - 1) >> 5)) last_n = (nm[k] >> ((len - 1) & 31)) & 1u;
-        if ((nm[0] & 1u) || last_n) {
-            // ones from position 0 / zeros back from position len-1
+            n_count += __popc(nm[k]);
+        }
+        if ((nm[0] & 1u) || last_n) {                            // terminal 'N' runs (trim.cpp:1191-1216)
             bool open = true;
             lead = 0;
 #pragma unroll
@@ -431,7 +427,6 @@ __device__ __forceinline__ void process_fast(const KernelCtx &kc, WarpState &ws,
                 }
             }
             open = true;
-            trail = len;
 #pragma unroll
             for (int k = K - 1; k >= 0; --k) {
                 if (open && (uint32_t)(k * 32) < len) {
@@ -442,155 +437,224 @@ __device__ __forceinline__ void process_fast(const KernelCtx &kc, WarpState &ws,
                     else trail = k * 32;
                 }
             }
-            if (lead >= len) trail = 0;     // all 'N'
+            if (lead >= len) trail = 0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const uint32_t p = k * 32 + lane;
                 if (p < lead || p >= trail) q[k] = o.in_off;
             }
         }
+        if (n_count >= o.max_poly_n) {                           // candidate for the N filter: longest run of the whole read
+            RunTracker rt;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if ((uint32_t)(k * 32) < len) rt.feed(nm[k]);
+            run = rt.best;
+        }
     }
-    const QualAt qa{qp, lead, trail, o.in_off};
-
-    // ---- PRE statistics (trim.cpp:247-258)
     int sum_q = 0;
-    uint32_t packed = 0, codes = 0;
+    uint32_t packed = 0;
     bool bad_q = false;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if ((uint32_t)(k * 32) < len) {
             const uint32_t p = k * 32 + lane;
-            const bool in = p < len;
-            const uint32_t e = H.lut()[c[k]];
-            const uint32_t code = e >> 28;
-            const int qv = max(0, q[k] - o.in_off);
-            if (in) {
+            if (p < len) {
+                const uint32_t e = H.lut()[c[k]];
+                const uint32_t code = e >> 28;
+                const int qv = max(0, q[k] - o.in_off);
                 sum_q += q[k];
                 packed += e & 0x1ffffffu;
                 bad_q |= qv > FQ_MAX_QUALITY_SCORE;
                 if (qv <= FQ_MAX_QUALITY_SCORE) atomicAdd(&H.preq()[qv * R + p], 1u);
                 if (code < 5) atomicAdd(&H.preb()[code * R + p], 1u);
             }
-            codes |= code << (3 * k);
         }
     }
-    if (__any_sync(0xffffffffu, bad_q)) { ws.err |= kErrQualGt41; ws.err_rec = min(ws.err_rec, r); }
-    sum_q = warp_sum_i(sum_q);
-    // per-class totals: 10-bit fields (A,T,C) and (G,N); a read has at most 320 bases
-    const uint32_t tATC = warp_sum(unpack5(packed, 0) | (unpack5(packed, 1) << 10) | (unpack5(packed, 2) << 20));
-    const uint32_t tGN = warp_sum(unpack5(packed, 3) | (unpack5(packed, 4) << 10));
-    const uint32_t nA = tATC & 1023u, nT = (tATC >> 10) & 1023u, nC = tATC >> 20, nG = tGN & 1023u, nN = tGN >> 10;
-    {
-        const uint32_t mine = lane == 0 ? nA : lane == 1 ? nT : lane == 2 ? nC : lane == 3 ? nG : nN;
-        scalar_stats(kc, ws, 0, len, mine, (int)average_quality(sum_q, len, o.in_off));
-    }
-    ws.acc_reads += 1;
-    ws.acc_len += len;
-    ws.max_pre_rows = max(ws.max_pre_rows, len);
+    if (__any_sync(0xffffffffu, bad_q)) { err |= kErrQualGt41; err_rec = min(err_rec, r); }
+    out_sum = warp_sum_i(sum_q);
+    out_atc = warp_sum(unpack5(packed, 0) | (unpack5(packed, 1) << 10) | (unpack5(packed, 2) << 20));
+    out_gn = warp_sum(unpack5(packed, 3) | (unpack5(packed, 4) << 10));
+    out_lead = lead;
+    out_trail = trail;
+    out_run = run;
+}
 
-    // ---- window
-    Window w = determine_window(kc, mate, r, len, qa);
-
-    // ---- window statistics and filters
-    float ave_q = 0.0f;
-    uint32_t wA = nA, wT = nT, wC = nC, wG = nG, wN = nN, n_lowg = 0;
-    if (w.ret) {
-        int sum_w = sum_q, max_qv = 0;
-        const bool whole = (w.lo == 0 && w.wl == len);
-        const bool need_max = o.in_off != o.out_off && o.out_off + FQ_MAX_QUALITY_SCORE > 127;   // re-encode can overflow
-        if (!whole || o.replace_q > 0 || need_max) {
-            uint32_t pk = 0;
-            int sw = 0, mq = 0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if ((uint32_t)(k * 32) < len) {
-                    const uint32_t p = k * 32 + lane;
-                    const bool inw = p >= w.lo && p < w.lo + w.wl;
-                    uint32_t code = (codes >> (3 * k)) & 7u;
-                    const int qv = max(0, q[k] - o.in_off);
-                    const bool lowg = inw && o.replace_q > 0 && c[k] == 'G' && qv < (int)o.replace_q;
-                    if (lowg) code = 4;
-                    if (inw) {
-                        sw += q[k];               // raw quality chars (terminal-N positions hold the offset char)
-                        mq = max(mq, qv);
-                        if (code < 5) pk += 1u << (5 * code);
-                    }
-                    n_lowg += __popc(__ballot_sync(0xffffffffu, lowg));
-                }
-            }
-            sum_w = warp_sum_i(sw);
-            max_qv = __reduce_max_sync(0xffffffffu, mq);
-            const uint32_t uATC = warp_sum(unpack5(pk, 0) | (unpack5(pk, 1) << 10) | (unpack5(pk, 2) << 20));
-            const uint32_t uGN = warp_sum(unpack5(pk, 3) | (unpack5(pk, 4) << 10));
-            wA = uATC & 1023u; wT = (uATC >> 10) & 1023u; wC = uATC >> 20; wG = uGN & 1023u; wN = uGN >> 10;
-        }
-        uint32_t max_run = 0;
-        if (any_n) {                                            // longest 'N' run inside the window
-            RunTracker rt;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if ((uint32_t)(k * 32) < len) {
-                    // window bits of this word
-                    const int lo_b = max((int)w.lo - k * 32, 0), hi_b = min((int)(w.lo + w.wl) - k * 32, 32);
-                    uint32_t wm = 0;
-                    if (lo_b < hi_b) wm = ((hi_b - lo_b) == 32 ? 0xffffffffu : ((1u << (hi_b - lo_b)) - 1u)) << lo_b;
-                    rt.feed(nm[k] & wm);
-                }
-            }
-            max_run = rt.best;
-        }
-        apply_filters(kc, ws, w, r, max_run, sum_w, wA, wT, wC, wG, max_qv, sp, qa, ave_q);
-    }
-
-    // ---- POST statistics (trim.cpp:527-548) as "removed" updates
-    if (w.ret) {
-        w.flags |= FQ_RR_VALID;
-        ws.acc_trimmed += 1;
-        ws.acc_trimmed_len += w.wl;
-        ws.max_post_rows = max(ws.max_post_rows, w.off5 + w.wl);
-        ws.max_post_len1 = max(ws.max_post_len1, w.wl + 1);
-        const uint32_t mine = lane == 0 ? wA : lane == 1 ? wT : lane == 2 ? wC : lane == 3 ? wG : wN;
-        scalar_stats(kc, ws, 1, w.wl, mine, (int)ave_q);
-    }
-    const bool whole_removed = !w.ret;
-    if (whole_removed || w.lo > 0 || w.lo + w.wl < len || n_lowg) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if ((uint32_t)(k * 32) < len) {
-                const uint32_t p = k * 32 + lane;
-                if (p < len) {
-                    const bool inside = !whole_removed && p >= w.lo && p < w.lo + w.wl;
-                    const uint32_t code = (codes >> (3 * k)) & 7u;
-                    const int qv = max(0, q[k] - o.in_off);
-                    if (!inside) {
-                        if (qv <= FQ_MAX_QUALITY_SCORE) atomicAdd(&H.remq()[qv * R + p], 1u);
-                        if (code < 5) atomicAdd(&H.remb()[code * R + p], 1u);
-                    } else if (n_lowg && c[k] == 'G' && qv < (int)o.replace_q) {
-                        atomicAdd(&H.remb()[3 * R + p], 1u);      // surviving G -> N: leaves column G, enters column N
-                        atomicAdd(&H.g2n()[p], 1u);
-                    }
-                }
+// Cooperative pass over one read for the "removed" histograms.
+//   mode 0: positions OUTSIDE the window -> rem hists; returns their class counts / quality sum;
+//           with --replace_to_N_q also counts the G->N candidates INSIDE the window.
+//   mode 1: positions INSIDE the window -> rem hists (read turned out invalid).
+//   mode 2: G->N positions inside the window of a valid read: leave column G, enter column N.
+__device__ __forceinline__ void removed_pass(const KernelCtx &kc, int mode, const uint8_t *sp, const signed char *qp, uint32_t len,
+                                             uint32_t lo, uint32_t wl, uint32_t lead, uint32_t trail, uint32_t &r_atc, uint32_t &r_gn,
+                                             int &r_sum, uint32_t &n_lowg, int &max_qv)
+{
+    const DevOpts &o = kc.o;
+    const SmemHist &H = kc.H;
+    const StatsLayout &L = kc.a.L;
+    const uint32_t lane = kc.lane, R = H.rows;
+    uint32_t pk = 0, lowg_cnt = 0;
+    int sum = 0, mq = 0;
+    for (uint32_t b = 0; b < len; b += 32) {
+        const uint32_t p = b + lane;
+        // skip chunks that cannot contain work
+        const bool chunk_inside = b >= lo && b + 32 <= lo + wl;
+        if (mode == 0 && chunk_inside && o.replace_q == 0 && max_qv < 0) continue;
+        if (mode != 0 && (b + 32 <= lo || b >= lo + wl)) continue;
+        if (p >= len) continue;
+        const bool inside = p >= lo && p < lo + wl;
+        const uint32_t c = sp[p];
+        int qc = (int)qp[p];
+        if (p < lead || p >= trail) qc = o.in_off;
+        const int qv = max(0, qc - o.in_off);
+        const uint32_t code = H.lut()[c] >> 28;
+        const bool lowg = inside && o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q;
+        if (mode == 0) {
+            if (!inside) {
+                sum += qc;
+                if (code < 5) pk += 1u << (5 * code);
+            } else {
+                lowg_cnt += lowg;
+                mq = max(mq, qv);
             }
         }
-    }
-    if (lane == 0) {
-        kc.a.res[mate][r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags));
-        if (kc.a.dbg[mate]) {
-            fq_read_result d;
-            d.offset_5 = w.off5;
-            d.length = w.ret ? w.wl : 0;
-            d.flags = (uint16_t)w.flags;
-            d.adapter = (int16_t)w.best_adapter;
-            d.avg_q = ave_q;
-            kc.a.dbg[mate][r] = d;
+        const bool to_rem = (mode == 0 && !inside) || (mode == 1 && inside);
+        if (to_rem) {
+            if (qv <= FQ_MAX_QUALITY_SCORE) {
+                if (p < R) atomicAdd(&H.remq()[qv * R + p], 1u);
+                else gadd(&kc.S[L.rem_q + (size_t)qv * L.rows + p], 1);
+            }
+            if (code < 5) {
+                if (p < R) atomicAdd(&H.remb()[code * R + p], 1u);
+                else gadd(&kc.S[L.rem_b + (size_t)code * L.rows + p], 1);
+            }
+        } else if (mode == 2 && lowg) {
+            if (p < R) { atomicAdd(&H.remb()[3 * R + p], 1u); atomicAdd(&H.g2n()[p], 1u); }
+            else { gadd(&kc.S[L.rem_b + (size_t)3 * L.rows + p], 1); gadd(&kc.S[L.g2n + p], 1); }
         }
     }
+    if (mode == 0) {
+        r_sum = warp_sum_i(sum);
+        r_atc = warp_sum(unpack5(pk, 0) | (unpack5(pk, 1) << 10) | (unpack5(pk, 2) << 20));
+        r_gn = warp_sum(unpack5(pk, 3) | (unpack5(pk, 4) << 10));
+        n_lowg = warp_sum(lowg_cnt);
+        max_qv = __reduce_max_sync(0xffffffffu, mq);
+    }
+}
+
+// Longest 'N' run inside [lo, lo+wl), cooperative, from global memory (rare).
+__device__ __forceinline__ uint32_t window_n_run(const KernelCtx &kc, const uint8_t *sp, uint32_t lo, uint32_t wl)
+{
+    RunTracker rt;
+    for (uint32_t b = 0; b < wl; b += 32) {
+        const uint32_t i = b + kc.lane;
+        rt.feed(__ballot_sync(0xffffffffu, i < wl && sp[lo + i] == 'N'));
+    }
+    return rt.best;
+}
+
+// One lane: the six composition increments of one read (trim.cpp:860-874).
+__device__ __forceinline__ void lane_composition(const KernelCtx &kc, int which, uint32_t len, uint32_t atc, uint32_t gn)
+{
+    const SmemHist &H = kc.H;
+    const float norm = composition_norm(len);
+    const uint32_t cnt[5] = {f10(atc, 0), f10(atc, 1), f10(atc, 2), f10(gn, 0), f10(gn, 1)};
+    const size_t comp = which ? kc.a.L.post_comp : kc.a.L.pre_comp;
+    const uint32_t iC = composition_bin_n(norm, cnt[2]), iG = composition_bin_n(norm, cnt[3]);
+    if (len == H.key) {
+        uint32_t *tab = H.compk() + (size_t)which * 7 * (H.key + 1);
+#pragma unroll
+        for (int h = 0; h < 5; ++h) atomicAdd(&tab[h * (H.key + 1) + cnt[h]], 1u);
+        const uint32_t s = cnt[2] + cnt[3];
+        const uint32_t delta = composition_bin_n(norm, s) - (iC + iG);          // bin(G)+bin(C) vs bin(G+C): 0 or 1
+        if (delta < 2) atomicAdd(&tab[(5 + delta) * (H.key + 1) + s], 1u);
+        else gadd(&kc.S[comp + 5 * (size_t)kCompBins + iC + iG], 1);
+    } else {
+#pragma unroll
+        for (int h = 0; h < 6; ++h) {
+            const uint32_t b = h == 2 ? iC : h == 3 ? iG : h == 5 ? iC + iG : composition_bin_n(norm, cnt[h == 5 ? 0 : h]);
+            if (b == 0) atomicAdd(&H.zero()[which * 6 + h], 1u);
+            else gadd(&kc.S[comp + (size_t)h * kCompBins + b], 1);
+        }
+    }
+}
+
+__device__ __forceinline__ void lane_scalar_stats(const KernelCtx &kc, int which, uint32_t len, uint32_t atc, uint32_t gn, int qbin)
+{
+    const SmemHist &H = kc.H;
+    lane_composition(kc, which, len, atc, gn);
+    qbin = min(max(qbin, 0), 41);
+    uint32_t *h = which ? H.postlen() : H.prelen();
+    if (len <= H.rows) atomicAdd(&h[len], 1u);
+    else gadd(&kc.S[(which ? kc.a.L.post_len : kc.a.L.pre_len) + len], 1);
+    atomicAdd(&H.qh()[(2 * which) * kQualCols + qbin], 1u);
+    atomicAdd(&H.qh()[(2 * which + 1) * kQualCols + qbin], len);
+}
+
+// Per-lane accumulators (reduced over the warp at the end of the kernel).
+struct LaneAcc {
+    uint32_t reads = 0, trimmed = 0;
+    unsigned long long len = 0, trimmed_len = 0;
+    uint32_t max_pre_rows = 0, max_post_rows = 0, max_post_len1 = 0;
+};
+
+// Window determination by ONE lane for its own read (same logic as determine_window, lane-private counters).
+__device__ __forceinline__ Window lane_window(const KernelCtx &kc, uint32_t mate, uint32_t r, uint32_t len, const QualAt &qa)
+{
+    const DevOpts &o = kc.o;
+    const SmemHist &H = kc.H;
+    Window w{0, len, 0, 0, true, -1};
+    if (o.filter_adapter && kc.a.adp[mate]) {
+        const uint2 v = kc.a.adp[mate][r];
+        w.best_adapter = kc.a.adp_best[mate][r];
+        if (w.best_adapter >= 0) w.flags |= FQ_RR_ADAPTER;
+        if (len != v.y) {
+            w.lo = v.x;
+            w.wl = v.y;
+            w.off5 += (v.y == 0) ? len : v.x;
+        }
+    }
+    if (o.trim_5 && !o.qc_only) {
+        if (o.trim_5 > w.wl) w.wl = 0;
+        else { w.lo += o.trim_5; w.wl -= o.trim_5; w.off5 += o.trim_5; }
+    }
+    if (o.trim_3 && !o.qc_only) {
+        if (o.trim_3 > w.wl) w.wl = 0;
+        else w.wl -= o.trim_3;
+    }
+    if (w.wl < o.min_len || w.wl == 0) {
+        atomicAdd(&H.filt()[FQ_READ_LENGTH], 1u);
+        atomicAdd(&H.filt()[FQ_BASE_LENGTH], w.wl);
+        w.flags |= FQ_RR_F_LENGTH;
+        w.ret = false;
+    }
+    if (!o.qc_only && w.ret) {
+        const uint32_t init_len = w.wl;
+        uint32_t f5 = 0;
+        if (o.mode == FQ_MODE_HARD) w.wl = hard_trim(qa, w.lo, (int)w.wl, o.quality, o.protect_5 != 0, f5);
+        else if (o.mode == FQ_MODE_BWA) w.wl = bwa_trim(qa, w.lo, (int)w.wl, o.quality, f5);
+        else w.wl = bwa_plus_trim(qa, w.lo, (int)w.wl, o.quality, o.protect_5 != 0, f5);
+        w.off5 += f5;
+        w.lo += f5;
+        if (init_len != w.wl) {
+            atomicAdd(&H.filt()[FQ_READ_QUAL_TRIM], 1u);
+            atomicAdd(&H.filt()[FQ_BASE_QUAL_TRIM], init_len - w.wl);
+            w.flags |= FQ_RR_QUAL_TRIMMED;
+        }
+        if (w.wl < o.min_len || w.wl == 0) {
+            atomicAdd(&H.filt()[FQ_READ_LENGTH], 1u);
+            atomicAdd(&H.filt()[FQ_BASE_LENGTH], w.wl);
+            w.flags |= FQ_RR_F_LENGTH;
+            w.ret = false;
+        }
+    }
+    return w;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Generic path: any length, chunk loops over global memory (L1 resident after the first pass).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void process_generic(const KernelCtx &kc, WarpState &ws, uint32_t mate, uint32_t r, const Rec &rc)
+__device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t mate, uint32_t r, const Rec &rc)
 {
     const DevOpts &o = kc.o;
     const SmemHist &H = kc.H;
@@ -649,15 +713,19 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, WarpState &
         nG += __popc(__ballot_sync(0xffffffffu, bc == 3));
         nN += __popc(__ballot_sync(0xffffffffu, bc == 4));
     }
-    if (__any_sync(0xffffffffu, bad_q)) { ws.err |= kErrQualGt41; ws.err_rec = min(ws.err_rec, r); }
+    if (__any_sync(0xffffffffu, bad_q) && lane == 0) { atomicOr(&kc.a.info->err, kErrQualGt41); atomicMin(&kc.a.info->err_record, r); }
     sum_q = warp_sum_i(sum_q);
     {
         const uint32_t mine = lane == 0 ? nA : lane == 1 ? nT : lane == 2 ? nC : lane == 3 ? nG : nN;
-        scalar_stats(kc, ws, 0, len, mine, (int)average_quality(sum_q, len, o.in_off));
+        scalar_stats(kc, 0, len, mine, (int)average_quality(sum_q, len, o.in_off));
     }
-    ws.acc_reads += 1;
-    ws.acc_len += len;
-    ws.max_pre_rows = max(ws.max_pre_rows, len);
+    if (lane == 0) {            // long reads are rare: counters go straight to the global block
+        gadd(&S[L.filter + FQ_TOTAL_COUNT], 1);
+        gadd(&S[L.filter + FQ_TOTAL_NUMBER], 1);
+        gadd(&S[L.filter + FQ_TOTAL_LENGTH], len);
+        atomicMax(&kc.a.rows->pre_rows, len);
+        atomicMax(&kc.a.rows->pre_len_size, len + 1);
+    }
 
     Window w = determine_window(kc, mate, r, len, qa);
 
@@ -688,16 +756,18 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, WarpState &
         }
         sum_w = warp_sum_i(sum_w);
         max_qv = __reduce_max_sync(0xffffffffu, max_qv);
-        apply_filters(kc, ws, w, r, rt.best, sum_w, wA, wT, wC, wG, max_qv, sp, qa, ave_q);
+        apply_filters(kc, w, r, rt.best, sum_w, wA, wT, wC, wG, max_qv, sp, qa, ave_q);
     }
     if (w.ret) {
         w.flags |= FQ_RR_VALID;
-        ws.acc_trimmed += 1;
-        ws.acc_trimmed_len += w.wl;
-        ws.max_post_rows = max(ws.max_post_rows, w.off5 + w.wl);
-        ws.max_post_len1 = max(ws.max_post_len1, w.wl + 1);
+        if (lane == 0) {
+            gadd(&S[L.filter + FQ_TOTAL_TRIMMED_NUMBER], 1);
+            gadd(&S[L.filter + FQ_TOTAL_TRIMMED_LENGTH], w.wl);
+            atomicMax(&kc.a.rows->post_rows, w.off5 + w.wl);
+            atomicMax(&kc.a.rows->post_len_size, w.wl + 1);
+        }
         const uint32_t mine = lane == 0 ? wA : lane == 1 ? wT : lane == 2 ? wC : lane == 3 ? wG : wN;
-        scalar_stats(kc, ws, 1, w.wl, mine, (int)ave_q);
+        scalar_stats(kc, 1, w.wl, mine, (int)ave_q);
     }
     const bool whole_removed = !w.ret;
     if (whole_removed || w.lo > 0 || w.lo + w.wl < len || n_lowg) {
@@ -756,35 +826,246 @@ __global__ void __launch_bounds__(kTrimThreads, 2) k_trim(const TrimArgs a, cons
     unsigned long long *const S = a.stats;
     const uint32_t R = H.rows;
     const KernelCtx kc{a, o, H, S, lane};
-    WarpState ws;
+    LaneAcc acc;
+    uint32_t err = 0, err_rec = 0xffffffffu;
+    const bool need_max = o.in_off != o.out_off && o.out_off + FQ_MAX_QUALITY_SCORE > 127;   // re-encode can overflow
 
-    for (uint32_t g = warp_global; g < total; g += n_warps) {
-        const uint32_t mate = g >= a.n_rec ? 1 : 0;
-        const uint32_t r = g - mate * a.n_rec;
-        const Rec rc = a.rec[mate][r];
-        if (rc.len <= 160 && rc.len <= R) process_fast<5>(kc, ws, mate, r, rc);
-        else if (rc.len <= 320 && rc.len <= R) process_fast<10>(kc, ws, mate, r, rc);
-        else process_generic(kc, ws, mate, r, rc);
+    for (uint32_t base = warp_global * 32; base < total; base += n_warps * 32) {
+        // ---- each lane owns one read of this group
+        const uint32_t g = base + lane;
+        LaneRead me;
+        me.done = g >= total;
+        const uint32_t mate = (!me.done && g >= a.n_rec) ? 1 : 0;
+        const uint32_t r = me.done ? 0 : g - mate * a.n_rec;
+        me.rc = Rec{0, 0, 0, 0};
+        if (!me.done) me.rc = (mate ? a.rec[1] : a.rec[0])[r];
+        me.sum_q = 0; me.cnt_atc = 0; me.cnt_gn = 0; me.lead = 0; me.trail = me.rc.len; me.run_whole = 0;
+        const uint8_t *raw_mine = mate ? a.raw[1] : a.raw[0];
+
+        // ---- phase 1: cooperative per-base pass, read by read
+        const uint32_t n_here = min(32u, total - base);
+        for (uint32_t j = 0; j < n_here; ++j) {
+            const uint32_t len = __shfl_sync(0xffffffffu, me.rc.len, j);
+            const uint32_t seq = __shfl_sync(0xffffffffu, me.rc.seq, j);
+            const uint32_t qual = __shfl_sync(0xffffffffu, me.rc.qual, j);
+            const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
+            const uint32_t rj = base + j - mj * a.n_rec;
+            const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
+            const uint8_t *sp = rawj + seq;
+            const signed char *qp = reinterpret_cast<const signed char *>(rawj + qual);
+            int s_sum = 0;
+            uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
+            bool generic = false;
+            if (len <= 160 && len <= R) phase1<5>(kc, sp, qp, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
+            else if (len <= 320 && len <= R) phase1<10>(kc, sp, qp, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
+            else {
+                const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
+                process_generic(kc, mj, rj, rcj);
+                generic = true;
+            }
+            if (lane == j) {
+                me.sum_q = s_sum; me.cnt_atc = s_atc; me.cnt_gn = s_gn; me.lead = s_lead; me.trail = s_trail; me.run_whole = s_run;
+                me.done = generic;
+            }
+        }
+
+        // ---- phase 2a: one lane per read: PRE scalar statistics and the window
+        const uint8_t *sp_mine = raw_mine + me.rc.seq;
+        const signed char *qp_mine = reinterpret_cast<const signed char *>(raw_mine + me.rc.qual);
+        const uint32_t len = me.rc.len;
+        const QualAt qa{qp_mine, me.lead, me.trail, o.in_off};
+        Window w{0, len, 0, 0, false, -1};
+        if (!me.done) {
+            lane_scalar_stats(kc, 0, len, me.cnt_atc, me.cnt_gn, (int)average_quality(me.sum_q, len, o.in_off));
+            acc.reads += 1;
+            acc.len += len;
+            acc.max_pre_rows = max(acc.max_pre_rows, len);
+            w = lane_window(kc, mate, r, len, qa);
+        }
+
+        // ---- phase 3a: cooperative pass over the bases outside the window (and G->N candidates / max quality inside)
+        uint32_t w_atc = me.cnt_atc, w_gn = me.cnt_gn, n_lowg = 0;
+        int sum_w = me.sum_q, max_qv = 0;
+        {
+            const bool partial = !me.done && (w.lo > 0 || w.lo + w.wl < len);
+            const bool want = !me.done && (partial || ((o.replace_q > 0 || need_max) && w.ret));
+            uint32_t todo = __ballot_sync(0xffffffffu, want);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
+                const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
+                const uint32_t lenj = __shfl_sync(0xffffffffu, len, j);
+                const uint8_t *sp = rawj + __shfl_sync(0xffffffffu, me.rc.seq, j);
+                const signed char *qp = reinterpret_cast<const signed char *>(rawj + __shfl_sync(0xffffffffu, me.rc.qual, j));
+                const uint32_t lo = __shfl_sync(0xffffffffu, w.lo, j), wl = __shfl_sync(0xffffffffu, w.wl, j);
+                const uint32_t lead = __shfl_sync(0xffffffffu, me.lead, j), trail = __shfl_sync(0xffffffffu, me.trail, j);
+                uint32_t r_atc = 0, r_gn = 0, nl = 0;
+                int r_sum = 0, mq = need_max ? 0 : -1;
+                removed_pass(kc, 0, sp, qp, lenj, lo, wl, lead, trail, r_atc, r_gn, r_sum, nl, mq);
+                if ((int)lane == j) {
+                    w_atc -= r_atc;            // fields never borrow: removed counts <= totals per class
+                    w_gn -= r_gn;
+                    sum_w -= r_sum;
+                    n_lowg = nl;
+                    max_qv = mq;
+                }
+            }
+        }
+
+        // ---- phase 2b: one lane per read: filters (trim.cpp:363-513)
+        float ave_q = 0.0f;
+        bool want_dinuc = false, want_run = false;
+        float norm2 = 0.0f;
+        uint32_t wA = f10(w_atc, 0), wT = f10(w_atc, 1), wC = f10(w_atc, 2), wG = f10(w_gn, 0), wN = f10(w_gn, 1);
+        if (!me.done && w.ret) {
+            wG -= n_lowg;                                       // G -> N replacement happens before the complexity filter
+            wN += n_lowg;
+            if (me.run_whole >= o.max_poly_n) want_run = true;  // exact run inside the window needed
+        }
+        {   // exact 'N' run of the window (rare: the whole read has a long enough run)
+            uint32_t todo = __ballot_sync(0xffffffffu, want_run);
+            uint32_t run_w = 0;
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
+                const uint8_t *sp = (mj ? a.raw[1] : a.raw[0]) + __shfl_sync(0xffffffffu, me.rc.seq, j);
+                const uint32_t rw = window_n_run(kc, sp, __shfl_sync(0xffffffffu, w.lo, j), __shfl_sync(0xffffffffu, w.wl, j));
+                if ((int)lane == j) run_w = rw;
+            }
+            if (want_run && run_w >= o.max_poly_n) {            // trim.cpp:363-371
+                atomicAdd(&H.filt()[FQ_READ_NN], 1u);
+                atomicAdd(&H.filt()[FQ_BASE_NN], w.wl);
+                w.flags |= FQ_RR_F_NN;
+                if (!o.qc_only) w.ret = false;
+            }
+        }
+        if (!me.done && w.ret) {
+            ave_q = average_quality(sum_w, w.wl, o.in_off);
+            if (ave_q < o.avg_q) {                              // trim.cpp:374-382
+                atomicAdd(&H.filt()[FQ_READ_AVG_Q], 1u);
+                atomicAdd(&H.filt()[FQ_BASE_AVG_Q], w.wl);
+                w.flags |= FQ_RR_F_AVGQ;
+                w.ret = false;
+            }
+        }
+        bool lowc = false;
+        if (!me.done && w.ret) {                                // low complexity, trim.cpp:405-513
+            const float norm = (float)(1.0 / (double)w.wl);     // trim.cpp:483
+            lowc = __fmul_rn((float)wA, norm) > o.lc || __fmul_rn((float)wT, norm) > o.lc ||
+                   __fmul_rn((float)wG, norm) > o.lc || __fmul_rn((float)wC, norm) > o.lc;
+            if (!lowc) {
+                norm2 = norm * 2.0f;                            // trim.cpp:499
+                const uint32_t second = max(max(min(wA, wT), min(wC, wG)), min(max(wA, wT), max(wC, wG)));
+                want_dinuc = __fmul_rn((float)second, norm2) > o.lc;   // a dinucleotide count <= second largest base count
+            }
+        }
+        {   // dinucleotide counts (rare), cooperative
+            uint32_t todo = __ballot_sync(0xffffffffu, want_dinuc);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
+                const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
+                const uint8_t *sp = rawj + __shfl_sync(0xffffffffu, me.rc.seq, j);
+                const QualAt qaj{reinterpret_cast<const signed char *>(rawj + __shfl_sync(0xffffffffu, me.rc.qual, j)),
+                                 __shfl_sync(0xffffffffu, me.lead, j), __shfl_sync(0xffffffffu, me.trail, j), o.in_off};
+                const bool res = dinucleotide_low_complexity(kc, sp, qaj, __shfl_sync(0xffffffffu, w.lo, j), __shfl_sync(0xffffffffu, w.wl, j),
+                                                             __shfl_sync(0xffffffffu, norm2, j));
+                if ((int)lane == j) lowc = res;
+            }
+        }
+        if (!me.done && w.ret) {
+            if (lowc) {
+                atomicAdd(&H.filt()[FQ_READ_LOW_COMPLEXITY], 1u);
+                atomicAdd(&H.filt()[FQ_BASE_LOW_COMPLEXITY], w.wl);
+                w.flags |= FQ_RR_F_LOWCOMP;
+                w.ret = false;
+            } else if (need_max && max_qv + o.out_off > 127) {  // trim.cpp:516-525
+                err |= kErrReencode;
+                err_rec = min(err_rec, r);
+            }
+        }
+
+        // ---- phase 2c: one lane per read: POST scalar statistics and the verdict (trim.cpp:527-548)
+        if (!me.done) {
+            if (w.ret) {
+                w.flags |= FQ_RR_VALID;
+                acc.trimmed += 1;
+                acc.trimmed_len += w.wl;
+                acc.max_post_rows = max(acc.max_post_rows, w.off5 + w.wl);
+                acc.max_post_len1 = max(acc.max_post_len1, w.wl + 1);
+                const uint32_t p_atc = wA | (wT << 10) | (wC << 20), p_gn = wG | (wN << 10);
+                lane_scalar_stats(kc, 1, w.wl, p_atc, p_gn, (int)ave_q);
+            }
+            (mate ? a.res[1] : a.res[0])[r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags));
+            fq_read_result *dbg = mate ? a.dbg[1] : a.dbg[0];
+            if (dbg) {
+                fq_read_result d;
+                d.offset_5 = w.off5;
+                d.length = w.ret ? w.wl : 0;
+                d.flags = (uint16_t)w.flags;
+                d.adapter = (int16_t)w.best_adapter;
+                d.avg_q = ave_q;
+                dbg[r] = d;
+            }
+        }
+
+        // ---- phase 3c: cooperative: the window of reads that turned out invalid (mode 1), surviving G->N (mode 2)
+        {
+            const bool inv = !me.done && !w.ret && w.wl > 0;
+            const bool g2n = !me.done && w.ret && n_lowg > 0;
+            uint32_t todo = __ballot_sync(0xffffffffu, inv || g2n);
+            const uint32_t inv_mask = __ballot_sync(0xffffffffu, inv);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
+                const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
+                const uint8_t *sp = rawj + __shfl_sync(0xffffffffu, me.rc.seq, j);
+                const signed char *qp = reinterpret_cast<const signed char *>(rawj + __shfl_sync(0xffffffffu, me.rc.qual, j));
+                uint32_t d0 = 0, d1 = 0, d3 = 0;
+                int d2 = 0, d4 = -1;
+                removed_pass(kc, ((inv_mask >> j) & 1u) ? 1 : 2, sp, qp, __shfl_sync(0xffffffffu, len, j), __shfl_sync(0xffffffffu, w.lo, j),
+                             __shfl_sync(0xffffffffu, w.wl, j), __shfl_sync(0xffffffffu, me.lead, j), __shfl_sync(0xffffffffu, me.trail, j),
+                             d0, d1, d2, d3, d4);
+            }
+        }
     }
 
-    // ---- merge: warp accumulators -> shared -> global (matrix.h:111-142 / trim.cpp:120-154)
-    if (lane == 0) {
-        if (ws.acc_reads) {
-            gadd(&S[L.filter + FQ_TOTAL_COUNT], ws.acc_reads);
-            gadd(&S[L.filter + FQ_TOTAL_NUMBER], ws.acc_reads);
-            gadd(&S[L.filter + FQ_TOTAL_LENGTH], ws.acc_len);
-            atomicMax(&a.rows->pre_rows, ws.max_pre_rows);
-            atomicMax(&a.rows->pre_len_size, ws.max_pre_rows + 1);
+    // ---- merge: lane accumulators -> warp -> global; shared -> global (matrix.h:111-142 / trim.cpp:120-154)
+    {
+        const uint32_t reads = warp_sum(acc.reads), trimmed = warp_sum(acc.trimmed);
+        unsigned long long len_sum = acc.len, tlen_sum = acc.trimmed_len;
+#pragma unroll
+        for (int k = 16; k; k >>= 1) {
+            len_sum += __shfl_xor_sync(0xffffffffu, len_sum, k);
+            tlen_sum += __shfl_xor_sync(0xffffffffu, tlen_sum, k);
         }
-        if (ws.acc_trimmed) {
-            gadd(&S[L.filter + FQ_TOTAL_TRIMMED_NUMBER], ws.acc_trimmed);
-            gadd(&S[L.filter + FQ_TOTAL_TRIMMED_LENGTH], ws.acc_trimmed_len);
-            atomicMax(&a.rows->post_rows, ws.max_post_rows);
-            atomicMax(&a.rows->post_len_size, ws.max_post_len1);
-        }
-        if (ws.err) {
-            atomicOr(&a.info->err, ws.err);
-            atomicMin(&a.info->err_record, ws.err_rec);
+        const uint32_t pre_rows = __reduce_max_sync(0xffffffffu, acc.max_pre_rows);
+        const uint32_t post_rows = __reduce_max_sync(0xffffffffu, acc.max_post_rows);
+        const uint32_t post_len1 = __reduce_max_sync(0xffffffffu, acc.max_post_len1);
+        const uint32_t err_all = __reduce_or_sync(0xffffffffu, err);
+        const uint32_t err_min = __reduce_min_sync(0xffffffffu, err_rec);
+        if (lane == 0) {
+            if (reads) {
+                gadd(&S[L.filter + FQ_TOTAL_COUNT], reads);
+                gadd(&S[L.filter + FQ_TOTAL_NUMBER], reads);
+                gadd(&S[L.filter + FQ_TOTAL_LENGTH], len_sum);
+                atomicMax(&a.rows->pre_rows, pre_rows);
+                atomicMax(&a.rows->pre_len_size, pre_rows + 1);
+            }
+            if (trimmed) {
+                gadd(&S[L.filter + FQ_TOTAL_TRIMMED_NUMBER], trimmed);
+                gadd(&S[L.filter + FQ_TOTAL_TRIMMED_LENGTH], tlen_sum);
+                atomicMax(&a.rows->post_rows, post_rows);
+                atomicMax(&a.rows->post_len_size, post_len1);
+            }
+            if (err_all) {
+                atomicOr(&a.info->err, err_all);
+                atomicMin(&a.info->err_record, err_min);
+            }
         }
     }
     __syncthreads();
