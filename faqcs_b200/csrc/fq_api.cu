@@ -88,7 +88,7 @@ struct fq_ctx {
     AdapterSet aset{};
     DevBuf d_adp_codes, d_adp_off, d_adp_or;
 
-    DevBuf d_raw[2], d_chunk[2], d_nl[2], d_rec[2], d_adp[2], d_adp_best[2], d_res[2], d_dbg[2], d_tile, d_out[4];
+    DevBuf d_raw[2], d_chunk[2], d_nl[2], d_rec[2], d_canon[2], d_adp[2], d_adp_best[2], d_res[2], d_dbg[2], d_tile, d_out[4];
     DevBuf d_info, d_stats, d_rows;
     BatchInfo *h_info = nullptr;       // pinned
     StatsLayout L{};
@@ -245,8 +245,9 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
     if (n_rec == 0) return FQ_OK;
     CK(ctx->d_nl[m].ensure((size_t)n_lines * 4));
     CK(ctx->d_rec[m].ensure((size_t)n_rec * sizeof(Rec)));
+    CK(ctx->d_canon[m].ensure((size_t)n_rec));
     k_scatter_lines<<<grid, 256, 0, ctx->stream>>>(d_raw, n, ctx->d_chunk[m].as<uint32_t>(), n_chunks, ctx->d_nl[m].as<uint32_t>());
-    k_build_records<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(d_raw, ctx->d_nl[m].as<uint32_t>(), n_rec, ctx->d_rec[m].as<Rec>(), info, m);
+    k_build_records<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(d_raw, ctx->d_nl[m].as<uint32_t>(), n_rec, ctx->d_rec[m].as<Rec>(), ctx->d_canon[m].as<uint8_t>(), info, m);
     ctx->launches += 2;
     *n_rec_out = n_rec;
     return FQ_OK;
@@ -412,6 +413,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         ea.raw[m] = m ? d_r2 : d_r1;
         ea.rec[m] = ctx->d_rec[m].as<Rec>();
         ea.res[m] = ctx->d_res[m].as<uint2>();
+        ea.canon[m] = ctx->d_canon[m].as<uint8_t>();
     }
     if (!o.qc_only) {
         // a trimmed record is never longer than its raw record, so the inputs bound the outputs
@@ -525,7 +527,7 @@ void fq_destroy(fq_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int m = 0; m < 2; ++m) {
-        ctx->d_raw[m].release(); ctx->d_chunk[m].release(); ctx->d_nl[m].release(); ctx->d_rec[m].release();
+        ctx->d_raw[m].release(); ctx->d_chunk[m].release(); ctx->d_nl[m].release(); ctx->d_rec[m].release(); ctx->d_canon[m].release();
         ctx->d_adp[m].release(); ctx->d_adp_best[m].release(); ctx->d_res[m].release(); ctx->d_dbg[m].release();
         ctx->h_dbg[m].release();
     }

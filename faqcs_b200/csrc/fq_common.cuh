@@ -123,6 +123,9 @@ struct StatsRows {
     uint32_t post_len_size;
 };
 
+// internal verdict flag (not part of the public FQ_RR_* set): terminal-N quality masking touched this read
+constexpr uint32_t kFlagMasked = 0x80u;
+
 // trim verdict packing
 constexpr uint32_t kResLenBits = 24;            // reads < 16 Mi bases
 constexpr uint32_t kResLenMask = (1u << kResLenBits) - 1;

@@ -19,6 +19,7 @@ struct EmitArgs {
     const uint8_t *raw[2];
     const Rec *rec[2];
     const uint2 *res[2];
+    const uint8_t *canon[2];     // 1 = LF line ends + bare '+' line (raw bytes == write_read output)
     uint32_t n_rec;
     uint32_t n_tiles;
     uint32_t *tile_sum;          // [4][n_tiles] -> exclusive bases after k_scan_tiles (u32: < 4 GiB per stream per batch)
@@ -28,10 +29,10 @@ struct EmitArgs {
     size_t filter_off;
 };
 
-__device__ __forceinline__ uint32_t header_len(const uint8_t *raw, const Rec &rc)
+__device__ __forceinline__ uint32_t header_len(const uint8_t *raw, const Rec &rc, bool canon = false)
 {
     uint32_t n = rc.seq - rc.hdr - 1;
-    if (n && raw[rc.hdr + n - 1] == '\r') --n;
+    if (!canon && n && raw[rc.hdr + n - 1] == '\r') --n;
     return n;
 }
 
@@ -48,7 +49,7 @@ __device__ __forceinline__ void route_sizes(const EmitArgs &a, const DevOpts &o,
     for (int m = 0; m < n_mates; ++m) {
         const Rec rc = a.rec[m][r];
         const uint2 v = a.res[m][r];
-        const uint32_t hl = header_len(a.raw[m], rc);
+        const uint32_t hl = header_len(a.raw[m], rc, a.canon[m][r] != 0);
         wl[m] = v.y & kResLenMask;
         valid[m] = ((v.y >> kResLenBits) & FQ_RR_VALID) != 0;
         trimmed[m] = hl + 2 * wl[m] + 5;
@@ -124,58 +125,104 @@ __global__ void __launch_bounds__(128) k_scan_tiles(uint32_t *tile_sum, uint32_t
     if (lane == 0) info->out_bytes[s] = carry;
 }
 
-// Copy one trimmed record.  All 32 lanes cooperate, byte-striped.
-__device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, const Rec &rc, uint32_t lo, uint32_t wl,
-                                              const DevOpts &o, uint32_t lane)
+// Warp-cooperative copy of n bytes between arbitrarily aligned addresses.  The body is written
+// as 16-byte aligned stores; each store gathers its bytes from five aligned 32-bit source words
+// with funnel shifts (the source is L1/L2 resident raw input, neighbouring lanes share words).
+__device__ __forceinline__ void copy_span(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane)
 {
-    const uint32_t hl = header_len(raw, rc);
-    const uint8_t *hp = raw + rc.hdr;
-    const uint8_t *sp = raw + rc.seq;
-    const signed char *qp = reinterpret_cast<const signed char *>(raw + rc.qual);
-    // terminal-N mask bounds (only matter when an end of the read is 'N')
-    uint32_t lead = 0, trail = rc.len;
-    if (rc.len && (sp[0] == 'N' || sp[rc.len - 1] == 'N')) {
-        while (lead < rc.len && sp[lead] == 'N') ++lead;
-        while (trail > 0 && sp[trail - 1] == 'N') --trail;
+    if (n < 48) {
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        return;
     }
-    const uint32_t s0 = hl + 1, s1 = s0 + wl, q0 = s1 + 3, q1 = q0 + wl, total = q1 + 1;
-    for (uint32_t i = lane; i < total; i += 32) {
-        uint32_t ch;
-        if (i < hl) ch = hp[i];
-        else if (i < s0) ch = '\n';
-        else if (i < s1) {
-            const uint32_t p = lo + (i - s0);
-            ch = sp[p];
-            if (o.replace_q > 0 && ch == 'G') {
-                int qc = (p < lead || p >= trail) ? o.in_off : (int)qp[p];
-                if (max(0, qc - o.in_off) < (int)o.replace_q) ch = 'N';
-            }
-        } else if (i < q0) ch = (i == s1 + 1) ? '+' : '\n';
-        else if (i < q1) {
-            const uint32_t p = lo + (i - q0);
-            int qc = (p < lead || p >= trail) ? o.in_off : (int)qp[p];
-            if (o.in_off != o.out_off) qc = max(0, qc - o.in_off) + o.out_off;      // trim.cpp:516-525
-            ch = (uint32_t)qc & 0xffu;
-        } else ch = '\n';
-        dst[i] = (uint8_t)ch;
+    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (lane < head) dst[lane] = src[lane];
+    const uint32_t body = (n - head) >> 4;
+    const uint8_t *s = src + head;
+    uint8_t *d = dst + head;
+    for (uint32_t c = lane; c < body; c += 32) {
+        const uint8_t *sc = s + 16 * c;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sc) & 3u) * 8u;
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sc) & ~(uintptr_t)3);
+        const uint32_t w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
+        const uint32_t w4 = sh ? __ldg(sw + 4) : 0u;          // only bytes below src + n are ever consumed from it
+        uint4 v;
+        v.x = __funnelshift_r(w0, w1, sh);
+        v.y = __funnelshift_r(w1, w2, sh);
+        v.z = __funnelshift_r(w2, w3, sh);
+        v.w = __funnelshift_r(w3, w4, sh);
+        *reinterpret_cast<uint4 *>(d + 16 * c) = v;
     }
+    for (uint32_t i = head + 16 * body + lane; i < n; i += 32) dst[i] = src[i];
 }
 
-// Copy one raw (discarded) record: def \n seq \n + \n qual \n with the original, unmasked bytes.
-__device__ __forceinline__ void write_raw(uint8_t *dst, const uint8_t *raw, const Rec &rc, uint32_t lane)
+// Emit one surviving read: def \n seq \n + \n qual \n (write_read, fastq.cpp:127-138) with the
+// mutations trim_read leaves behind.  `plain`: the record is canonical, untrimmed and untouched,
+// so the output is its raw bytes.
+__device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, const Rec &rc, bool canon, uint32_t lo, uint32_t wl,
+                                              uint32_t flags, const DevOpts &o, uint32_t lane)
 {
-    const uint32_t hl = header_len(raw, rc);
-    const uint32_t s0 = hl + 1, s1 = s0 + rc.len, q0 = s1 + 3, q1 = q0 + rc.len, total = q1 + 1;
-    for (uint32_t i = lane; i < total; i += 32) {
-        uint32_t ch;
-        if (i < hl) ch = raw[rc.hdr + i];
-        else if (i < s0) ch = '\n';
-        else if (i < s1) ch = raw[rc.seq + (i - s0)];
-        else if (i < q0) ch = (i == s1 + 1) ? '+' : '\n';
-        else if (i < q1) ch = raw[rc.qual + (i - q0)];
-        else ch = '\n';
-        dst[i] = (uint8_t)ch;
+    const uint32_t hl = header_len(raw, rc, canon);
+    const bool masked = (flags & kFlagMasked) != 0;
+    const bool requal = o.in_off != o.out_off;
+    if (canon && lo == 0 && wl == rc.len && !masked && !requal && o.replace_q == 0) {
+        copy_span(dst, raw + rc.hdr, hl + 2 * wl + 5, lane);
+        return;
     }
+    const uint8_t *sp = raw + rc.seq;
+    const signed char *qp = reinterpret_cast<const signed char *>(raw + rc.qual);
+    uint32_t lead = 0, trail = rc.len;
+    if (masked) {                                               // terminal-N mask bounds (trim.cpp:1191-1216)
+        while (lead < rc.len && sp[lead] == 'N') ++lead;
+        while (trail > 0 && sp[trail - 1] == 'N') --trail;
+        if (lead >= rc.len) trail = 0;
+    }
+    const uint32_t s0 = hl + 1, s1 = s0 + wl, q0 = s1 + 3, q1 = q0 + wl;
+    // header (+ its '\n' and, when nothing was cut at the 5' end, the bases: one contiguous source run)
+    if (canon && lo == 0 && o.replace_q == 0) copy_span(dst, raw + rc.hdr, s1, lane);
+    else {
+        copy_span(dst, raw + rc.hdr, hl, lane);
+        if (lane == 0) dst[hl] = '\n';
+        if (o.replace_q == 0) copy_span(dst + s0, sp + lo, wl, lane);
+        else {
+            for (uint32_t i = lane; i < wl; i += 32) {          // G -> N below --replace_to_N_q (trim.cpp:390-403)
+                const uint32_t p = lo + i;
+                uint32_t ch = sp[p];
+                if (ch == 'G') {
+                    const int qc = (p < lead || p >= trail) ? o.in_off : (int)qp[p];
+                    if (max(0, qc - o.in_off) < (int)o.replace_q) ch = 'N';
+                }
+                dst[s0 + i] = (uint8_t)ch;
+            }
+        }
+    }
+    if (lane < 3) dst[s1 + lane] = lane == 1 ? '+' : '\n';
+    if (!masked && !requal) copy_span(dst + q0, raw + rc.qual + lo, wl, lane);
+    else {
+        for (uint32_t i = lane; i < wl; i += 32) {
+            const uint32_t p = lo + i;
+            int qc = (p < lead || p >= trail) ? o.in_off : (int)qp[p];
+            if (requal) qc = max(0, qc - o.in_off) + o.out_off;  // trim.cpp:516-525
+            dst[q0 + i] = (uint8_t)qc;
+        }
+    }
+    if (lane == 3) dst[q1] = '\n';
+}
+
+// Emit one discarded read: the raw, unmasked record (copy taken before trim(), FaQCs.cpp:279-285).
+__device__ __forceinline__ void write_raw(uint8_t *dst, const uint8_t *raw, const Rec &rc, bool canon, uint32_t lane)
+{
+    const uint32_t hl = header_len(raw, rc, canon);
+    if (canon) {
+        copy_span(dst, raw + rc.hdr, hl + 2 * rc.len + 5, lane);
+        return;
+    }
+    const uint32_t s0 = hl + 1, s1 = s0 + rc.len, q0 = s1 + 3, q1 = q0 + rc.len;
+    copy_span(dst, raw + rc.hdr, hl, lane);
+    if (lane == 0) dst[hl] = '\n';
+    copy_span(dst + s0, raw + rc.seq, rc.len, lane);
+    if (lane < 3) dst[s1 + lane] = lane == 1 ? '+' : '\n';
+    copy_span(dst + q0, raw + rc.qual, rc.len, lane);
+    if (lane == 3) dst[q1] = '\n';
 }
 
 __global__ void __launch_bounds__(kTile) k_emit(const EmitArgs a, const DevOpts o)
@@ -221,23 +268,25 @@ __global__ void __launch_bounds__(kTile) k_emit(const EmitArgs a, const DevOpts 
         if (o.paired) {
             const Rec r0 = a.rec[0][rr], r1 = a.rec[1][rr];
             const uint2 e0 = a.res[0][rr], e1 = a.res[1][rr];
+            const bool c0 = a.canon[0][rr] != 0, c1 = a.canon[1][rr] != 0;
             if (v0 && v1) {
-                write_trimmed(a.out[0] + s_off[0][t], a.raw[0], r0, e0.x, e0.y & kResLenMask, o, lane);
-                write_trimmed(a.out[1] + s_off[1][t], a.raw[1], r1, e1.x, e1.y & kResLenMask, o, lane);
+                write_trimmed(a.out[0] + s_off[0][t], a.raw[0], r0, c0, e0.x, e0.y & kResLenMask, e0.y >> kResLenBits, o, lane);
+                write_trimmed(a.out[1] + s_off[1][t], a.raw[1], r1, c1, e1.x, e1.y & kResLenMask, e1.y >> kResLenBits, o, lane);
             } else {
-                if (v0) write_trimmed(a.out[2] + s_off[2][t], a.raw[0], r0, e0.x, e0.y & kResLenMask, o, lane);
-                else if (v1) write_trimmed(a.out[2] + s_off[2][t], a.raw[1], r1, e1.x, e1.y & kResLenMask, o, lane);
+                if (v0) write_trimmed(a.out[2] + s_off[2][t], a.raw[0], r0, c0, e0.x, e0.y & kResLenMask, e0.y >> kResLenBits, o, lane);
+                else if (v1) write_trimmed(a.out[2] + s_off[2][t], a.raw[1], r1, c1, e1.x, e1.y & kResLenMask, e1.y >> kResLenBits, o, lane);
                 if (o.discard) {
                     uint32_t off = s_off[3][t];
-                    if (!v0) { write_raw(a.out[3] + off, a.raw[0], r0, lane); off += header_len(a.raw[0], r0) + 2 * r0.len + 5; }
-                    if (!v1) write_raw(a.out[3] + off, a.raw[1], r1, lane);
+                    if (!v0) { write_raw(a.out[3] + off, a.raw[0], r0, c0, lane); off += header_len(a.raw[0], r0, c0) + 2 * r0.len + 5; }
+                    if (!v1) write_raw(a.out[3] + off, a.raw[1], r1, c1, lane);
                 }
             }
         } else {
             const Rec r0 = a.rec[0][rr];
             const uint2 e0 = a.res[0][rr];
-            if (v0) write_trimmed(a.out[2] + s_off[2][t], a.raw[0], r0, e0.x, e0.y & kResLenMask, o, lane);
-            else if (o.discard) write_raw(a.out[3] + s_off[3][t], a.raw[0], r0, lane);
+            const bool c0 = a.canon[0][rr] != 0;
+            if (v0) write_trimmed(a.out[2] + s_off[2][t], a.raw[0], r0, c0, e0.x, e0.y & kResLenMask, e0.y >> kResLenBits, o, lane);
+            else if (o.discard) write_raw(a.out[3] + s_off[3][t], a.raw[0], r0, c0, lane);
         }
     }
 }

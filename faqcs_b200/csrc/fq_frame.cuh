@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) k_scatter_lines(const uint8_t *__restrict
 // '\n' (CRLF input); |seq| must equal |qual| (fastq.cpp:118-122).
 __global__ void __launch_bounds__(256) k_build_records(const uint8_t *__restrict__ raw,
                                                        const uint32_t *__restrict__ nl_pos, uint32_t n_rec,
-                                                       Rec *__restrict__ rec, BatchInfo *info, int mate)
+                                                       Rec *__restrict__ rec, uint8_t *__restrict__ canon, BatchInfo *info, int mate)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t len = 0, cr = 0;
@@ -176,6 +176,9 @@ __global__ void __launch_bounds__(256) k_build_records(const uint8_t *__restrict
         bad = (len != qlen);
         cr = c0 + c1 + c2 + c3;
         rec[r] = Rec{hdr, seq, qual, len};
+        // canonical record: LF line ends and a bare "+" line, i.e. the raw bytes ARE what write_read
+        // (fastq.cpp:127-138) prints for an untouched read, so emission can be a block copy
+        canon[r] = (uint8_t)(cr == 0 && p2 == plus + 1 && raw[plus] == '+');
     }
     // block-level reductions: max length, CR count, first bad record
     uint32_t m = len;

@@ -794,7 +794,7 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
         }
     }
     if (lane == 0) {
-        kc.a.res[mate][r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags));
+        kc.a.res[mate][r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags | ((lead > 0 || trail < len) ? kFlagMasked : 0u)));
         if (kc.a.dbg[mate]) {
             fq_read_result d;
             d.offset_5 = w.off5;
@@ -999,7 +999,8 @@ __global__ void __launch_bounds__(kTrimThreads, 2) k_trim(const TrimArgs a, cons
                 const uint32_t p_atc = wA | (wT << 10) | (wC << 20), p_gn = wG | (wN << 10);
                 lane_scalar_stats(kc, 1, w.wl, p_atc, p_gn, (int)ave_q);
             }
-            (mate ? a.res[1] : a.res[0])[r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags));
+            const uint32_t masked = (me.lead > 0 || me.trail < len) ? kFlagMasked : 0u;
+            (mate ? a.res[1] : a.res[0])[r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags | masked));
             fq_read_result *dbg = mate ? a.dbg[1] : a.dbg[0];
             if (dbg) {
                 fq_read_result d;
