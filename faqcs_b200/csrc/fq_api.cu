@@ -224,18 +224,37 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
 {
     *n_rec_out = 0;
     if (n == 0) return FQ_OK;
-    if (n >= (1ull << 32)) return fail(ctx, FQ_ERR_ARG, "batch larger than 4 GiB per mate: split it");
+    if (n >= (1ull << 30)) return fail(ctx, FQ_ERR_ARG, "batch larger than 1 GiB per mate: split it");
     if ((reinterpret_cast<uintptr_t>(d_raw) & 15) != 0) return fail(ctx, FQ_ERR_ARG, "device input must be 16-byte aligned");
     BatchInfo *info = ctx->d_info.as<BatchInfo>();
-    const uint32_t n_chunks = (uint32_t)((n + kChunkBytes - 1) / kChunkBytes);
-    CK(ctx->d_chunk[m].ensure((size_t)n_chunks * 4));
-    const int grid = std::max(1, std::min<int>((n_chunks + 7) / 8, ctx->sm_count * 8));
-    k_count_lines<<<grid, 256, 0, ctx->stream>>>(d_raw, n, ctx->d_chunk[m].as<uint32_t>(), n_chunks, info, m);
-    k_scan_chunks<<<1, 1024, 0, ctx->stream>>>(ctx->d_chunk[m].as<uint32_t>(), n_chunks, info, m);
-    ctx->launches += 2;
-    CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const uint32_t n_lines = ctx->h_info->n_lines[m];
+    // single-pass line index (k_frame_lines); nl_pos capacity is a guess (>= 24 bytes per line on average),
+    // the kernel counts every line regardless, so an overflow is detected and the pass repeated once.
+    const uint32_t n_tiles = (uint32_t)((n + kFrameTile - 1) / kFrameTile);
+    CK(ctx->d_chunk[m].ensure((size_t)n_tiles * 8 + 16));
+    uint32_t n_lines = 0;
+    size_t cap_lines = std::max<size_t>(1u << 16, n / 24);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(ctx->d_nl[m].ensure(cap_lines * 4));
+        CK(cudaMemsetAsync(ctx->d_chunk[m].p, 0, (size_t)n_tiles * 8 + 16, ctx->stream));
+        unsigned long long *status = ctx->d_chunk[m].as<unsigned long long>();
+        uint32_t *ticket = reinterpret_cast<uint32_t *>(status + n_tiles);
+        const int grid = std::max(1, std::min<int>(n_tiles, ctx->sm_count * 8));
+        if (attempt) { CK(cudaMemsetAsync(&info->n_cr[m], 0, 4, ctx->stream)); CK(cudaMemsetAsync(&info->n_cr_eol[m], 0, 4, ctx->stream)); }
+        k_frame_lines<<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, ctx->d_nl[m].as<uint32_t>(), (uint32_t)std::min<size_t>(cap_lines, 0xffffffffu),
+                                                              status, ticket, n_tiles, info, m);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_lines = ctx->h_info->n_lines[m];
+        if (n_lines <= cap_lines) break;
+        cap_lines = n_lines;
+    }
+    if (ctx->h_info->n_cr[m]) {
+        // CRLF input (or stray CRs): exact CR count, to be compared with the CRs that sit right before a '\n'
+        CK(cudaMemsetAsync(&info->n_cr[m], 0, 4, ctx->stream));
+        k_count_byte<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_raw, n, '\r', &info->n_cr[m]);
+        ctx->launches++;
+    }
     if (n_lines % 4 != 0) {
         static const char *msg[4] = {"", "fastq.cpp:next_read: Unable to read sequence", "fastq.cpp:next_read: Unable to read '+'",
                                      "fastq.cpp:next_read: Unable to read quality"};
@@ -243,12 +262,10 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
     }
     const uint32_t n_rec = n_lines / 4;
     if (n_rec == 0) return FQ_OK;
-    CK(ctx->d_nl[m].ensure((size_t)n_lines * 4));
     CK(ctx->d_rec[m].ensure((size_t)n_rec * sizeof(Rec)));
     CK(ctx->d_canon[m].ensure((size_t)n_rec));
-    k_scatter_lines<<<grid, 256, 0, ctx->stream>>>(d_raw, n, ctx->d_chunk[m].as<uint32_t>(), n_chunks, ctx->d_nl[m].as<uint32_t>());
-    k_build_records<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(d_raw, ctx->d_nl[m].as<uint32_t>(), n_rec, ctx->d_rec[m].as<Rec>(), ctx->d_canon[m].as<uint8_t>(), info, m);
-    ctx->launches += 2;
+    k_build_records<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nl[m].as<uint32_t>(), n_rec, ctx->d_rec[m].as<Rec>(), ctx->d_canon[m].as<uint8_t>(), info, m);
+    ctx->launches++;
     *n_rec_out = n_rec;
     return FQ_OK;
 }

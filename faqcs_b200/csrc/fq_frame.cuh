@@ -153,44 +153,195 @@ __global__ void __launch_bounds__(256) k_scatter_lines(const uint8_t *__restrict
     }
 }
 
-// Record descriptors from 4 consecutive line ends.  One thread per record.
-// Grammar per fastq.cpp: content of a line ends at '\r' when it is followed by the
-// '\n' (CRLF input); |seq| must equal |qual| (fastq.cpp:118-122).
-__global__ void __launch_bounds__(256) k_build_records(const uint8_t *__restrict__ raw,
-                                                       const uint32_t *__restrict__ nl_pos, uint32_t n_rec,
-                                                       Rec *__restrict__ rec, uint8_t *__restrict__ canon, BatchInfo *info, int mate)
+// ---------------------------------------------------------------------------------------------
+// Single-pass line index: every '\n' offset written at its global rank, one read of the input.
+// 32 KiB tiles handed out by an atomic ticket; the running line count is carried across tiles
+// with a decoupled look-back (status word = flag << 62 | count: 1 = tile aggregate, 2 = inclusive
+// prefix).  Each lane owns 128 contiguous bytes of its warp's 4 KiB chunk, so one warp scan per
+// chunk orders the ranks.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kFrameThreads = 256;
+constexpr uint32_t kFrameTile = (kFrameThreads / 32) * kChunkBytes;   // 32 KiB
+// A line-index entry is the byte offset of a '\n' plus two facts about the byte before it, so
+// that record building never has to touch the raw bytes again (a batch is < 1 GiB per mate).
+constexpr uint32_t kNlCr = 1u << 31;      // preceded by '\r'  (CRLF line end)
+constexpr uint32_t kNlPlus = 1u << 30;    // preceded by '+'
+constexpr uint32_t kNlPosMask = (1u << 30) - 1;
+
+// Exact zero-byte mask: 0x80 in every byte of x that is zero (no cross-byte borrows).
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
+{
+    const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | x | 0x7f7f7f7fu);
+}
+// 4-bit mask (bit b = byte b) of the bytes of w equal to the byte replicated in c4.
+__device__ __forceinline__ uint32_t eq_nibble(uint32_t w, uint32_t c4)
+{
+    // 0x80 flags -> bits 0,8,16,24 -> gathered into bits 21..24 by one multiply (no colliding partial products)
+    return (((zero_bytes(w ^ c4) >> 7) * 0x00204081u) >> 21) & 0xfu;
+}
+__device__ __forceinline__ uint32_t eq_mask16(const uint4 &v, uint32_t c4)
+{
+    return eq_nibble(v.x, c4) | (eq_nibble(v.y, c4) << 4) | (eq_nibble(v.z, c4) << 8) | (eq_nibble(v.w, c4) << 12);
+}
+__device__ __forceinline__ uint32_t has_byte(uint32_t w, uint32_t c4)      // non-zero iff some byte of w equals c (may over-flag bytes, never misses)
+{
+    const uint32_t x = w ^ c4;
+    return (x - 0x01010101u) & ~x & 0x80808080u;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__restrict__ raw, uint64_t n, uint32_t *__restrict__ nl_pos,
+                                                               uint32_t cap_lines, unsigned long long *status, uint32_t *ticket,
+                                                               uint32_t n_tiles, BatchInfo *info, int mate)
+{
+    __shared__ uint32_t s_tile, s_prefix;
+    __shared__ uint32_t s_warp[kFrameThreads / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t any_cr = 0, cr_eol = 0;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const uint64_t chunk_base = (uint64_t)tile * kFrameTile + (uint64_t)wid * kChunkBytes;
+        // coalesced: vector k of lane l covers bytes chunk_base + (k*32 + l)*16 .. +16
+        uint32_t m16[4] = {0, 0, 0, 0};                 // two 16-bit newline masks per register
+        uint32_t cA = 0, cB = 0, cC = 0;                // per-vector newline counts, 10-bit fields (k = 0..2, 3..5, 6..7)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t off = chunk_base + (uint64_t)(k * 32 + lane) * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (off + 16 <= n) v = __ldg(reinterpret_cast<const uint4 *>(raw + off));
+            else if (off < n) {
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (uint32_t b = 0; b < 16 && off + b < n; ++b) w[b >> 2] |= (uint32_t)raw[off + b] << (8 * (b & 3));
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            const uint32_t m = eq_mask16(v, 0x0a0a0a0au);
+            any_cr |= has_byte(v.x, 0x0d0d0d0du) | has_byte(v.y, 0x0d0d0d0du) | has_byte(v.z, 0x0d0d0d0du) | has_byte(v.w, 0x0d0d0d0du);
+            m16[k >> 1] |= m << (16 * (k & 1));
+            const uint32_t c = __popc(m);
+            if (k < 3) cA |= c << (10 * k);
+            else if (k < 6) cB |= c << (10 * (k - 3));
+            else cC |= c << (10 * (k - 6));
+        }
+        const uint32_t iA = warp_incl_scan(cA, lane), iB = warp_incl_scan(cB, lane), iC = warp_incl_scan(cC, lane);
+        const uint32_t tA = __shfl_sync(0xffffffffu, iA, 31), tB = __shfl_sync(0xffffffffu, iB, 31), tC = __shfl_sync(0xffffffffu, iC, 31);
+        const uint32_t warp_total = (tA & 1023u) + ((tA >> 10) & 1023u) + (tA >> 20) + (tB & 1023u) + ((tB >> 10) & 1023u) + (tB >> 20) +
+                                    (tC & 1023u) + ((tC >> 10) & 1023u);
+        if (lane == 0) s_warp[wid] = warp_total;
+        __syncthreads();
+        if (wid == 0) {
+            // decoupled look-back, 32 predecessor tiles per step
+            uint32_t tile_total = 0;
+#pragma unroll
+            for (int k = 0; k < (int)(kFrameThreads / 32); ++k) tile_total += s_warp[k];
+            volatile unsigned long long *st = status;
+            uint32_t prefix = 0;
+            if (tile > 0) {
+                if (lane == 0) { st[tile] = (1ull << 62) | tile_total; __threadfence(); }
+                int hi = (int)tile - 1;
+                while (hi >= 0) {
+                    const int j = hi - (int)lane;
+                    unsigned long long sv = 2ull << 62;  // lanes past tile 0 behave like a zero inclusive prefix
+                    if (j >= 0) { do { sv = st[j]; } while ((sv >> 62) == 0); }
+                    const uint32_t incl = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                    const int stop = incl ? __ffs(incl) - 1 : 31;
+                    const uint32_t val = (int)lane <= stop ? (uint32_t)sv : 0u;
+                    prefix += __reduce_add_sync(0xffffffffu, val);
+                    if (incl) break;
+                    hi -= 32;
+                }
+            }
+            if (lane == 0) {
+                __threadfence();
+                st[tile] = (2ull << 62) | (unsigned long long)(prefix + tile_total);
+                s_prefix = prefix;
+                if (tile == n_tiles - 1) info->n_lines[mate] = prefix + tile_total;
+            }
+        }
+        __syncthreads();
+        uint32_t rank0 = s_prefix;
+        for (uint32_t k = 0; k < wid; ++k) rank0 += s_warp[k];
+        // ranks are ordered by (vector k, lane, byte)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t incl = k < 3 ? (iA >> (10 * k)) & 1023u : k < 6 ? (iB >> (10 * (k - 3))) & 1023u : (iC >> (10 * (k - 6))) & 1023u;
+            const uint32_t tot = k < 3 ? (tA >> (10 * k)) & 1023u : k < 6 ? (tB >> (10 * (k - 3))) & 1023u : (tC >> (10 * (k - 6))) & 1023u;
+            uint32_t m = (m16[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            uint32_t rank = rank0 + incl - __popc(m);
+            const uint64_t off = chunk_base + (uint64_t)(k * 32 + lane) * 16;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                const uint64_t pos = off + b;
+                const uint32_t prev = pos ? raw[pos - 1] : 0;         // L1 resident: just loaded
+                uint32_t e = (uint32_t)pos;
+                if (prev == '\r') { e |= kNlCr; ++cr_eol; }
+                if (prev == '+') e |= kNlPlus;
+                if (rank < cap_lines) nl_pos[rank] = e;
+                ++rank;
+                m &= m - 1;
+            }
+            rank0 += tot;
+        }
+        __syncthreads();      // s_tile / s_warp / s_prefix are reused by the next tile
+    }
+    any_cr = __reduce_or_sync(0xffffffffu, any_cr);
+    cr_eol = __reduce_add_sync(0xffffffffu, cr_eol);
+    if (lane == 0) {
+        if (any_cr) atomicOr(&info->n_cr[mate], 1u);      // "some CR exists": the host then asks for the exact count
+        if (cr_eol) atomicAdd(&info->n_cr_eol[mate], cr_eol);
+    }
+}
+
+// Exact count of one byte value (only launched when k_frame_lines saw a '\r': CRLF input).
+__global__ void __launch_bounds__(256) k_count_byte(const uint8_t *__restrict__ raw, uint64_t n, uint32_t c, uint32_t *out)
+{
+    uint32_t cnt = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) cnt += raw[i] == c;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
+// Record descriptors from 4 consecutive line-index entries.  One thread per record; the raw bytes
+// are not touched.  Grammar per fastq.cpp: the content of a line ends at the '\r' of a CRLF line
+// end; |seq| must equal |qual| (fastq.cpp:118-122).
+__global__ void __launch_bounds__(256) k_build_records(const uint32_t *__restrict__ nl_pos, uint32_t n_rec, Rec *__restrict__ rec,
+                                                       uint8_t *__restrict__ canon, BatchInfo *info, int mate)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t len = 0, cr = 0;
+    uint32_t len = 0;
     bool bad = false;
     if (r < n_rec) {
-        const uint32_t p0 = nl_pos[4 * r], p1 = nl_pos[4 * r + 1], p2 = nl_pos[4 * r + 2], p3 = nl_pos[4 * r + 3];
-        const uint32_t hdr = r ? nl_pos[4 * r - 1] + 1 : 0;
+        const uint4 e = reinterpret_cast<const uint4 *>(nl_pos)[r];
+        const uint32_t p0 = e.x & kNlPosMask, p1 = e.y & kNlPosMask, p2 = e.z & kNlPosMask, p3 = e.w & kNlPosMask;
+        const uint32_t hdr = r ? (nl_pos[4 * r - 1] & kNlPosMask) + 1 : 0;
         const uint32_t seq = p0 + 1, plus = p1 + 1, qual = p2 + 1;
-        const uint32_t c0 = (p0 > hdr && raw[p0 - 1] == '\r');
-        const uint32_t c1 = (p1 > seq && raw[p1 - 1] == '\r');
-        const uint32_t c2 = (p2 > plus && raw[p2 - 1] == '\r');
-        const uint32_t c3 = (p3 > qual && raw[p3 - 1] == '\r');
+        // a '\r' right before the '\n' belongs to the line end only if the line is not empty
+        const uint32_t c0 = (e.x & kNlCr) && p0 > hdr, c1 = (e.y & kNlCr) && p1 > seq;
+        const uint32_t c2 = (e.z & kNlCr) && p2 > plus, c3 = (e.w & kNlCr) && p3 > qual;
         len = p1 - seq - c1;
         const uint32_t qlen = p3 - qual - c3;
         bad = (len != qlen);
-        cr = c0 + c1 + c2 + c3;
         rec[r] = Rec{hdr, seq, qual, len};
         // canonical record: LF line ends and a bare "+" line, i.e. the raw bytes ARE what write_read
         // (fastq.cpp:127-138) prints for an untouched read, so emission can be a block copy
-        canon[r] = (uint8_t)(cr == 0 && p2 == plus + 1 && raw[plus] == '+');
+        canon[r] = (uint8_t)(!(c0 | c1 | c2 | c3) && p2 == plus + 1 && (e.z & kNlPlus));
     }
-    // block-level reductions: max length, CR count, first bad record
     uint32_t m = len;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        cr += __shfl_xor_sync(0xffffffffu, cr, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (m) atomicMax(&info->max_len[mate], m);
-        if (cr) atomicAdd(&info->n_cr_eol[mate], cr);
-    }
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&info->max_len[mate], m);
     if (bad) {
         atomicOr(&info->err, kErrLenMismatch);
         atomicMin(&info->err_record, r);
@@ -223,6 +374,17 @@ __global__ void __launch_bounds__(256) k_detect_offset(const uint8_t *__restrict
 }
 
 // parse_id(r1.def) == parse_id(r2.def) (trim.cpp:188-222, FaQCs.cpp:383-389).  One thread per pair.
+// Headers are read as aligned 32-bit words (funnel-shifted to the header start): the common
+// case -- ids equal up to the first space -- is decided after ~|id|/4 word compares.
+__device__ __forceinline__ uint32_t load_word_at(const uint8_t *p)
+{
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const uint32_t lo = __ldg(w);
+    const uint32_t hi = sh ? __ldg(w + 1) : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
 __device__ __forceinline__ uint32_t id_length(const uint8_t *h, uint32_t n)
 {
     uint32_t loc = 0;
@@ -240,6 +402,21 @@ __global__ void __launch_bounds__(256) k_check_pair_ids(const uint8_t *__restric
     const Rec a = rec1[r], b = rec2[r];
     uint32_t na = a.seq - a.hdr - 1, nb = b.seq - b.hdr - 1;
     const uint8_t *ha = raw1 + a.hdr, *hb = raw2 + b.hdr;
+    // fast path: both headers agree word by word up to and including a space (no '/1' '.1' suffix before it)
+    {
+        const uint32_t m = min(na, nb);
+        bool decided = false, same = false;
+        for (uint32_t i = 0; i + 4 <= m && !decided; i += 4) {
+            const uint32_t wa = load_word_at(ha + i), wb = load_word_at(hb + i);
+            const uint32_t sp = __vcmpeq4(wa, 0x20202020u);      // 0xff where wa holds a space
+            const uint32_t diff = wa ^ wb;
+            const uint32_t fs = sp ? (uint32_t)((__ffs(sp) - 1) >> 3) : 4u;      // first space (little endian byte order)
+            const uint32_t fd = diff ? (uint32_t)((__ffs(diff) - 1) >> 3) : 4u;  // first differing byte
+            if (fs < fd) { same = true; decided = true; }        // identical up to and including the first space
+            else if (fd < 4) decided = true;                     // differ before a space: let the exact path decide
+        }
+        if (decided && same) return;
+    }
     if (na && ha[na - 1] == '\r') --na;
     if (nb && hb[nb - 1] == '\r') --nb;
     const uint32_t la = id_length(ha, na), lb = id_length(hb, nb);
