@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Regenerate the committed golden fixtures by running the UNMODIFIED reference binary
+(oracle/_ref/FaQCs, built from /root/reference by `make -C oracle ref`) on small seeded inputs.
+
+    python tests/golden/make_golden.py
+
+Each fixture is one .npz holding the inputs, the reference's emitted FASTQ streams, its
+QC.stats.txt and the integers of its ten --debug matrix / histogram files.  The tests in
+tests/test_golden.py replay them against the CPU oracle (always) and the CUDA path (-m gpu),
+so parity stays pinned on machines where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import refcli  # noqa: E402
+from faqcs_b200 import synth  # noqa: E402
+from faqcs_b200.api import MODE_HARD, Options  # noqa: E402
+from parity import MATRIX_FIELDS  # noqa: E402
+
+AD = dict(__import__("faqcs_b200.api", fromlist=["BUILTIN_ADAPTERS"]).BUILTIN_ADAPTERS)
+
+
+def micro_records():
+    rng = np.random.default_rng(2026)
+    rnd = lambda n, al="ACGT": "".join(rng.choice(list(al), size=n))
+    noA = lambda n: rnd(n, "CGT")
+    recs = [("@hard_all_low", "A" * 30 + "C" * 30, "#" * 60), ("@hard_high_low", "ACGT" * 15, "I" * 30 + "#" * 30),
+            ("@termN", "NN" + rnd(70) + "TNN", "I" * 75), ("@allN", "N" * 64, "I" * 64),
+            ("@mono86", "A" * 86 + "CGTCGTCGTCGTCG", "I" * 99 + "5"), ("@di", "AC" * 50, "I" * 99 + "5"),
+            ("@q2", rnd(20) + AD["Nextera-primer-adapter-1"] + rnd(10) + AD["Nextera-primer-adapter-2"] + rnd(30), "I" * 124 + "5"),
+            ("@tie", noA(30) + "A" * 20 + noA(30) + "A" * 20 + noA(10), "I" * 109 + "5"),
+            ("@polyG", "G" * 80, "I" * 79 + "5")]
+    for L in range(1, 30):
+        q = "".join(chr(33 + int(x)) for x in rng.choice([2, 2, 2, 8, 20, 30, 40], size=L))
+        recs.append((f"@short{L}", rnd(L, "ACGTN"), q))
+    return recs
+
+
+CASES = {
+    # name: (workload factory, Options kwargs, reference extras)
+    "c2_defaults": (lambda: synth.c2(1500), dict(discard_output=True), dict(threads=2)),
+    "c4_qc_only": (lambda: synth.c4(3000), dict(qc_only=True), dict(threads=1)),
+    "c5_hard_ascii64": (lambda: synth.c5(2500), dict(mode=MODE_HARD, quality=20, average_quality=25.0, replace_to_N_q=10,
+                                                      discard_output=True), dict(threads=2)),
+    "c3_adapters": (lambda: synth.c3(400), dict(filter_adapter=True, num_thread=1), dict(threads=1, polyA=True, artifacts=True)),
+    "micro_adapter_polya": (lambda: synth.Workload("micro", np.frombuffer(synth.fastq_bytes(micro_records()), dtype=np.uint8), None, []),
+                            dict(filter_adapter=True, num_thread=1, min_read_length=1, low_complexity_cutoff_ratio=1.0, quality=10,
+                                 input_quality_offset=33, discard_output=True), dict(threads=1, polyA=True)),
+}
+
+
+def main():
+    assert refcli.have_ref(), "build the reference first: make -C oracle ref"
+    for name, (factory, okw, extra) in CASES.items():
+        w = factory()
+        opt = Options(**okw)
+        polyA = extra.get("polyA", False)
+        artifacts = w.artifacts if extra.get("artifacts") else None
+        flags = refcli.flags_for(opt, polyA=polyA)
+        if w.r2 is not None:
+            ref = refcli.run_reference(w.r1, w.r2, flags=flags, threads=extra["threads"], artifacts=artifacts)
+        else:
+            ref = refcli.run_reference(unpaired=w.r1, flags=flags, threads=extra["threads"], artifacts=artifacts)
+        assert ref["returncode"] == 0, ref["stderr"]
+        adapters = refcli.adapters_for(opt.filter_adapter, polyA, artifacts)
+        out = dict(r1=np.asarray(w.r1), r2=np.asarray(w.r2) if w.r2 is not None else np.zeros(0, np.uint8),
+                   paired=np.array([w.r2 is not None]), stats_txt=np.frombuffer(ref["stats_txt"].encode(), dtype=np.uint8),
+                   options=np.frombuffer(repr(okw).encode(), dtype=np.uint8),
+                   adapters=np.frombuffer(repr(adapters).encode(), dtype=np.uint8),
+                   cmd=np.frombuffer(" ".join(["FaQCs"] + flags + ["-t", str(extra["threads"])]).encode(), dtype=np.uint8))
+        for i, s in enumerate(ref["streams"]):
+            out[f"stream{i}"] = np.frombuffer(s, dtype=np.uint8)
+        for f in MATRIX_FIELDS:
+            out[f] = ref[f]
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()
