@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block-pairs", type=int, default=250_000, help="pairs generated on the host (numpy)")
     ap.add_argument("--batch-pairs", type=int, default=2_000_000, help="pairs per step (block replicated in HBM)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-pairs", type=int, default=500_000, help="sample size of the cpu_baseline leg")
     ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,18 +281,29 @@ def main():
             h2[k * w.r2.size:(k + 1) * w.r2.size] = w.r2
         cb2 = CBatchOut()
 
-        def host_step():
-            eng._check(eng.lib.fq_process_host(eng.ctx, C.c_void_p(h1.ctypes.data), n1, C.c_void_p(h2.ctypes.data), n2, 0, 1, C.byref(cb2)))
+        def pipeline(n_steps):
+            """submit(i+1); run(i); wait(i-1): upload, kernels and download of three consecutive batches overlap."""
+            tk = [None] * n_steps
+            t = C.c_uint64()
+            eng._check(eng.lib.fq_submit_host(eng.ctx, C.c_void_p(h1.ctypes.data), n1, C.c_void_p(h2.ctypes.data), n2, 0, 1, C.byref(t)))
+            tk[0] = t.value
+            for i in range(n_steps):
+                if i + 1 < n_steps:
+                    eng._check(eng.lib.fq_submit_host(eng.ctx, C.c_void_p(h1.ctypes.data), n1, C.c_void_p(h2.ctypes.data), n2, 0, 1, C.byref(t)))
+                    tk[i + 1] = t.value
+                eng._check(eng.lib.fq_run(eng.ctx, tk[i]))
+                if i > 0:
+                    eng._check(eng.lib.fq_wait(eng.ctx, tk[i - 1], C.byref(cb2)))
+            eng._check(eng.lib.fq_wait(eng.ctx, tk[n_steps - 1], C.byref(cb2)))
 
-        host_step()
+        pipeline(2)                                  # warm-up: allocates the pinned output slots
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(ext)
-        for _ in range(args.e2e_steps):
-            host_step()
+        pipeline(args.e2e_steps)
         f1.record(ext)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -302,7 +313,7 @@ def main():
         e2e = {"value": world * reads_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": n1 + n2, "d2h_bytes_per_step": int(sum(int(cb2.bytes[i]) for i in range(4))),
                "ms_per_step": float(ems.item()) / args.e2e_steps,
-               "api": "fq_process_host (pinned host buffers, synchronous H2D -> kernels -> D2H)"}
+               "api": "fq_submit_host / fq_run / fq_wait (pinned host buffers; H2D, kernels and D2H of consecutive batches overlap)"}
         eng.host_free(h1)
         eng.host_free(h2)
 

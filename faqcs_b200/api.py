@@ -267,6 +267,10 @@ class Engine:
             L.fq_stream.restype = C.c_void_p
             L.fq_stats_device_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                                  C.POINTER(C.c_void_p)]
+            L.fq_submit_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int,
+                                         C.POINTER(C.c_uint64)]
+            L.fq_run.argtypes = [C.c_void_p, C.c_uint64]
+            L.fq_wait.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(CBatchOut)]
             L.fq_stats_reserve_rows.argtypes = [C.c_void_p, C.c_uint32]
             L.fq_set_check_pair_ids.argtypes = [C.c_void_p, C.c_int]
             L.fq_host_alloc.argtypes = [C.c_size_t]
@@ -349,6 +353,25 @@ class Engine:
                                                C.c_void_p(d_r2) if d_r2 else None, n2,
                                                first_record_index, int(is_final), int(copy_out), C.byref(out)))
         return self._collect(out, d_r2 is not None, want_data=copy_out)
+
+    # ---- pipelined host path (submit -> run -> wait) ---------------------------------------------
+    def submit(self, r1, r2=None, first_record_index: int = 0, is_final: bool = True) -> int:
+        p1, n1, k1 = self._buf(r1)
+        p2, n2, k2 = self._buf(r2)
+        t = C.c_uint64()
+        self._check(self.lib.fq_submit_host(self.ctx, p1, n1, p2, n2, first_record_index, int(is_final), C.byref(t)))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (k1, k2, r2 is not None)       # keep the host buffers alive until run()
+        return t.value
+
+    def run(self, ticket: int):
+        self._check(self.lib.fq_run(self.ctx, ticket))
+
+    def wait(self, ticket: int, want_data: bool = True) -> BatchResult:
+        out = CBatchOut()
+        self._check(self.lib.fq_wait(self.ctx, ticket, C.byref(out)))
+        _, _, paired = self._inflight.pop(ticket)
+        return self._collect(out, paired, want_data=want_data)
 
     def last_timing(self) -> dict:
         """Device ms of the last batch by segment (CUDA events on the context's stream)."""

@@ -88,11 +88,18 @@ struct fq_ctx {
     AdapterSet aset{};
     DevBuf d_adp_codes, d_adp_off, d_adp_or;
 
-    DevBuf d_raw[2], d_chunk[2], d_nl[2], d_rec[2], d_canon[2], d_adp[2], d_adp_best[2], d_res[2], d_dbg[2], d_tile, d_out[4];
+    DevBuf d_raw[2], d_chunk[2], d_nl[2], d_rec[2], d_canon[2], d_adp[2], d_adp_best[2], d_res[2], d_dbg[2], d_tile, d_out[2][4];
+    DevBuf d_raw_slot[2][2];           // pipelined submit: raw input slots
     DevBuf d_info, d_stats, d_rows;
     BatchInfo *h_info = nullptr;       // pinned
     StatsLayout L{};
-    PinnedBuf h_out[4], h_dbg[2], h_stats;
+    PinnedBuf h_out[2][4], h_dbg[2], h_stats;
+    int out_slot = 0;                   // which d_out / h_out set process_common fills
+    bool async_out = false;            // D2H on s_out, caller waits on ev_out
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    struct Pending { bool used = false, ran = false; size_t n1 = 0, n2 = 0; bool paired = false; uint64_t first = 0; int is_final = 0; uint64_t ticket = 0; fq_batch_out out{}; } pend[2];
+    uint64_t next_ticket = 0;
     bool debug_results = false;
     bool check_pair_ids = true;
 
@@ -436,8 +443,8 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         // a trimmed record is never longer than its raw record, so the inputs bound the outputs
         const size_t cap[4] = {paired ? n1 : 0, paired ? n2 : 0, paired ? std::max(n1, n2) : n1, o.discard ? n1 + n2 : 0};
         for (int s = 0; s < 4; ++s) {
-            if (cap[s]) CK(ctx->d_out[s].ensure(cap[s] + 16));
-            ea.out[s] = ctx->d_out[s].as<uint8_t>();
+            if (cap[s]) CK(ctx->d_out[ctx->out_slot][s].ensure(cap[s] + 16));
+            ea.out[s] = ctx->d_out[ctx->out_slot][s].as<uint8_t>();
         }
     }
     k_route<<<ea.n_tiles, kTile, 0, ctx->stream>>>(ea, o);
@@ -465,15 +472,24 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     out->paired_base_length = hi.paired_bases;
     for (int s = 0; s < 4; ++s) {
         out->bytes[s] = o.qc_only ? 0 : hi.out_bytes[s];
-        ctx->last_dev_out[s] = out->bytes[s] ? ctx->d_out[s].p : nullptr;
+        ctx->last_dev_out[s] = out->bytes[s] ? ctx->d_out[ctx->out_slot][s].p : nullptr;
     }
     if (copy_out) {
+        // D2H of the four streams: on the compute stream (synchronous API) or, pipelined, on the copy-out
+        // stream behind an event so that it overlaps the next batch's kernels
+        cudaStream_t cs = ctx->stream;
+        if (ctx->async_out) {
+            CK(cudaEventRecord(ctx->ev_comp[ctx->out_slot], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[ctx->out_slot], 0));
+            cs = ctx->s_out;
+        }
         for (int s = 0; s < 4; ++s) {
             if (!out->bytes[s]) continue;
-            CK(ctx->h_out[s].ensure(out->bytes[s]));
-            CK(cudaMemcpyAsync(ctx->h_out[s].p, ctx->d_out[s].p, out->bytes[s], cudaMemcpyDeviceToHost, ctx->stream));
-            out->data[s] = static_cast<const uint8_t *>(ctx->h_out[s].p);
+            CK(ctx->h_out[ctx->out_slot][s].ensure(out->bytes[s]));
+            CK(cudaMemcpyAsync(ctx->h_out[ctx->out_slot][s].p, ctx->d_out[ctx->out_slot][s].p, out->bytes[s], cudaMemcpyDeviceToHost, cs));
+            out->data[s] = static_cast<const uint8_t *>(ctx->h_out[ctx->out_slot][s].p);
         }
+        if (ctx->async_out) CK(cudaEventRecord(ctx->ev_out[ctx->out_slot], ctx->s_out));
     }
     if (ctx->debug_results) {
         for (int m = 0; m < n_mates; ++m) {
@@ -518,6 +534,13 @@ fq_status fq_create(const fq_options *opt, int device, fq_ctx **out)
         ctx->sm_count = prop.multiProcessorCount;
         ctx->smem_optin = prop.sharedMemPerBlockOptin;
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_out[k], cudaEventDisableTiming));
+        }
         for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_info), sizeof(BatchInfo)));
         CK(ctx->d_info.ensure(sizeof(BatchInfo)));
@@ -548,7 +571,15 @@ void fq_destroy(fq_ctx *ctx)
         ctx->d_adp[m].release(); ctx->d_adp_best[m].release(); ctx->d_res[m].release(); ctx->d_dbg[m].release();
         ctx->h_dbg[m].release();
     }
-    for (int s = 0; s < 4; ++s) { ctx->d_out[s].release(); ctx->h_out[s].release(); }
+    for (int k = 0; k < 2; ++k) {
+        for (int s = 0; s < 4; ++s) { ctx->d_out[k][s].release(); ctx->h_out[k][s].release(); }
+        for (int m = 0; m < 2; ++m) ctx->d_raw_slot[k][m].release();
+        if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+        if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
+        if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
+    }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     ctx->d_tile.release(); ctx->d_info.release(); ctx->d_stats.release(); ctx->d_rows.release();
     ctx->d_adp_codes.release(); ctx->d_adp_off.release(); ctx->d_adp_or.release();
     ctx->h_stats.release();
@@ -648,8 +679,68 @@ fq_status fq_process_host(fq_ctx *ctx, const uint8_t *r1, size_t n1, const uint8
         CK(ctx->d_raw[1].ensure(n2 + 16));
         if (n2) CK(cudaMemcpyAsync(ctx->d_raw[1].p, r2, n2, cudaMemcpyHostToDevice, ctx->stream));
     }
+    ctx->out_slot = 0;
+    ctx->async_out = false;
     return process_common(ctx, ctx->d_raw[0].as<uint8_t>(), n1, paired ? ctx->d_raw[1].as<uint8_t>() : nullptr, n2, paired,
                           first_record_index, is_final, 1, out);
+}
+
+// ---- pipelined host path: submit (H2D on its own stream) / run (kernels) / wait (D2H on its own stream) ----
+fq_status fq_submit_host(fq_ctx *ctx, const uint8_t *r1, size_t n1, const uint8_t *r2, size_t n2,
+                         uint64_t first_record_index, int is_final, uint64_t *ticket)
+{
+    if (!ctx || !ticket || (!r1 && n1) || (!r2 && n2)) return FQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t t = ctx->next_ticket;
+    const int slot = (int)(t & 1);
+    if (ctx->pend[slot].used) return fail(ctx, FQ_ERR_STATE, "fq_submit_host: the batch submitted two tickets ago has not been collected with fq_wait");
+    fq_ctx::Pending &p = ctx->pend[slot];
+    p = fq_ctx::Pending{};
+    p.used = true;
+    p.n1 = n1; p.n2 = n2; p.paired = r2 != nullptr; p.first = first_record_index; p.is_final = is_final; p.ticket = t;
+    CK(ctx->d_raw_slot[slot][0].ensure(n1 + 16));
+    if (n1) CK(cudaMemcpyAsync(ctx->d_raw_slot[slot][0].p, r1, n1, cudaMemcpyHostToDevice, ctx->s_in));
+    if (p.paired) {
+        CK(ctx->d_raw_slot[slot][1].ensure(n2 + 16));
+        if (n2) CK(cudaMemcpyAsync(ctx->d_raw_slot[slot][1].p, r2, n2, cudaMemcpyHostToDevice, ctx->s_in));
+    }
+    CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+    ctx->next_ticket++;
+    *ticket = t;
+    return FQ_OK;
+}
+
+fq_status fq_run(fq_ctx *ctx, uint64_t ticket)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    const int slot = (int)(ticket & 1);
+    fq_ctx::Pending &p = ctx->pend[slot];
+    if (!p.used || p.ticket != ticket || p.ran) return fail(ctx, FQ_ERR_STATE, "fq_run: unknown or already processed ticket");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
+    ctx->out_slot = slot;
+    ctx->async_out = true;
+    fq_status st = process_common(ctx, ctx->d_raw_slot[slot][0].as<uint8_t>(), p.n1, p.paired ? ctx->d_raw_slot[slot][1].as<uint8_t>() : nullptr,
+                                  p.n2, p.paired, p.first, p.is_final, 1, &p.out);
+    ctx->async_out = false;
+    if (st != FQ_OK) { p.used = false; return st; }
+    p.ran = true;
+    return FQ_OK;
+}
+
+fq_status fq_wait(fq_ctx *ctx, uint64_t ticket, fq_batch_out *out)
+{
+    if (!ctx || !out) return FQ_ERR_ARG;
+    const int slot = (int)(ticket & 1);
+    fq_ctx::Pending &p = ctx->pend[slot];
+    if (!p.used || p.ticket != ticket || !p.ran) return fail(ctx, FQ_ERR_STATE, "fq_wait: ticket has not been run");
+    CK(cudaSetDevice(ctx->device));
+    bool any = false;
+    for (int s = 0; s < 4; ++s) any |= p.out.bytes[s] != 0;
+    if (any) CK(cudaEventSynchronize(ctx->ev_out[slot]));
+    *out = p.out;
+    p.used = false;
+    return FQ_OK;
 }
 
 fq_status fq_process_device(fq_ctx *ctx, const void *d_r1, size_t n1, const void *d_r2, size_t n2,
@@ -657,6 +748,8 @@ fq_status fq_process_device(fq_ctx *ctx, const void *d_r1, size_t n1, const void
 {
     if (!ctx || !out || (!d_r1 && n1) || (!d_r2 && n2)) return FQ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    ctx->out_slot = 0;
+    ctx->async_out = false;
     return process_common(ctx, static_cast<const uint8_t *>(d_r1), n1, static_cast<const uint8_t *>(d_r2), n2, d_r2 != nullptr,
                           first_record_index, is_final, copy_out, out);
 }

@@ -229,6 +229,20 @@ fq_status fq_process_host(fq_ctx *ctx, const uint8_t *r1, size_t n1,
                           uint64_t first_record_index, int is_final,
                           fq_batch_out *out);
 
+/* Pipelined form of fq_process_host for streaming runs.  fq_submit_host starts the host->device
+ * copy of a batch on its own stream and returns a ticket; fq_run executes the kernels for that
+ * ticket and starts the device->host copy of its outputs on another stream; fq_wait blocks until
+ * those outputs are in host memory.  Two batches can be in flight, so the usual loop is
+ *     submit(i+1); run(i); wait(i-1);
+ * which overlaps upload(i+1), compute(i) and download(i-1).  Tickets must be run and waited in
+ * submission order; the input buffers must stay valid until fq_run(ticket) has returned, the
+ * output pointers until the ticket two submissions later is run. */
+fq_status fq_submit_host(fq_ctx *ctx, const uint8_t *r1, size_t n1,
+                         const uint8_t *r2, size_t n2,
+                         uint64_t first_record_index, int is_final, uint64_t *ticket);
+fq_status fq_run(fq_ctx *ctx, uint64_t ticket);
+fq_status fq_wait(fq_ctx *ctx, uint64_t ticket, fq_batch_out *out);
+
 /* Same, with the raw bytes already resident in device memory (d_r1/d_r2 are
  * device pointers on the context's device).  Output stays on the device unless
  * copy_out != 0; out->data then points at host copies as above.  With

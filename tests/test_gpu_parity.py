@@ -133,6 +133,35 @@ def test_pairs_routing_with_discard():
     both(a, b, lambda: Options(discard_output=True, quality=12, input_quality_offset=33), batch_records=700)
 
 
+def test_pipelined_submit_run_wait_equals_synchronous():
+    from faqcs_b200 import shard
+    w = synth.c2(12000)
+    opt = lambda: Options(discard_output=True, quality=12)
+    with Engine(opt()) as a, Engine(opt()) as b:
+        a.autodetect(w.r1, w.r2)
+        b.autodetect(w.r1, w.r2)
+        sync = a.process(w.r1, w.r2)
+        b1, b2 = shard.record_batches(w.r1, 2500), shard.record_batches(w.r2, 2500)
+        n = len(b1)
+        streams = [b"", b"", b"", b""]
+        tk = [None] * n
+        tk[0] = b.submit(w.r1[b1[0][0]:b1[0][1]], w.r2[b2[0][0]:b2[0][1]], 0, n == 1)
+        done = []
+        for i in range(n):
+            if i + 1 < n:
+                tk[i + 1] = b.submit(w.r1[b1[i + 1][0]:b1[i + 1][1]], w.r2[b2[i + 1][0]:b2[i + 1][1]], (i + 1) * 2500, i + 2 == n)
+            b.run(tk[i])
+            if i > 0:
+                done.append(b.wait(tk[i - 1]))
+        done.append(b.wait(tk[n - 1]))
+        for res in done:
+            for k in range(4):
+                streams[k] += res.streams[k]
+        assert [bytes(x) for x in streams] == [bytes(x) for x in sync.streams]
+        assert not a.stats().diff(b.stats())
+        assert sum(r.n_records for r in done) == sync.n_records
+
+
 def test_long_reads_beyond_shared_rows():
     rng = np.random.default_rng(12)
     recs = []
