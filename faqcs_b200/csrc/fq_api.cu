@@ -98,7 +98,9 @@ struct fq_ctx {
     bool async_out = false;            // D2H on s_out, caller waits on ev_out
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    struct Pending { bool used = false, ran = false; size_t n1 = 0, n2 = 0; bool paired = false; uint64_t first = 0; int is_final = 0; uint64_t ticket = 0; fq_batch_out out{}; } pend[2];
+    // pipelined path: an input slot is busy from submit until run returns, an output slot from run until wait
+    struct Submitted { bool busy = false; size_t n1 = 0, n2 = 0; bool paired = false; uint64_t first = 0; int is_final = 0; uint64_t ticket = 0; } sub[2];
+    struct Finished { bool busy = false; uint64_t ticket = 0; fq_batch_out out{}; } fin[2];
     uint64_t next_ticket = 0;
     bool debug_results = false;
     bool check_pair_ids = true;
@@ -693,10 +695,10 @@ fq_status fq_submit_host(fq_ctx *ctx, const uint8_t *r1, size_t n1, const uint8_
     CK(cudaSetDevice(ctx->device));
     const uint64_t t = ctx->next_ticket;
     const int slot = (int)(t & 1);
-    if (ctx->pend[slot].used) return fail(ctx, FQ_ERR_STATE, "fq_submit_host: the batch submitted two tickets ago has not been collected with fq_wait");
-    fq_ctx::Pending &p = ctx->pend[slot];
-    p = fq_ctx::Pending{};
-    p.used = true;
+    if (ctx->sub[slot].busy) return fail(ctx, FQ_ERR_STATE, "fq_submit_host: the batch submitted two tickets ago has not been run yet");
+    fq_ctx::Submitted &p = ctx->sub[slot];
+    p = fq_ctx::Submitted{};
+    p.busy = true;
     p.n1 = n1; p.n2 = n2; p.paired = r2 != nullptr; p.first = first_record_index; p.is_final = is_final; p.ticket = t;
     CK(ctx->d_raw_slot[slot][0].ensure(n1 + 16));
     if (n1) CK(cudaMemcpyAsync(ctx->d_raw_slot[slot][0].p, r1, n1, cudaMemcpyHostToDevice, ctx->s_in));
@@ -714,17 +716,21 @@ fq_status fq_run(fq_ctx *ctx, uint64_t ticket)
 {
     if (!ctx) return FQ_ERR_ARG;
     const int slot = (int)(ticket & 1);
-    fq_ctx::Pending &p = ctx->pend[slot];
-    if (!p.used || p.ticket != ticket || p.ran) return fail(ctx, FQ_ERR_STATE, "fq_run: unknown or already processed ticket");
+    fq_ctx::Submitted &p = ctx->sub[slot];
+    if (!p.busy || p.ticket != ticket) return fail(ctx, FQ_ERR_STATE, "fq_run: unknown or already processed ticket");
+    if (ctx->fin[slot].busy) return fail(ctx, FQ_ERR_STATE, "fq_run: the outputs of the ticket two submissions ago have not been collected with fq_wait");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
     ctx->out_slot = slot;
     ctx->async_out = true;
+    fq_ctx::Finished &f = ctx->fin[slot];
     fq_status st = process_common(ctx, ctx->d_raw_slot[slot][0].as<uint8_t>(), p.n1, p.paired ? ctx->d_raw_slot[slot][1].as<uint8_t>() : nullptr,
-                                  p.n2, p.paired, p.first, p.is_final, 1, &p.out);
+                                  p.n2, p.paired, p.first, p.is_final, 1, &f.out);
     ctx->async_out = false;
-    if (st != FQ_OK) { p.used = false; return st; }
-    p.ran = true;
+    p.busy = false;                       // the kernels are done with the raw input slot
+    if (st != FQ_OK) return st;
+    f.busy = true;
+    f.ticket = ticket;
     return FQ_OK;
 }
 
@@ -732,14 +738,14 @@ fq_status fq_wait(fq_ctx *ctx, uint64_t ticket, fq_batch_out *out)
 {
     if (!ctx || !out) return FQ_ERR_ARG;
     const int slot = (int)(ticket & 1);
-    fq_ctx::Pending &p = ctx->pend[slot];
-    if (!p.used || p.ticket != ticket || !p.ran) return fail(ctx, FQ_ERR_STATE, "fq_wait: ticket has not been run");
+    fq_ctx::Finished &f = ctx->fin[slot];
+    if (!f.busy || f.ticket != ticket) return fail(ctx, FQ_ERR_STATE, "fq_wait: ticket has not been run");
     CK(cudaSetDevice(ctx->device));
     bool any = false;
-    for (int s = 0; s < 4; ++s) any |= p.out.bytes[s] != 0;
+    for (int s = 0; s < 4; ++s) any |= f.out.bytes[s] != 0;
     if (any) CK(cudaEventSynchronize(ctx->ev_out[slot]));
-    *out = p.out;
-    p.used = false;
+    *out = f.out;
+    f.busy = false;
     return FQ_OK;
 }
 
