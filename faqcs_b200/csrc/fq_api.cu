@@ -236,27 +236,34 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
     if (n >= (1ull << 30)) return fail(ctx, FQ_ERR_ARG, "batch larger than 1 GiB per mate: split it");
     if ((reinterpret_cast<uintptr_t>(d_raw) & 15) != 0) return fail(ctx, FQ_ERR_ARG, "device input must be 16-byte aligned");
     BatchInfo *info = ctx->d_info.as<BatchInfo>();
-    // single-pass line index (k_frame_lines); nl_pos capacity is a guess (>= 24 bytes per line on average),
-    // the kernel counts every line regardless, so an overflow is detected and the pass repeated once.
-    const uint32_t n_tiles = (uint32_t)((n + kFrameTile - 1) / kFrameTile);
-    CK(ctx->d_chunk[m].ensure((size_t)n_tiles * 8 + 16));
+    // single-pass segmented line index: one contiguous segment per resident warp, no cross-warp dependency
+    int frame_ctas = 4;                                     // resident CTAs per SM -> exactly one wave of segments
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&frame_ctas, k_frame_lines, kFrameThreads, 0));
+    const uint32_t want_warps = (uint32_t)ctx->sm_count * (uint32_t)std::max(frame_ctas, 1) * (kFrameThreads / 32);
+    uint32_t seg_bytes = (uint32_t)((n + want_warps - 1) / want_warps);
+    seg_bytes = std::max<uint32_t>(kChunkBytes, (seg_bytes + kChunkBytes - 1) / kChunkBytes * kChunkBytes);
+    const uint32_t n_seg = (uint32_t)((n + seg_bytes - 1) / seg_bytes);
+    CK(ctx->d_chunk[m].ensure(((size_t)n_seg * 2 + 2) * 4));
+    uint32_t *seg_count = ctx->d_chunk[m].as<uint32_t>();
+    uint32_t *seg_base = seg_count + n_seg;
     uint32_t n_lines = 0;
-    size_t cap_lines = std::max<size_t>(1u << 16, n / 24);
+    uint32_t seg_cap = seg_bytes / 24 + 64;                 // lines per segment region: >= 24 bytes per line on average
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CK(ctx->d_nl[m].ensure(cap_lines * 4));
-        CK(cudaMemsetAsync(ctx->d_chunk[m].p, 0, (size_t)n_tiles * 8 + 16, ctx->stream));
-        unsigned long long *status = ctx->d_chunk[m].as<unsigned long long>();
-        uint32_t *ticket = reinterpret_cast<uint32_t *>(status + n_tiles);
-        const int grid = std::max(1, std::min<int>(n_tiles, ctx->sm_count * 8));
-        if (attempt) { CK(cudaMemsetAsync(&info->n_cr[m], 0, 4, ctx->stream)); CK(cudaMemsetAsync(&info->n_cr_eol[m], 0, 4, ctx->stream)); }
-        k_frame_lines<<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, ctx->d_nl[m].as<uint32_t>(), (uint32_t)std::min<size_t>(cap_lines, 0xffffffffu),
-                                                              status, ticket, n_tiles, info, m);
-        ctx->launches++;
+        CK(ctx->d_nl[m].ensure((size_t)n_seg * seg_cap * 4));
+        const int grid = (n_seg + kFrameThreads / 32 - 1) / (kFrameThreads / 32);
+        if (attempt) {
+            CK(cudaMemsetAsync(&info->n_cr[m], 0, 4, ctx->stream));
+            CK(cudaMemsetAsync(&info->n_cr_eol[m], 0, 4, ctx->stream));
+            CK(cudaMemsetAsync(&info->seg_overflow, 0, 4, ctx->stream));
+        }
+        k_frame_lines<<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, seg_bytes, n_seg, ctx->d_nl[m].as<uint32_t>(), seg_cap, seg_count, info, m);
+        k_scan_segments<<<1, 1024, 0, ctx->stream>>>(seg_count, n_seg, seg_base, info, m);
+        ctx->launches += 2;
         CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         n_lines = ctx->h_info->n_lines[m];
-        if (n_lines <= cap_lines) break;
-        cap_lines = n_lines;
+        if (ctx->h_info->seg_overflow == 0) break;
+        seg_cap = ctx->h_info->seg_overflow + 64;           // very short lines: repeat once with the exact need
     }
     if (ctx->h_info->n_cr[m]) {
         // CRLF input (or stray CRs): exact CR count, to be compared with the CRs that sit right before a '\n'
@@ -273,7 +280,8 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
     if (n_rec == 0) return FQ_OK;
     CK(ctx->d_rec[m].ensure((size_t)n_rec * sizeof(Rec)));
     CK(ctx->d_canon[m].ensure((size_t)n_rec));
-    k_build_records<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nl[m].as<uint32_t>(), n_rec, ctx->d_rec[m].as<Rec>(), ctx->d_canon[m].as<uint8_t>(), info, m);
+    const LineIndex li{ctx->d_nl[m].as<uint32_t>(), seg_base, seg_cap, n_seg};
+    k_build_records<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(li, n_rec, ctx->d_rec[m].as<Rec>(), ctx->d_canon[m].as<uint8_t>(), info, m);
     ctx->launches++;
     *n_rec_out = n_rec;
     return FQ_OK;

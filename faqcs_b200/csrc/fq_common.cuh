@@ -63,6 +63,8 @@ struct BatchInfo {
     uint32_t n_cr_eol[2];      // '\r' immediately before a line's '\n'
     uint32_t err;              // kErr* bits
     uint32_t err_record;       // smallest record index that raised an error
+    uint32_t seg_overflow;     // largest per-segment line count that did not fit its index region (0 = none)
+    uint32_t pad0;
     unsigned long long detect_key;   // autodetect: (record << 8 | offset), min over decisive reads
     unsigned long long out_bytes[4];
     unsigned long long n_valid[2];

@@ -31,134 +31,8 @@ __device__ __forceinline__ uint32_t match16(const uint4 &v, uint32_t c4)
     return m4(v.x) | (m4(v.y) << 4) | (m4(v.z) << 8) | (m4(v.w) << 12);
 }
 
-// Pass 1: newline (and CR) count per 4 KiB chunk.  `n` bytes at `raw` (16-byte aligned).
-__global__ void __launch_bounds__(256) k_count_lines(const uint8_t *__restrict__ raw, uint64_t n,
-                                                     uint32_t *__restrict__ chunk_count, uint32_t n_chunks,
-                                                     BatchInfo *info, int mate)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    uint32_t cr_total = 0;
-    for (uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps_per_grid) {
-        const uint64_t base = (uint64_t)chunk * kChunkBytes;
-        uint32_t cnt = 0;
-        if (base + kChunkBytes <= n) {
-            const uint4 *p = reinterpret_cast<const uint4 *>(raw + base);
-            uint4 v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = ld_stream16(p + k * 32 + lane);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                cnt += __popc(match16(v[k], 0x0a0a0a0au));
-                cr_total += __popc(match16(v[k], 0x0d0d0d0du));
-            }
-        } else {                                       // ragged tail chunk: byte loop
-            for (uint64_t i = base + lane; i < n; i += 32) {
-                const uint8_t c = raw[i];
-                cnt += (c == '\n');
-                cr_total += (c == '\r');
-            }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) chunk_count[chunk] = cnt;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) cr_total += __shfl_xor_sync(0xffffffffu, cr_total, o);
-    if (lane == 0 && cr_total) atomicAdd(&info->n_cr[mate], cr_total);
-}
-
-// Exclusive scan of the chunk counts (single CTA, 1024 threads, sequential tiles).
-__global__ void __launch_bounds__(1024) k_scan_chunks(uint32_t *__restrict__ chunk_count, uint32_t n_chunks,
-                                                      BatchInfo *info, int mate)
-{
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_chunks; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n_chunks ? chunk_count[i] : 0;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= (uint32_t)o) x += y;
-        }
-        if (lane == 31) warp_sum[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t s = warp_sum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= (uint32_t)o) s += y;
-            }
-            warp_sum[lane] = s;     // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t before = carry + (wid ? warp_sum[wid - 1] : 0) + (x - v);
-        if (i < n_chunks) chunk_count[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) info->n_lines[mate] = carry;
-}
-
-// Pass 2: write the byte offset of every '\n' at its global rank.
-__global__ void __launch_bounds__(256) k_scatter_lines(const uint8_t *__restrict__ raw, uint64_t n,
-                                                       const uint32_t *__restrict__ chunk_base, uint32_t n_chunks,
-                                                       uint32_t *__restrict__ nl_pos)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps_per_grid) {
-        const uint64_t base = (uint64_t)chunk * kChunkBytes;
-        uint32_t rank = chunk_base[chunk];
-        if (base + kChunkBytes <= n) {
-            const uint4 *p = reinterpret_cast<const uint4 *>(raw + base);
-            uint4 v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = ld_stream16(p + k * 32 + lane);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint32_t m = match16(v[k], 0x0a0a0a0au);
-                const uint32_t c = __popc(m);
-                uint32_t x = c;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                    if (lane >= (uint32_t)o) x += y;
-                }
-                uint32_t r = rank + x - c;
-                const uint32_t pos0 = (uint32_t)(base + (uint64_t)(k * 32 + lane) * 16);
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    nl_pos[r++] = pos0 + b;
-                    m &= m - 1;
-                }
-                rank += __shfl_sync(0xffffffffu, x, 31);
-            }
-        } else {
-            for (uint64_t i0 = base; i0 < n; i0 += 32) {
-                const uint64_t i = i0 + lane;
-                const bool is_nl = i < n && raw[i] == '\n';
-                const uint32_t m = __ballot_sync(0xffffffffu, is_nl);
-                if (is_nl) nl_pos[rank + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
-                rank += __popc(m);
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Single-pass line index: every '\n' offset written at its global rank, one read of the input.
-// 32 KiB tiles handed out by an atomic ticket; the running line count is carried across tiles
-// with a decoupled look-back (status word = flag << 62 | count: 1 = tile aggregate, 2 = inclusive
-// prefix).  Each lane owns 128 contiguous bytes of its warp's 4 KiB chunk, so one warp scan per
-// chunk orders the ranks.
+// Single-pass line index: every '\n' offset recorded in order, one read of the input.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kFrameThreads = 256;
 constexpr uint32_t kFrameTile = (kFrameThreads / 32) * kChunkBytes;   // 32 KiB
@@ -200,35 +74,42 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane)
     return x;
 }
 
-__global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__restrict__ raw, uint64_t n, uint32_t *__restrict__ nl_pos,
-                                                               uint32_t cap_lines, unsigned long long *status, uint32_t *ticket,
-                                                               uint32_t n_tiles, BatchInfo *info, int mate)
+// Line index, one pass, no cross-warp dependency.  Warp w owns the contiguous byte segment
+// [w * seg_bytes, (w+1) * seg_bytes) and streams it 4 KiB at a time (coalesced 16-byte loads);
+// it writes the offsets of its '\n' bytes, in order, to its own region nl_seg[w * seg_cap ...]
+// and its line count to seg_count[w].  A tiny scan (k_scan_segments) then turns the counts into
+// global line bases and k_build_records maps global line numbers to (segment, local index).
+__global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__restrict__ raw, uint64_t n, uint32_t seg_bytes, uint32_t n_seg,
+                                                               uint32_t *__restrict__ nl_seg, uint32_t seg_cap, uint32_t *__restrict__ seg_count,
+                                                               BatchInfo *info, int mate)
 {
-    __shared__ uint32_t s_tile, s_prefix;
-    __shared__ uint32_t s_warp[kFrameThreads / 32];
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t any_cr = 0, cr_eol = 0;
-    while (true) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= n_tiles) break;
-        const uint64_t chunk_base = (uint64_t)tile * kFrameTile + (uint64_t)wid * kChunkBytes;
-        // coalesced: vector k of lane l covers bytes chunk_base + (k*32 + l)*16 .. +16
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_seg) return;
+    const uint64_t seg_lo = (uint64_t)w * seg_bytes;
+    const uint64_t seg_hi = min((uint64_t)n, seg_lo + seg_bytes);
+    uint32_t *out = nl_seg + (size_t)w * seg_cap;
+    uint32_t rank0 = 0, any_cr = 0, cr_eol = 0;
+    for (uint64_t chunk_base = seg_lo; chunk_base < seg_hi; chunk_base += kChunkBytes) {
+        // vector k of lane l covers bytes chunk_base + (k*32 + l)*16 .. +16
         uint32_t m16[4] = {0, 0, 0, 0};                 // two 16-bit newline masks per register
         uint32_t cA = 0, cB = 0, cC = 0;                // per-vector newline counts, 10-bit fields (k = 0..2, 3..5, 6..7)
+        uint4 v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint64_t off = chunk_base + (uint64_t)(k * 32 + lane) * 16;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (off + 16 <= n) v = __ldg(reinterpret_cast<const uint4 *>(raw + off));
-            else if (off < n) {
-                uint32_t w[4] = {0, 0, 0, 0};
-                for (uint32_t b = 0; b < 16 && off + b < n; ++b) w[b >> 2] |= (uint32_t)raw[off + b] << (8 * (b & 3));
-                v = make_uint4(w[0], w[1], w[2], w[3]);
+            v[k] = make_uint4(0, 0, 0, 0);
+            if (off + 16 <= seg_hi) v[k] = __ldg(reinterpret_cast<const uint4 *>(raw + off));
+            else if (off < seg_hi) {
+                uint32_t x[4] = {0, 0, 0, 0};
+                for (uint32_t b = 0; b < 16 && off + b < seg_hi; ++b) x[b >> 2] |= (uint32_t)raw[off + b] << (8 * (b & 3));
+                v[k] = make_uint4(x[0], x[1], x[2], x[3]);
             }
-            const uint32_t m = eq_mask16(v, 0x0a0a0a0au);
-            any_cr |= has_byte(v.x, 0x0d0d0d0du) | has_byte(v.y, 0x0d0d0d0du) | has_byte(v.z, 0x0d0d0d0du) | has_byte(v.w, 0x0d0d0d0du);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t m = eq_mask16(v[k], 0x0a0a0a0au);
+            any_cr |= has_byte(v[k].x, 0x0d0d0d0du) | has_byte(v[k].y, 0x0d0d0d0du) | has_byte(v[k].z, 0x0d0d0d0du) | has_byte(v[k].w, 0x0d0d0d0du);
             m16[k >> 1] |= m << (16 * (k & 1));
             const uint32_t c = __popc(m);
             if (k < 3) cA |= c << (10 * k);
@@ -237,42 +118,6 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__
         }
         const uint32_t iA = warp_incl_scan(cA, lane), iB = warp_incl_scan(cB, lane), iC = warp_incl_scan(cC, lane);
         const uint32_t tA = __shfl_sync(0xffffffffu, iA, 31), tB = __shfl_sync(0xffffffffu, iB, 31), tC = __shfl_sync(0xffffffffu, iC, 31);
-        const uint32_t warp_total = (tA & 1023u) + ((tA >> 10) & 1023u) + (tA >> 20) + (tB & 1023u) + ((tB >> 10) & 1023u) + (tB >> 20) +
-                                    (tC & 1023u) + ((tC >> 10) & 1023u);
-        if (lane == 0) s_warp[wid] = warp_total;
-        __syncthreads();
-        if (wid == 0) {
-            // decoupled look-back, 32 predecessor tiles per step
-            uint32_t tile_total = 0;
-#pragma unroll
-            for (int k = 0; k < (int)(kFrameThreads / 32); ++k) tile_total += s_warp[k];
-            volatile unsigned long long *st = status;
-            uint32_t prefix = 0;
-            if (tile > 0) {
-                if (lane == 0) { st[tile] = (1ull << 62) | tile_total; __threadfence(); }
-                int hi = (int)tile - 1;
-                while (hi >= 0) {
-                    const int j = hi - (int)lane;
-                    unsigned long long sv = 2ull << 62;  // lanes past tile 0 behave like a zero inclusive prefix
-                    if (j >= 0) { do { sv = st[j]; } while ((sv >> 62) == 0); }
-                    const uint32_t incl = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
-                    const int stop = incl ? __ffs(incl) - 1 : 31;
-                    const uint32_t val = (int)lane <= stop ? (uint32_t)sv : 0u;
-                    prefix += __reduce_add_sync(0xffffffffu, val);
-                    if (incl) break;
-                    hi -= 32;
-                }
-            }
-            if (lane == 0) {
-                __threadfence();
-                st[tile] = (2ull << 62) | (unsigned long long)(prefix + tile_total);
-                s_prefix = prefix;
-                if (tile == n_tiles - 1) info->n_lines[mate] = prefix + tile_total;
-            }
-        }
-        __syncthreads();
-        uint32_t rank0 = s_prefix;
-        for (uint32_t k = 0; k < wid; ++k) rank0 += s_warp[k];
         // ranks are ordered by (vector k, lane, byte)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -288,20 +133,47 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__
                 uint32_t e = (uint32_t)pos;
                 if (prev == '\r') { e |= kNlCr; ++cr_eol; }
                 if (prev == '+') e |= kNlPlus;
-                if (rank < cap_lines) nl_pos[rank] = e;
+                if (rank < seg_cap) out[rank] = e;
                 ++rank;
                 m &= m - 1;
             }
             rank0 += tot;
         }
-        __syncthreads();      // s_tile / s_warp / s_prefix are reused by the next tile
     }
     any_cr = __reduce_or_sync(0xffffffffu, any_cr);
     cr_eol = __reduce_add_sync(0xffffffffu, cr_eol);
     if (lane == 0) {
+        seg_count[w] = rank0;
+        if (rank0 > seg_cap) atomicMax(&info->seg_overflow, rank0);
         if (any_cr) atomicOr(&info->n_cr[mate], 1u);      // "some CR exists": the host then asks for the exact count
         if (cr_eol) atomicAdd(&info->n_cr_eol[mate], cr_eol);
     }
+}
+
+// Exclusive scan of the segment line counts (n_seg <= a few thousand): one CTA.  seg_base gets n_seg + 1 entries.
+__global__ void __launch_bounds__(1024) k_scan_segments(const uint32_t *__restrict__ seg_count, uint32_t n_seg, uint32_t *__restrict__ seg_base,
+                                                        BatchInfo *info, int mate)
+{
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_seg; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_seg ? seg_count[i] : 0;
+        const uint32_t x = warp_incl_scan(v, lane);
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        if (wid == 0) warp_sum[lane] = warp_incl_scan(warp_sum[lane], lane);
+        __syncthreads();
+        const uint32_t before = carry + (wid ? warp_sum[wid - 1] : 0) + (x - v);
+        if (i < n_seg) seg_base[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { seg_base[n_seg] = carry; info->n_lines[mate] = carry; }
 }
 
 // Exact count of one byte value (only launched when k_frame_lines saw a '\r': CRLF input).
@@ -313,30 +185,58 @@ __global__ void __launch_bounds__(256) k_count_byte(const uint8_t *__restrict__ 
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
 }
 
-// Record descriptors from 4 consecutive line-index entries.  One thread per record; the raw bytes
-// are not touched.  Grammar per fastq.cpp: the content of a line ends at the '\r' of a CRLF line
-// end; |seq| must equal |qual| (fastq.cpp:118-122).
-__global__ void __launch_bounds__(256) k_build_records(const uint32_t *__restrict__ nl_pos, uint32_t n_rec, Rec *__restrict__ rec,
+// Record descriptors from 4 consecutive lines of the segmented line index.  One thread per record; the
+// raw bytes are not touched.  Grammar per fastq.cpp: the content of a line ends at the '\r' of a CRLF
+// line end; |seq| must equal |qual| (fastq.cpp:118-122).
+struct LineIndex {
+    const uint32_t *nl_seg;
+    const uint32_t *seg_base;     // [n_seg + 1] global line number of each segment's first line
+    uint32_t seg_cap, n_seg;
+    // entry of global line g; s is a hint that is advanced (lines are looked up in increasing order)
+    __device__ __forceinline__ uint32_t at(uint32_t g, uint32_t &s) const
+    {
+        while (g >= seg_base[s + 1]) ++s;
+        return nl_seg[(size_t)s * seg_cap + (g - seg_base[s])];
+    }
+    __device__ __forceinline__ uint32_t find(uint32_t g) const      // segment holding global line g
+    {
+        uint32_t lo = 0, hi = n_seg;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (seg_base[mid] <= g) lo = mid; else hi = mid;
+        }
+        return lo;
+    }
+};
+
+__global__ void __launch_bounds__(256) k_build_records(const LineIndex li, uint32_t n_rec, Rec *__restrict__ rec,
                                                        uint8_t *__restrict__ canon, BatchInfo *info, int mate)
 {
+    __shared__ uint32_t s_seg;
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) {
+        const uint32_t r0 = blockIdx.x * blockDim.x;
+        s_seg = li.find(r0 ? 4 * r0 - 1 : 0);          // the CTA's 1024 lines sit in this segment or the next few
+    }
+    __syncthreads();
     uint32_t len = 0;
     bool bad = false;
     if (r < n_rec) {
-        const uint4 e = reinterpret_cast<const uint4 *>(nl_pos)[r];
-        const uint32_t p0 = e.x & kNlPosMask, p1 = e.y & kNlPosMask, p2 = e.z & kNlPosMask, p3 = e.w & kNlPosMask;
-        const uint32_t hdr = r ? (nl_pos[4 * r - 1] & kNlPosMask) + 1 : 0;
+        uint32_t s = s_seg;
+        const uint32_t hdr = r ? (li.at(4 * r - 1, s) & kNlPosMask) + 1 : 0;
+        const uint32_t ex = li.at(4 * r, s), ey = li.at(4 * r + 1, s), ez = li.at(4 * r + 2, s), ew = li.at(4 * r + 3, s);
+        const uint32_t p0 = ex & kNlPosMask, p1 = ey & kNlPosMask, p2 = ez & kNlPosMask, p3 = ew & kNlPosMask;
         const uint32_t seq = p0 + 1, plus = p1 + 1, qual = p2 + 1;
         // a '\r' right before the '\n' belongs to the line end only if the line is not empty
-        const uint32_t c0 = (e.x & kNlCr) && p0 > hdr, c1 = (e.y & kNlCr) && p1 > seq;
-        const uint32_t c2 = (e.z & kNlCr) && p2 > plus, c3 = (e.w & kNlCr) && p3 > qual;
+        const uint32_t c0 = (ex & kNlCr) && p0 > hdr, c1 = (ey & kNlCr) && p1 > seq;
+        const uint32_t c2 = (ez & kNlCr) && p2 > plus, c3 = (ew & kNlCr) && p3 > qual;
         len = p1 - seq - c1;
         const uint32_t qlen = p3 - qual - c3;
         bad = (len != qlen);
         rec[r] = Rec{hdr, seq, qual, len};
         // canonical record: LF line ends and a bare "+" line, i.e. the raw bytes ARE what write_read
         // (fastq.cpp:127-138) prints for an untouched read, so emission can be a block copy
-        canon[r] = (uint8_t)(!(c0 | c1 | c2 | c3) && p2 == plus + 1 && (e.z & kNlPlus));
+        canon[r] = (uint8_t)(!(c0 | c1 | c2 | c3) && p2 == plus + 1 && (ez & kNlPlus));
     }
     uint32_t m = len;
 #pragma unroll
