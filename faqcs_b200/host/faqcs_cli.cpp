@@ -1,0 +1,634 @@
+// faqcs_cli.cpp -- command-line driver with the FaQCs v2.10 flag set, output file names and
+// QC.stats.txt layout, running the trim / filter / statistics path on the GPU through the C ABI
+// (include/faqcs_b200.h).  Host side only: option parsing (options.cpp:72-774), gz/plain input
+// (zlib), batching at record boundaries, ordered writers, write_stats (FaQCs.cpp:759-1034) and
+// the --debug data files of plot() (plot.cpp:540-681).  The R/PDF report and k-mer rarefaction
+// are out of scope.
+//
+//   faqcs_b200 -1 r1.fq -2 r2.fq -d outdir [FaQCs flags]        extra: --device N, --batch_mb N
+#include <getopt.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/faqcs_b200.h"
+
+using namespace std;
+
+#define FAQCS_VERSION "2.10"
+static const char *kPhiX = "__PhiX174_NC_001422__";
+static const char *kPhiXComplement = "__PhiX174_NC_001422_complement__";
+static const char *kPhiXSeq =
+#include "phix174.inc"
+    ;
+
+struct Cli {
+    bool print_usage = false, protect_5 = false, replace_N = false, kmer_rarefaction = false, discard_output = false;
+    bool qc_only = false, trim_only = false, filter_adapter = false, filter_phiX = false, debug = false;
+    int mode = FQ_MODE_BWA_PLUS;
+    string prefix = "QC", plots_file, stats_file, input_read1_file, input_read2_file, input_unpaired_file;
+    string trimmed_read1_file, trimmed_read2_file, trimmed_unpaired_file, trimmed_discard_file, output_dir, artifact_file;
+    float average_quality = 0.0f, low_complexity_cutoff_ratio = 0.85f, filterAdapterMismatchRate = 0.2f;
+    char input_quality_offset = SCHAR_MIN, output_quality_offset = 33, quality = 5;
+    unsigned num_thread = 0, min_read_length = 50, max_num_poly_N = 2, kmer = 31, num_subsample = 10, trim_5 = 0, trim_3 = 0;
+    unsigned split_size = 1000000, replace_to_N_q = 0;
+    vector<pair<string, string>> adapter;
+    int device = 0;
+    size_t batch_mb = 256;
+    bool has_paired() const { return !input_read1_file.empty(); }       // has_paired() tests read1 twice, FaQCs.h:135-138
+    bool has_unpaired() const { return !input_unpaired_file.empty(); }
+};
+
+static unsigned strtou(const string &b)      // options.cpp:798-818
+{
+    size_t ret = 0;
+    long long p = 1;
+    for (auto i = b.rbegin(); i != b.rend(); ++i) {
+        if (!isdigit((unsigned char)*i)) throw "options.cpp:strtou: Invalid character";
+        ret += (size_t)(*i - '0') * p;
+        p *= 10;
+    }
+    if (ret > UINT_MAX) throw "options.cpp:strtou: Overflow!";
+    return (unsigned)ret;
+}
+
+static string reverse_complement(string s)   // options.cpp:894-996
+{
+    for (char &c : s) {
+        switch (c) {
+            case 'A': c = 'T'; break; case 'a': c = 't'; break; case 'T': c = 'A'; break; case 't': c = 'a'; break;
+            case 'G': c = 'C'; break; case 'g': c = 'c'; break; case 'C': c = 'G'; break; case 'c': c = 'g'; break;
+            case 'M': c = 'K'; break; case 'm': c = 'k'; break; case 'R': c = 'Y'; break; case 'r': c = 'y'; break;
+            case 'V': c = 'B'; break; case 'v': c = 'b'; break; case 'Y': c = 'R'; break; case 'y': c = 'r'; break;
+            case 'H': c = 'D'; break; case 'h': c = 'd'; break; case 'K': c = 'M'; break; case 'k': c = 'm'; break;
+            case 'D': c = 'H'; break; case 'd': c = 'h'; break; case 'B': c = 'V'; break; case 'b': c = 'v'; break;
+            default: break;      // S, W, N map to themselves
+        }
+    }
+    reverse(s.begin(), s.end());
+    return s;
+}
+
+static void parse_artifact_file(const string &fn, vector<pair<string, string>> &out)   // options.cpp:820-891
+{
+    gzFile fin = gzopen(fn.c_str(), "r");
+    if (!fin) {
+        cerr << "Unable to open " << fn << " for loading artifact sequences" << endl;
+        throw "I/O error";
+    }
+    const int buffer_len = 4096;
+    char buffer[buffer_len];
+    string defline;
+    string data;
+    while (gzgets(fin, buffer, buffer_len)) {
+        char *ptr = strchr(buffer, '>');
+        if (ptr) {
+            if (!data.empty()) out.push_back(make_pair(defline, data));
+            data.clear();
+            ++ptr;
+            for (char *p = ptr; *p; ++p)
+                if (*p == '\n' || *p == '\r') *p = '\0';
+            if (strlen(ptr) == (size_t)(buffer_len - 1)) defline = buffer + string("...");
+            else defline = ptr;
+        } else {
+            for (char *p = buffer; *p; ++p)
+                if (!isspace((unsigned char)*p)) data.push_back(*p);
+        }
+    }
+    if (!data.empty()) out.push_back(make_pair(defline, data));
+    gzclose(fin);
+}
+
+static void usage()
+{
+    cerr << "FaQCs version " << FAQCS_VERSION << " (faqcs_b200: GPU trim/filter/statistics path)" << endl;
+    cerr << "Input File(s):\n\t-u\t\t\t<File> Unpaired reads\n\t-1\t\t\t<File> First paired read file\n\t-2\t\t\t<File> Second paired read file\n";
+    cerr << "Trim:\n\t--mode\t\t\t\"HARD\" or \"BWA\" or \"BWA_plus\" (default BWA_plus)\n\t-q\t\t\t<INT> Targets # as quality level (default 5) for trimming\n";
+    cerr << "\t--5end\t\t\t<INT> Cut # bp from 5 end before quality trimming/filtering\n\t--3end\t\t\t<INT> Cut # bp from 3 end before quality trimming/filtering\n";
+    cerr << "\t--adapter\t\t<bool> Trim reads with illumina adapter/primers (default: no)\n\t--rate\t\t\t<FLOAT> Mismatch ratio of adapters' length (default: 0.2, allow 20% mismatches)\n";
+    cerr << "\t--polyA\t\t\t<bool>  Trim poly A ( > 15 )\n\t--artifactFile\t\t<File> additional artifact (adapters/primers/contaminations) reference file in fasta format\n";
+    cerr << "Filters:\n\t--min_L\t\t\t<INT> Trimmed read should have to be at least this minimum length (default:50)\n\t--avg_q\t\t\t<NUM> Average quality cutoff (default:0, no filtering)\n";
+    cerr << "\t-n\t\t\t<INT> Trimmed read has greater than or equal to this number of continuous base \"N\" will be discarded.\n\t--lc\t\t\t<FLOAT> Low complexity filter ratio (default: 0.85)\n\t--phiX\t\t\t<bool> Filter phiX reads (slow)\n";
+    cerr << "Q_Format:\n\t--ascii\t\t\tEncoding type: 33 or 64 or autoCheck (default)\n\t--out_ascii\t\tOutput encoding. (default: 33)\n";
+    cerr << "Output:\n\t--prefix\t\t<TEXT> Output file prefix. (default: QC)\n\t--stats\t\t\t<File> Statistical numbers output file (default: prefix.stats.txt)\n\t-d\t\t\t<PATH> Output directory.\n";
+    cerr << "Options:\n\t-t\t\t\t<INT > # of CPUs the reference would run with (only reproduces its -t dependent adapter threshold)\n";
+    cerr << "\t--split_size\t\t<INT> (kept for compatibility)\n\t--qc_only\t\t<bool> no Filters, no Trimming, report numbers.\n\t--discard\t\t<bool> Output discarded reads\n";
+    cerr << "\t--substitute\t\t<bool> (not implemented, as in FaQCs)\n\t--trim_only\t\t<bool> No quality report. Output trimmed reads only.\n\t--replace_to_N_q\t<INT> Replace base G to N when below this quality score (default:0, off)\n";
+    cerr << "\t--5trim_off\t\t<bool> Turn off trimming from 5'end.\n\t--debug\t\t\t<bool> Keep intermediate files\n\t--version\t\t<bool> Print the version and exit\n";
+    cerr << "GPU:\n\t--device\t\t<INT> CUDA device (default 0)\n\t--batch_mb\t\t<INT> MiB of FASTQ per mate per batch (default 256)\n";
+}
+
+static void parse_options(int argc, char *argv[], Cli &o)
+{
+    for (int i = 1; i < argc; ++i) {                      // deprecated -p f1 f2 (options.cpp:78-96)
+        if (strncmp(argv[i], "-p", 2) == 0 && strncmp(argv[i], "-prefix", 7) != 0 && strcmp(argv[i], "-phiX") != 0 && strcmp(argv[i], "-polyA") != 0) {
+            if (i + 2 >= argc) throw "options.cpp:Options: Unable to extract file names after depricated '-p' flag";
+            o.input_read1_file = argv[i + 1];
+            o.input_read2_file = argv[i + 2];
+            cerr << "The paired read flag (-p) has been deprecated. Please specify paired read files with -1 <file> and -2 <file>" << endl;
+        }
+    }
+    o.print_usage = (argc == 1);
+    bool trim_polyA = false, version = false;
+    int config_opt = 0, long_index = 0;
+    const char *options = "d:t:n:1:2:p:q:u:?h";
+    struct option long_opts[] = {
+        {"mode", true, &config_opt, 1}, {"5end", true, &config_opt, 2}, {"3end", true, &config_opt, 3}, {"adapter", false, &config_opt, 4},
+        {"rate", true, &config_opt, 5}, {"polyA", false, &config_opt, 6}, {"artifactFile", true, &config_opt, 7}, {"min_L", true, &config_opt, 8},
+        {"avg_q", true, &config_opt, 9}, {"lc", true, &config_opt, 10}, {"phiX", false, &config_opt, 11}, {"ascii", true, &config_opt, 12},
+        {"out_ascii", true, &config_opt, 13}, {"prefix", true, &config_opt, 14}, {"stats", true, &config_opt, 15}, {"split_size", true, &config_opt, 16},
+        {"qc_only", false, &config_opt, 17}, {"kmer_rarefaction", false, &config_opt, 18}, {"subset", true, &config_opt, 19},
+        {"discard", false, &config_opt, 20}, {"substitute", false, &config_opt, 21}, {"trim_only", false, &config_opt, 22},
+        {"5trim_off", false, &config_opt, 23}, {"debug", false, &config_opt, 24}, {"version", false, &config_opt, 25}, {"R1", true, &config_opt, 26},
+        {"R2", true, &config_opt, 27}, {"replace_to_N_q", true, &config_opt, 31}, {"device", true, &config_opt, 40}, {"batch_mb", true, &config_opt, 41},
+        {0, 0, 0, 0}};
+    int opt_code;
+    opterr = 0;
+    while ((opt_code = getopt_long_only(argc, argv, options, long_opts, &long_index)) != EOF) {
+        switch (opt_code) {
+            case 0:
+                switch (config_opt) {
+                    case 1: {
+                        string m = optarg;
+                        for (char &c : m) c = (char)tolower(c);
+                        o.mode = m == "hard" ? FQ_MODE_HARD : m == "bwa" ? FQ_MODE_BWA : m == "bwa_plus" ? FQ_MODE_BWA_PLUS : -1;
+                        break;
+                    }
+                    case 2: o.trim_5 = strtou(optarg); break;
+                    case 3: o.trim_3 = strtou(optarg); break;
+                    case 4: o.filter_adapter = true; break;
+                    case 5: o.filterAdapterMismatchRate = (float)atof(optarg); break;
+                    case 6: trim_polyA = true; break;
+                    case 7: o.artifact_file = optarg; o.filter_adapter = true; break;
+                    case 8: o.min_read_length = strtou(optarg); break;
+                    case 9: o.average_quality = (float)atof(optarg); break;
+                    case 10: o.low_complexity_cutoff_ratio = (float)atof(optarg); break;
+                    case 11: o.filter_phiX = true; break;
+                    case 12: {
+                        const int v = atoi(optarg);
+                        if (v <= SCHAR_MIN || v > SCHAR_MAX) throw "options.cpp:Options::Options: ascii out of bounds!";
+                        o.input_quality_offset = (char)v;
+                        break;
+                    }
+                    case 13: {
+                        const int v = atoi(optarg);
+                        if (v <= SCHAR_MIN || v > SCHAR_MAX) throw "options.cpp:Options::Options: out_ascii out of bounds!";
+                        o.output_quality_offset = (char)v;
+                        break;
+                    }
+                    case 14: o.prefix = optarg; break;
+                    case 15: o.stats_file = optarg; break;
+                    case 16: o.split_size = strtou(optarg); break;
+                    case 17: o.qc_only = true; break;
+                    case 18: o.kmer_rarefaction = true; break;
+                    case 19: o.num_subsample = strtou(optarg); break;
+                    case 20: o.discard_output = true; break;
+                    case 21: o.replace_N = true; break;
+                    case 22: o.trim_only = true; break;
+                    case 23: o.protect_5 = true; break;
+                    case 24: o.debug = true; break;
+                    case 25: version = true; break;
+                    case 26: o.input_read1_file = optarg; break;
+                    case 27: o.input_read2_file = optarg; break;
+                    case 31: o.replace_to_N_q = strtou(optarg); break;
+                    case 40: o.device = atoi(optarg); break;
+                    case 41: o.batch_mb = (size_t)max(1, atoi(optarg)); break;
+                    default: cerr << "Unknown flag!" << endl; break;
+                }
+                break;
+            case '1': o.input_read1_file = optarg; break;
+            case '2': o.input_read2_file = optarg; break;
+            case 'u': o.input_unpaired_file = optarg; break;
+            case 'd': o.output_dir = optarg; break;
+            case 'n': o.max_num_poly_N = strtou(optarg); break;
+            case 'q': {
+                const int v = atoi(optarg);
+                if (v <= SCHAR_MIN || v > SCHAR_MAX) throw "options.cpp:Options::Options: q out of bounds!";
+                o.quality = (char)v;
+                break;
+            }
+            case 't': o.num_thread = strtou(optarg); break;
+            case 'h': case '?': o.print_usage = true; break;
+            case 'p': break;
+            default: cerr << '"' << (char)opt_code << "\" is not a valid option!" << endl; break;
+        }
+    }
+    if (o.print_usage) { usage(); return; }
+    if (version) { cerr << "Version: " << FAQCS_VERSION << endl; o.print_usage = true; return; }
+    if (o.input_read1_file.empty() != o.input_read2_file.empty()) {
+        if (o.input_read1_file.empty()) cerr << "Please specify a read one file (-1 <file>)" << endl;
+        if (o.input_read2_file.empty()) cerr << "Please specify a read one file (-2 <file>)" << endl;
+        o.print_usage = true;
+        return;
+    }
+    if (o.input_unpaired_file.empty() && o.input_read1_file.empty() && o.input_read2_file.empty()) {
+        cerr << "Please specify either a pair of fastq files (-1 <file> -2 <file>)  or a single fastq file of unpaired reads (-u <file>)" << endl;
+        o.print_usage = true;
+        return;
+    }
+    if (o.low_complexity_cutoff_ratio > 1.0 || o.low_complexity_cutoff_ratio < 0.0) {
+        cerr << "Please specify a low complexity cutoff ration (-lc) in the range 0 <= ratio <= 1.0" << endl;
+        o.print_usage = true;
+        return;
+    }
+    if (o.filterAdapterMismatchRate > 1.0 || o.filterAdapterMismatchRate < 0.0) {
+        cerr << "Please specify an adapter mismatch rate (-adapter) in the range 0 <= rate <= 1.0" << endl;
+        o.print_usage = true;
+        return;
+    }
+    if (o.kmer_rarefaction) cerr << "**Warning** --kmer_rarefaction is outside the scope of faqcs_b200 and is ignored" << endl;
+    if (o.replace_N) cerr << "**Warning** \"-substitue\" is not currently implemented" << endl;
+    if (o.filter_adapter) {                               // built-in adapters, options.cpp:576-618 (sequence data)
+        static const char *builtin[][2] = {
+            {"cre-loxp-forward", "TCGTATAACTTCGTATAATGTATGCTATACGAAGTTATTACG"},
+            {"cre-loxp-reverse", "AGCATATTGAAGCATATTACATACGATATGCTTCAATAATGC"},
+            {"TruSeq-adapter-1", "GGGGTAGTGTGGATCCTCCTCTAGGCAGTTGGGTTATTCTAGAAGCAGATGTGTTGGCTGTTTCTGAAACTCTGGAAAA"},
+            {"TruSeq-adapter-3", "CAACAGCCGGTCAAAACATCTGGAGGGTAAGCCATAAACACCTCAACAGAAAA"},
+            {"PCR-primer-1", "CGATAACTTCGTATAATGTATGCTATACGAAGTTATTACG"},
+            {"PCR-primer-2", "GCATAACTTCGTATAGCATACATTATACGAAGTTATACGA"},
+            {"Nextera-primer-adapter-1", "GATCGGAAGAGCACACGTCTGAACTCCAGTCAC"},
+            {"Nextera-primer-adapter-2", "GATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"},
+            {"Nextera-junction-adapter-1", "CTGTCTCTTATACACATCTAGATGTGTATAAGAGACAG"}};
+        for (auto &b : builtin) o.adapter.push_back(make_pair(string(b[0]), string(b[1])));
+    }
+    if (trim_polyA) o.adapter.push_back(make_pair(string("polyA"), string(20, 'A')));
+    if (o.filter_phiX) {
+        o.adapter.push_back(make_pair(string(kPhiX), string(kPhiXSeq)));
+        o.adapter.push_back(make_pair(string(kPhiXComplement), reverse_complement(kPhiXSeq)));
+    }
+    if (!o.artifact_file.empty()) parse_artifact_file(o.artifact_file, o.adapter);
+    const string base = o.output_dir + "/" + o.prefix;    // options.cpp:696-741
+    if (!o.input_read1_file.empty() && !o.input_read2_file.empty()) {
+        o.trimmed_read1_file = base + ".1.trimmed.fastq";
+        o.trimmed_read2_file = base + ".2.trimmed.fastq";
+    }
+    o.trimmed_unpaired_file = base + ".unpaired.trimmed.fastq";
+    o.trimmed_discard_file = o.discard_output ? base + ".discard.trimmed.fastq" : "";
+    if (o.plots_file.empty()) o.plots_file = base + "_qc_report.pdf";
+    if (o.stats_file.empty()) o.stats_file = base + ".stats.txt";
+    if (o.mode < 0) {
+        o.mode = FQ_MODE_BWA_PLUS;
+        if (!o.qc_only) cerr << "Not recognized mode. Bwa extension trimming algorithm is used." << endl;
+    } else if (!o.qc_only) {
+        cerr << (o.mode == FQ_MODE_HARD ? "Hard trimming is used." : o.mode == FQ_MODE_BWA ? "Bwa trimming is used." : "Bwa extension trimming is used.") << endl;
+    }
+}
+
+// ---- input: gz or plain, whole records per batch -------------------------------------------------
+struct Source {
+    gzFile f = nullptr;
+    bool eof = false;
+    vector<uint8_t> carry;       // bytes read but not yet submitted (tail of the previous fill)
+    bool open(const string &fn) { f = gzopen(fn.c_str(), "r"); if (f) gzbuffer(f, 1 << 20); return f != nullptr; }
+    void close() { if (f) gzclose(f); f = nullptr; }
+    // fill buf[0..cap) starting with the carry; returns bytes available
+    size_t fill(uint8_t *buf, size_t cap)
+    {
+        size_t n = carry.size();
+        if (n) memcpy(buf, carry.data(), n);
+        carry.clear();
+        while (!eof && n < cap) {
+            const int got = gzread(f, buf + n, (unsigned)min<size_t>(cap - n, 1u << 30));
+            if (got < 0) throw "fastq.cpp:next_read: Unable to read header";
+            if (got == 0) { eof = true; break; }
+            n += (size_t)got;
+        }
+        return n;
+    }
+};
+
+// offset just past the k-th complete record (4 lines) in buf[0..n); also counts the complete records
+static size_t count_records(const uint8_t *buf, size_t n, vector<size_t> *ends_every, size_t every)
+{
+    size_t lines = 0, recs = 0;
+    const uint8_t *p = buf, *end = buf + n;
+    while (p < end) {
+        const uint8_t *nl = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
+        if (!nl) break;
+        p = nl + 1;
+        if ((++lines & 3) == 0) {
+            ++recs;
+            if (ends_every && recs % every == 0) ends_every->push_back((size_t)(p - buf));
+        }
+    }
+    return recs;
+}
+static size_t offset_of_record(const uint8_t *buf, size_t n, size_t k)
+{
+    size_t lines = 0;
+    const uint8_t *p = buf, *end = buf + n;
+    if (k == 0) return 0;
+    while (p < end) {
+        const uint8_t *nl = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
+        if (!nl) break;
+        p = nl + 1;
+        if (++lines == 4 * k) return (size_t)(p - buf);
+    }
+    return n;
+}
+
+struct Run {
+    Cli &o;
+    fq_ctx *ctx = nullptr;
+    uint64_t records_done = 0;
+    bool first_batch = true;
+    explicit Run(Cli &opt) : o(opt) {}
+    void check(fq_status st) { if (st != FQ_OK) throw string(fq_last_error(ctx)); }
+};
+
+static FILE *open_out(const string &fn, const char *what)
+{
+    FILE *f = fopen(fn.c_str(), "wb");
+    if (!f) { cerr << "Unable to open " << fn << " for writing " << what << endl; throw "I/O error"; }
+    setvbuf(f, nullptr, _IOFBF, 8 << 20);
+    return f;
+}
+
+// process_paired (FaQCs.cpp:153-538) / process_unpaired (:540-757): read -> GPU -> four ordered writers.
+static void process(Run &R, bool paired)
+{
+    Cli &o = R.o;
+    Source s1, s2;
+    if (paired) {
+        if (!s1.open(o.input_read1_file)) { cerr << "Unable to open " << o.input_read1_file << " for loading read one sequences" << endl; throw "I/O error"; }
+        if (!s2.open(o.input_read2_file)) { cerr << "Unable to open " << o.input_read2_file << " for loading read two sequences" << endl; throw "I/O error"; }
+    } else if (!s1.open(o.input_unpaired_file)) {
+        cerr << "Unable to open " << o.input_unpaired_file << " for loading unpaired read sequences" << endl;
+        throw "I/O error";
+    }
+    FILE *fout[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (!o.qc_only) {
+        if (paired) {
+            fout[0] = open_out(o.trimmed_read1_file, "read one sequences");
+            fout[1] = open_out(o.trimmed_read2_file, "read two sequences");
+        }
+        fout[2] = open_out(o.trimmed_unpaired_file, "unpaired sequences");      // re-opened (truncated) by the -u pass: Q11
+        if (!o.trimmed_discard_file.empty()) fout[3] = open_out(o.trimmed_discard_file, "discarded sequences");
+    }
+    const size_t cap = o.batch_mb << 20;
+    uint8_t *buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [slot][mate], pinned
+    for (int k = 0; k < 2; ++k)
+        for (int m = 0; m < (paired ? 2 : 1); ++m)
+            if (!(buf[k][m] = (uint8_t *)fq_host_alloc(cap))) throw "unable to allocate pinned host memory";
+    const bool emulate = o.filter_adapter || o.filter_phiX;             // Q3: keep batches on 32768-record boundaries
+    uint64_t first_index = 0, pending_ticket = 0;
+    bool have_pending = false;
+    auto drain = [&](uint64_t ticket) {
+        fq_batch_out out;
+        R.check(fq_wait(R.ctx, ticket, &out));
+        for (int s = 0; s < 4; ++s)
+            if (fout[s] && out.bytes[s]) fwrite(out.data[s], 1, out.bytes[s], fout[s]);
+    };
+    for (int slot = 0;; slot ^= 1) {
+        size_t n1 = s1.fill(buf[slot][0], cap), n2 = paired ? s2.fill(buf[slot][1], cap) : 0;
+        const bool at_eof = s1.eof && (!paired || s2.eof);
+        size_t use1 = n1, use2 = n2;
+        if (!at_eof) {
+            size_t r1 = count_records(buf[slot][0], n1, nullptr, 1), r2 = paired ? count_records(buf[slot][1], n2, nullptr, 1) : r1;
+            size_t nrec = min(r1, r2);
+            if (emulate && nrec >= FQ_REF_BATCH) nrec -= nrec % FQ_REF_BATCH;
+            if (nrec == 0) throw "record larger than the batch buffer: raise --batch_mb";
+            use1 = offset_of_record(buf[slot][0], n1, nrec);
+            if (paired) use2 = offset_of_record(buf[slot][1], n2, nrec);
+            s1.carry.assign(buf[slot][0] + use1, buf[slot][0] + n1);
+            if (paired) s2.carry.assign(buf[slot][1] + use2, buf[slot][1] + n2);
+        }
+        if (R.first_batch) {
+            // A1 on the first 32768 records (FaQCs.cpp:261-277, 393-414, 609-619, 669-683); an empty input throws
+            const size_t a1 = offset_of_record(buf[slot][0], use1, FQ_REF_BATCH), a2 = paired ? offset_of_record(buf[slot][1], use2, FQ_REF_BATCH) : 0;
+            int32_t off = 0, q = 0;
+            const int q_before = o.quality;
+            R.check(fq_autodetect(R.ctx, buf[slot][0], a1, paired ? buf[slot][1] : nullptr, a2, &off, &q));
+            o.input_quality_offset = (char)off;
+            o.quality = (char)q;
+            if (q != q_before) cerr << "The input looks like NextSeq data and the quality level (-q) is adjusted to 20 for trimming." << endl;
+            R.first_batch = false;
+        }
+        uint64_t ticket = 0;
+        if (use1 || use2 || at_eof) {
+            R.check(fq_submit_host(R.ctx, buf[slot][0], use1, paired ? buf[slot][1] : nullptr, use2, first_index, at_eof ? 1 : 0, &ticket));
+            R.check(fq_run(R.ctx, ticket));
+            if (have_pending) drain(pending_ticket);
+            pending_ticket = ticket;
+            have_pending = true;
+            // records of this batch (for first_record_index): count on the host side
+            first_index += count_records(buf[slot][0], use1, nullptr, 1);
+        }
+        if (at_eof) break;
+    }
+    if (have_pending) drain(pending_ticket);
+    for (int k = 0; k < 2; ++k)
+        for (int m = 0; m < 2; ++m) fq_host_free(buf[k][m]);
+    for (FILE *f : fout) if (f) fclose(f);
+    s1.close();
+    s2.close();
+}
+
+// write_stats (FaQCs.cpp:759-1034): same expressions, same stream state.
+static void write_stats(const fq_stats_view &v, const Cli &o)
+{
+    ofstream fout(o.stats_file.c_str());
+    if (!fout) { cerr << "Unable to open " << o.stats_file << " for writing filtering statistics" << endl; return; }
+    const uint64_t *S = v.filter_stats;
+    auto pct = [](uint64_t a, uint64_t b) { return (100.0 * a) / b; };
+    // adapter stats are keyed by name (duplicates merge); phiX pseudo-adapters are not listed (FaQCs.cpp:92-116)
+    map<string, pair<size_t, size_t>> adapters;
+    for (uint32_t j = 0; j < v.n_adapters; ++j) {
+        const string &name = o.adapter[j].first;
+        if (name == kPhiX || name == kPhiXComplement) continue;
+        if (v.adapter_reads[j] == 0 && adapters.find(name) == adapters.end()) continue;
+        adapters[name].first += v.adapter_reads[j];
+        adapters[name].second += v.adapter_bases[j];
+    }
+    auto adapter_lines = [&]() {
+        deque<pair<size_t, string>> order;
+        for (auto &a : adapters) order.push_back(make_pair(a.second.first, a.first));
+        sort(order.begin(), order.end());
+        for (auto i = order.rbegin(); i != order.rend(); ++i) {
+            const auto &st = adapters[i->second];
+            fout << "    " << i->second << " " << st.first << " reads (" << pct(st.first, S[FQ_TOTAL_NUMBER]) << " %) " << st.second << " bases ("
+                 << pct(st.second, S[FQ_TOTAL_LENGTH]) << " %)\n";
+        }
+    };
+    fout << fixed << setprecision(2);
+    if (o.qc_only) {
+        fout << "\n";
+        fout << "Reads #: " << S[FQ_TOTAL_COUNT] << "\n";
+        fout << "Total bases: " << S[FQ_TOTAL_LENGTH] << "\n";
+        fout << "Reads Length: " << float(S[FQ_TOTAL_LENGTH]) / S[FQ_TOTAL_COUNT] << "\n";
+        fout << "Processed " << S[FQ_TOTAL_NUMBER] << " reads for quality check only\n";
+        fout << "  Reads length < " << o.min_read_length << " bp: " << S[FQ_READ_LENGTH] << " (" << pct(S[FQ_READ_LENGTH], S[FQ_TOTAL_NUMBER]) << " %)\n";
+        fout << "  Reads have " << o.max_num_poly_N << " continuous base \"N\": " << S[FQ_READ_NN] << " (" << pct(S[FQ_READ_NN], S[FQ_TOTAL_NUMBER]) << " %)\n";
+        fout << "  Low complexity Reads  (>" << o.low_complexity_cutoff_ratio * 100.0 << "% mono/di-nucleotides): " << S[FQ_READ_LOW_COMPLEXITY] << " ("
+             << pct(S[FQ_READ_LOW_COMPLEXITY], S[FQ_TOTAL_NUMBER]) << " %)\n";
+        fout << "  Reads < average quality " << o.average_quality << ": " << S[FQ_READ_AVG_Q] << " (" << pct(S[FQ_READ_AVG_Q], S[FQ_TOTAL_NUMBER]) << " %)\n";
+        if (o.filter_phiX) fout << "  Reads hits to phiX sequence: " << S[FQ_READ_PHIX] << " (" << pct(S[FQ_READ_PHIX], S[FQ_TOTAL_NUMBER]) << " %)\n";
+        if (o.filter_adapter) {
+            fout << "  Reads with Adapters/Primers: " << S[FQ_READ_ADAPTER] << " (" << pct(S[FQ_READ_ADAPTER], S[FQ_TOTAL_NUMBER]) << " %)\n";
+            adapter_lines();
+        }
+        return;
+    }
+    fout << "Before Trimming\n";
+    fout << "Reads #: " << S[FQ_TOTAL_NUMBER] << "\n";
+    fout << "Total bases: " << S[FQ_TOTAL_LENGTH] << "\n";
+    fout << "Reads Length: " << float(S[FQ_TOTAL_LENGTH]) / S[FQ_TOTAL_NUMBER] << "\n";
+    fout << "\nAfter Trimming\n";
+    fout << "Reads #: " << S[FQ_TOTAL_TRIMMED_NUMBER] << " (" << pct(S[FQ_TOTAL_TRIMMED_NUMBER], S[FQ_TOTAL_NUMBER]) << " %)\n";
+    fout << "Total bases: " << S[FQ_TOTAL_TRIMMED_LENGTH] << " (" << pct(S[FQ_TOTAL_TRIMMED_LENGTH], S[FQ_TOTAL_LENGTH]) << " %)\n";
+    if (S[FQ_TOTAL_TRIMMED_NUMBER] > 0) fout << "Mean Reads Length: " << float(S[FQ_TOTAL_TRIMMED_LENGTH]) / S[FQ_TOTAL_TRIMMED_NUMBER] << "\n";
+    else fout << "Mean Reads Length: 0\n";
+    if (o.has_paired()) {
+        fout << "  Paired Reads #: " << S[FQ_PAIRED_READ_NUMBER] << " (" << pct(S[FQ_PAIRED_READ_NUMBER], S[FQ_TOTAL_TRIMMED_NUMBER]) << " %)\n";
+        fout << "  Paired total bases: " << S[FQ_PAIRED_BASE_LENGTH] << " (" << pct(S[FQ_PAIRED_BASE_LENGTH], S[FQ_TOTAL_TRIMMED_LENGTH]) << " %)\n";
+        fout << "  Unpaired Reads #: " << S[FQ_TOTAL_TRIMMED_NUMBER] - S[FQ_PAIRED_READ_NUMBER] << " ("
+             << pct(S[FQ_TOTAL_TRIMMED_NUMBER] - S[FQ_PAIRED_READ_NUMBER], S[FQ_TOTAL_TRIMMED_NUMBER]) << " %)\n";
+        fout << "  Unpaired total bases: " << S[FQ_TOTAL_TRIMMED_LENGTH] - S[FQ_PAIRED_BASE_LENGTH] << " ("
+             << pct(S[FQ_TOTAL_TRIMMED_LENGTH] - S[FQ_PAIRED_BASE_LENGTH], S[FQ_TOTAL_TRIMMED_LENGTH]) << " %)\n";
+    }
+    fout << "\nDiscarded reads #: " << S[FQ_TOTAL_NUMBER] - S[FQ_TOTAL_TRIMMED_NUMBER] << " (" << pct(S[FQ_TOTAL_NUMBER] - S[FQ_TOTAL_TRIMMED_NUMBER], S[FQ_TOTAL_NUMBER]) << " %)\n";
+    fout << "Trimmed bases: " << S[FQ_TOTAL_LENGTH] - S[FQ_TOTAL_TRIMMED_LENGTH] << " (" << pct(S[FQ_TOTAL_LENGTH] - S[FQ_TOTAL_TRIMMED_LENGTH], S[FQ_TOTAL_LENGTH]) << " %)\n";
+    fout << "  Reads Filtered by length cutoff (" << o.min_read_length << " bp): " << S[FQ_READ_LENGTH] << " (" << pct(S[FQ_READ_LENGTH], S[FQ_TOTAL_NUMBER]) << " %)\n";
+    fout << "  Bases Filtered by length cutoff: " << S[FQ_BASE_LENGTH] << " (" << pct(S[FQ_BASE_LENGTH], S[FQ_TOTAL_LENGTH]) << " %)\n";
+    fout << "  Reads Filtered by continuous base \"N\" (" << o.max_num_poly_N << "): " << S[FQ_READ_NN] << " (" << pct(S[FQ_READ_NN], S[FQ_TOTAL_NUMBER]) << " %)\n";
+    fout << "  Bases Filtered by continuous base \"N\": " << S[FQ_BASE_NN] << " (" << pct(S[FQ_BASE_NN], S[FQ_TOTAL_LENGTH]) << " %)\n";
+    fout << "  Reads Filtered by low complexity ratio (" << setprecision(1) << o.low_complexity_cutoff_ratio << setprecision(2) << "): " << S[FQ_READ_LOW_COMPLEXITY]
+         << " (" << pct(S[FQ_READ_LOW_COMPLEXITY], S[FQ_TOTAL_NUMBER]) << " %)\n";
+    fout << "  Bases Filtered by low complexity ratio: " << S[FQ_BASE_LOW_COMPLEXITY] << " (" << pct(S[FQ_BASE_LOW_COMPLEXITY], S[FQ_TOTAL_LENGTH]) << " %)\n";
+    if (o.average_quality > 0.0) {
+        fout << "  Reads Filtered by avg quality (" << o.average_quality << "): " << S[FQ_READ_AVG_Q] << " (" << pct(S[FQ_READ_AVG_Q], S[FQ_TOTAL_NUMBER]) << " %)\n";
+        fout << "  Bases Filtered by avg quality: " << S[FQ_BASE_AVG_Q] << " (" << pct(S[FQ_BASE_AVG_Q], S[FQ_TOTAL_LENGTH]) << " %)\n";
+    }
+    if (o.filter_phiX) {
+        fout << "  Reads Filtered by phiX sequence: " << S[FQ_READ_PHIX] << " (" << pct(S[FQ_READ_PHIX], S[FQ_TOTAL_NUMBER]) << " %)\n";
+        fout << "  Bases Filtered by phiX sequence: " << S[FQ_BASE_PHIX] << " (" << pct(S[FQ_BASE_PHIX], S[FQ_TOTAL_LENGTH]) << " %)\n";
+    }
+    fout << "  Reads Trimmed by quality (" << setprecision(1) << float(o.quality) << setprecision(2) << "): " << S[FQ_READ_QUAL_TRIM] << " ("
+         << pct(S[FQ_READ_QUAL_TRIM], S[FQ_TOTAL_NUMBER]) << " %)\n";
+    fout << "  Bases Trimmed by quality: " << S[FQ_BASE_QUAL_TRIM] << " (" << pct(S[FQ_BASE_QUAL_TRIM], S[FQ_TOTAL_LENGTH]) << " %)\n";
+    if (o.trim_5 > 0) fout << "  Reads Trimmed with " << o.trim_5 << " bp from 5' end\n";
+    if (o.trim_3 > 0) fout << "  Reads Trimmed with " << o.trim_3 << " bp from 3' end\n";
+    if (o.filter_adapter) {
+        fout << "  Reads Trimmed with Adapters/Primers: " << S[FQ_READ_ADAPTER] << " (" << pct(S[FQ_READ_ADAPTER], S[FQ_TOTAL_NUMBER]) << " %)\n";
+        fout << "  Bases Trimmed with Adapters/Primers: " << S[FQ_BASE_ADAPTER] << " (" << pct(S[FQ_BASE_ADAPTER], S[FQ_TOTAL_LENGTH]) << " %)\n";
+        adapter_lines();
+    }
+    if (o.replace_N) fout << "\nN base random substitution: A " << S[FQ_N_TO_A] << ", T " << S[FQ_N_TO_T] << ", C " << S[FQ_N_TO_C] << ", G " << S[FQ_N_TO_G] << "\n";
+}
+
+// The ten --debug data files of plot() (plot.cpp:31-78, writers :540-681).
+static void write_debug_files(const fq_stats_view &v, const Cli &o)
+{
+    const string dir = o.output_dir + "/";
+    auto write_matrix = [&](const string &fn, const uint64_t *m, uint32_t rows, uint32_t cols) {
+        if (rows == 0) return;
+        ofstream f(fn.c_str());
+        for (uint32_t i = 0; i < rows; ++i) {
+            f << m[(size_t)i * cols];
+            for (uint32_t j = 1; j < cols; ++j) f << '\t' << m[(size_t)i * cols + j];
+            f << endl;
+        }
+    };
+    auto write_qhist = [&](const string &fn, const uint64_t *r, const uint64_t *b) {
+        ofstream f(fn.c_str());
+        f << "Score\treadsNum\treadsBases" << endl;
+        for (int i = FQ_MAX_QUALITY_SCORE; i >= 0; --i) f << i << '\t' << r[i] << '\t' << b[i] << endl;
+    };
+    auto write_content = [&](const string &fn, const uint64_t *c) {
+        ofstream f(fn.c_str());
+        f << setprecision(2) << fixed;
+        static const char *label[6] = {"A", "T", "C", "G", "N", "GC"};
+        for (int h = 0; h < 6; ++h)
+            for (unsigned i = 0; i < FQ_NUM_COMPOSITION_BIN; ++i) {
+                const uint64_t num = c[(size_t)h * FQ_NUM_COMPOSITION_BIN + i];
+                if (num) f << label[h] << "\t" << i * 0.01 << '\t' << num << endl;
+            }
+    };
+    auto write_len = [&](const string &fn, const uint64_t *h, uint32_t n) {
+        ofstream f(fn.c_str());
+        for (uint32_t i = 1; i < n; ++i) f << i << '\t' << h[i] << endl;
+    };
+    write_matrix(dir + "qa." + o.prefix + ".quality.matrix", v.pre_quality_matrix, v.pre_rows, FQ_NUM_QUAL);
+    write_matrix(dir + o.prefix + ".quality.matrix", v.post_quality_matrix, v.post_rows, FQ_NUM_QUAL);
+    write_matrix(dir + "qa." + o.prefix + ".base.matrix", v.pre_base_matrix, v.pre_rows, FQ_NUM_BASE);
+    write_matrix(dir + o.prefix + ".base.matrix", v.post_base_matrix, v.post_rows, FQ_NUM_BASE);
+    write_qhist(dir + "qa." + o.prefix + ".for_qual_histogram.txt", v.pre_read_quality_hist, v.pre_base_quality_hist);
+    write_qhist(dir + o.prefix + ".for_qual_histogram.txt", v.post_read_quality_hist, v.post_base_quality_hist);
+    write_content(dir + "qa." + o.prefix + ".base_content.txt", v.pre_composition);
+    write_content(dir + o.prefix + ".base_content.txt", v.post_composition);
+    write_len(dir + "qa." + o.prefix + ".length_count.txt", v.pre_length_hist, v.pre_len_size);
+    write_len(dir + o.prefix + ".length_count.txt", v.post_length_hist, v.post_len_size);
+}
+
+static void remove_file(const string &fn)      // FaQCs.cpp:1046-1053
+{
+    struct stat st;
+    if (!fn.empty() && stat(fn.c_str(), &st) == 0) {
+        cerr << "The output " << fn << " file exists and will be overwritten." << endl;
+        unlink(fn.c_str());
+    }
+}
+
+int main(int argc, char *argv[])
+{
+    Cli o;
+    fq_ctx *ctx = nullptr;
+    try {
+        parse_options(argc, argv, o);
+        if (o.print_usage) return EXIT_FAILURE;
+        struct stat st;
+        if (!(stat(o.output_dir.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) && mkdir(o.output_dir.c_str(), 0700) != 0) {
+            cerr << "Unable to create requested output directory: \"" << o.output_dir << '"' << endl;
+            return EXIT_FAILURE;
+        }
+        for (const string *f : {&o.plots_file, &o.stats_file, &o.trimmed_read1_file, &o.trimmed_read2_file, &o.trimmed_unpaired_file, &o.trimmed_discard_file}) remove_file(*f);
+
+        vector<fq_adapter> adapters;
+        for (auto &a : o.adapter) adapters.push_back(fq_adapter{a.first.c_str(), a.second.c_str()});
+        fq_options f{};
+        f.mode = o.mode; f.quality = o.quality; f.trim_5 = o.trim_5; f.trim_3 = o.trim_3; f.min_read_length = o.min_read_length;
+        f.max_num_poly_N = o.max_num_poly_N; f.average_quality = o.average_quality; f.low_complexity_cutoff_ratio = o.low_complexity_cutoff_ratio;
+        f.adapter_mismatch_rate = o.filterAdapterMismatchRate;
+        f.input_quality_offset = o.input_quality_offset == SCHAR_MIN ? FQ_OFFSET_AUTO : (int)o.input_quality_offset;
+        f.output_quality_offset = o.output_quality_offset; f.replace_to_N_q = o.replace_to_N_q; f.qc_only = o.qc_only; f.protect_5 = o.protect_5;
+        f.filter_adapter = o.filter_adapter || o.filter_phiX; f.discard_output = o.discard_output;
+        f.num_thread = o.num_thread ? o.num_thread : max(1u, thread::hardware_concurrency());     // -t 0 = all cores (options.cpp:124)
+        f.n_adapters = (uint32_t)adapters.size(); f.adapters = adapters.data();
+        if (fq_create(&f, o.device, &ctx) != FQ_OK) throw string(fq_last_error(nullptr));
+        Run R(o);
+        R.ctx = ctx;
+        if (o.has_paired()) process(R, true);
+        if (o.has_unpaired()) {
+            R.first_batch = true;      // offset detection only if still unknown; the NextSeq check runs per input (FaQCs.cpp:586,673-683)
+            process(R, false);
+        }
+        fq_stats_view v;
+        if (fq_stats(ctx, &v) != FQ_OK) throw string(fq_last_error(ctx));
+        write_stats(v, o);
+        if (!o.trim_only && o.debug) write_debug_files(v, o);    // the reference deletes these unless --debug (plot.cpp:517-537)
+        fq_destroy(ctx);
+    } catch (const char *error) {
+        cerr << "Caught the error " << error << endl;
+        if (ctx) fq_destroy(ctx);
+        return EXIT_FAILURE;
+    } catch (const string &error) {
+        cerr << "Caught the error " << error << endl;
+        if (ctx) fq_destroy(ctx);
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}

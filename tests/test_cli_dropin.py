@@ -1,0 +1,87 @@
+"""Drop-in check at the command line: the same flags through the reference binary (oracle/_ref/FaQCs)
+and through faqcs_b200/host/faqcs_b200 must leave byte-identical files: the four trimmed FASTQ files,
+QC.stats.txt and the ten --debug matrix / histogram files."""
+import gzip
+import os
+import shutil
+import signal
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import refcli
+from faqcs_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "faqcs_b200", "host", "faqcs_b200")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refcli.have_ref(), reason="reference binary not present"),
+              pytest.mark.skipif(not os.path.exists(CLI), reason="CLI not built")]
+
+
+def run_both(inputs, flags, threads=2, extra_cli=()):
+    tmp = tempfile.mkdtemp(prefix="faqcs_cli_")
+    try:
+        args = []
+        for flag, (name, data) in inputs.items():
+            path = os.path.join(tmp, name)
+            if name.endswith(".gz"):
+                with gzip.open(path, "wb", compresslevel=1) as fh:
+                    fh.write(bytes(data))
+            else:
+                open(path, "wb").write(bytes(data))
+            args += [flag, path]
+        outs = {}
+        for tag, exe, more in (("ref", refcli.REF_BIN, []), ("gpu", CLI, list(extra_cli))):
+            out = os.path.join(tmp, tag)
+            p = subprocess.run([exe, "-d", out, "-t", str(threads), "--debug"] + args + list(flags) + more, stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, preexec_fn=lambda: signal.signal(signal.SIGPIPE, signal.SIG_IGN))
+            assert p.returncode == 0, (tag, p.stderr.decode(errors="replace")[-600:])
+            outs[tag] = {n: open(os.path.join(out, n), "rb").read() for n in sorted(os.listdir(out)) if not n.endswith(".pdf")}
+        return outs
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def assert_same_files(outs):
+    ref, gpu = outs["ref"], outs["gpu"]
+    assert sorted(ref) == sorted(gpu), (sorted(ref), sorted(gpu))
+    for name in ref:
+        if ref[name] != gpu[name]:
+            a, b = gpu[name], ref[name]
+            k = next((j for j in range(min(len(a), len(b))) if a[j] != b[j]), min(len(a), len(b)))
+            raise AssertionError(f"{name} differs at byte {k}: {a[max(0,k-80):k+80]!r} vs reference {b[max(0,k-80):k+80]!r}")
+
+
+def test_paired_defaults_discard_small_batches():
+    w = synth.c2(40000)
+    outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, ["--discard"], threads=4, extra_cli=["--batch_mb", "3"])
+    assert_same_files(outs)
+    assert len(outs["ref"]) == 15          # 4 fastq + stats + 10 data files
+
+
+def test_unpaired_gz_ascii64_hard():
+    w = synth.c5(20000)
+    outs = run_both({"-u": ("u.fq.gz", w.r1)}, ["--mode", "HARD", "-q", "20", "--avg_q", "25", "--replace_to_N_q", "10", "--discard"])
+    assert_same_files(outs)
+
+
+def test_qc_only_single_end():
+    w = synth.c4(30000)
+    assert_same_files(run_both({"-u": ("u.fq", w.r1)}, ["--qc_only"]))
+
+
+def test_adapters_polya_artifacts():
+    w = synth.c3(2000)
+    fa = "".join(f">{n}\n{s}\n" for n, s in w.artifacts).encode()
+    outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "--artifactFile": ("primers.fa", fa)},
+                    ["--adapter", "--polyA", "--rate", "0.2", "--5end", "3", "--min_L", "40"], threads=3)
+    assert_same_files(outs)
+
+
+def test_paired_then_unpaired_truncation_quirk():
+    w = synth.c2(3000)
+    u = synth.c4(2000)
+    outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "-u": ("u.fq", u.r1)}, ["--discard", "-q", "20"])
+    assert_same_files(outs)            # Q11: the -u pass truncates QC.unpaired / QC.discard written by the paired pass
