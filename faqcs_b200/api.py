@@ -209,7 +209,8 @@ def _np_from(ptr, n, dtype=np.uint64):
 
 
 def default_library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfaqcs_b200.so")
+    """In-tree build output; FAQCS_B200_LIB selects another build of the same library (kernel tuning variants)."""
+    return os.environ.get("FAQCS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfaqcs_b200.so")
 
 
 def load_library(path: Optional[str] = None) -> C.CDLL:

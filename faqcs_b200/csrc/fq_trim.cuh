@@ -41,19 +41,11 @@ __host__ __device__ __forceinline__ int base_code_slow(uint32_t c)
     c |= 0x20u;
     return c == 'a' ? 0 : c == 't' ? 1 : c == 'c' ? 2 : c == 'g' ? 3 : c == 'n' ? 4 : 5;
 }
-// LUT entry (16 bytes per character):
-//   x: bits 28..31 = class, bits 0..24 = 1 << (5 * class)      (generic path, packed per-lane counters)
-//   y: 10-bit one-hot fields A,T,C   z: 10-bit one-hot fields G,N   (per-read class counts, summed with REDUX)
-//   w: 6-bit one-hot fields A,T,C,G,N                               (per-position counts over the 32 reads of a group)
-__host__ __device__ __forceinline__ uint4 lut_entry(uint32_t c)
+// LUT entry: bits 28..31 = class, bits 0..24 = 1 << (5 * class) for classes 0..4 (packed per-lane counters).
+__host__ __device__ __forceinline__ uint32_t lut_entry(uint32_t c)
 {
     const int code = base_code_slow(c);
-    uint4 e;
-    e.x = ((uint32_t)code << 28) | (code < 5 ? (1u << (5 * code)) : 0u);
-    e.y = code < 3 ? (1u << (10 * code)) : 0u;
-    e.z = (code == 3 || code == 4) ? (1u << (10 * (code - 3))) : 0u;
-    e.w = code < 5 ? (1u << (6 * code)) : 0u;
-    return e;
+    return ((uint32_t)code << 28) | (code < 5 ? (1u << (5 * code)) : 0u);
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
@@ -151,24 +143,23 @@ extern __shared__ uint32_t g_smem[];
 struct SmemHist {
     uint32_t rows, key;
     // [42][rows] pre / removed quality, [5][rows] pre / removed base, [rows] g2n, [rows+1] x2 length,
-    // [4][42] avg-Q hists, [32] filter counters, [256] x 16-byte LUT, [12] composition bin 0, [2][7][key+1] composition by count
+    // [4][42] avg-Q hists, [32] filter counters, [256] LUT, [12] composition bin 0, [2][7][key+1] composition by count
     __host__ __device__ static size_t words(uint32_t rows, uint32_t key)
     {
-        return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + 4 * kQualCols + 32 + 1024 + 12 +
+        return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + 4 * kQualCols + 32 + 256 + 12 +
                (key == 0xffffffffu ? 0 : 14 * ((size_t)key + 1));
     }
-    __device__ __forceinline__ uint32_t *lut() const { return g_smem; }                 // first: 16-byte aligned entries
-    __device__ __forceinline__ uint32_t *preq() const { return g_smem + 1024; }
-    __device__ __forceinline__ uint32_t *remq() const { return preq() + kQualCols * rows; }
-    __device__ __forceinline__ uint32_t *preb() const { return preq() + 2 * kQualCols * rows; }
-    __device__ __forceinline__ uint32_t *remb() const { return preq() + (2 * kQualCols + kBaseCols) * rows; }
-    __device__ __forceinline__ uint32_t *g2n() const { return preq() + (2 * kQualCols + 2 * kBaseCols) * rows; }
-    __device__ __forceinline__ uint32_t *prelen() const { return preq() + (2 * kQualCols + 2 * kBaseCols + 1) * rows; }
+    __device__ __forceinline__ uint32_t *preq() const { return g_smem; }
+    __device__ __forceinline__ uint32_t *remq() const { return g_smem + kQualCols * rows; }
+    __device__ __forceinline__ uint32_t *preb() const { return g_smem + 2 * kQualCols * rows; }
+    __device__ __forceinline__ uint32_t *remb() const { return g_smem + (2 * kQualCols + kBaseCols) * rows; }
+    __device__ __forceinline__ uint32_t *g2n() const { return g_smem + (2 * kQualCols + 2 * kBaseCols) * rows; }
+    __device__ __forceinline__ uint32_t *prelen() const { return g_smem + (2 * kQualCols + 2 * kBaseCols + 1) * rows; }
     __device__ __forceinline__ uint32_t *postlen() const { return prelen() + rows + 1; }
     __device__ __forceinline__ uint32_t *qh() const { return postlen() + rows + 1; }
     __device__ __forceinline__ uint32_t *filt() const { return qh() + 4 * kQualCols; }
-    __device__ __forceinline__ uint32_t *zero() const { return filt() + 32; }
-    __device__ __forceinline__ const uint4 *lut4() const { return reinterpret_cast<const uint4 *>(lut()); }
+    __device__ __forceinline__ uint32_t *lut() const { return filt() + 32; }
+    __device__ __forceinline__ uint32_t *zero() const { return lut() + 256; }
     __device__ __forceinline__ uint32_t *compk() const { return zero() + 12; }
 };
 
@@ -293,7 +284,7 @@ __device__ __forceinline__ bool dinucleotide_low_complexity(const KernelCtx &kc,
         const bool in = i < wl;
         const uint32_t p = lo + i;
         const uint32_t c = in ? sp[p] : 0;
-        int cur = in ? (int)(kc.H.lut()[4 * c] >> 28) : 4;
+        int cur = in ? (int)(kc.H.lut()[c] >> 28) : 4;
         if (cur > 3) cur = 4;
         if (in && o.replace_q > 0 && c == 'G' && qa(p) < (int)o.replace_q) cur = 4;
         int prev = __shfl_up_sync(0xffffffffu, cur, 1);
@@ -392,115 +383,101 @@ struct LaneRead {
 
 __device__ __forceinline__ uint32_t f10(uint32_t packed, int field) { return (packed >> (10 * field)) & 1023u; }
 
-// Phase 1 for the read owned by lane j: PRE matrices + per-read summaries.  Lean on purpose: one
-// predicate per chunk, loads with immediate offsets from per-lane base pointers, out-of-range lanes
-// carry neutral values (base 0 -> LUT entry 0, quality = the offset char) so nothing else is predicated.
-// ACC: per-position base counts are kept in registers (6-bit fields) across the 32 reads of the group.
-template <int K, bool ACC>
+// Phase 1 for the read owned by lane j: PRE matrices + per-read summaries.
+template <int K>
 __device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *sp, const signed char *qp, uint32_t len, uint32_t r,
-                                       uint32_t (&acc)[5], int &out_sum, uint32_t &out_atc, uint32_t &out_gn, uint32_t &out_lead,
-                                       uint32_t &out_trail, uint32_t &out_run, uint32_t &err, uint32_t &err_rec)
+                                       int &out_sum, uint32_t &out_atc, uint32_t &out_gn, uint32_t &out_lead, uint32_t &out_trail,
+                                       uint32_t &out_run, uint32_t &err, uint32_t &err_rec)
 {
     const DevOpts &o = kc.o;
     const SmemHist &H = kc.H;
     const uint32_t lane = kc.lane, R = H.rows;
-    const uint8_t *spl = sp + lane;
-    const signed char *qpl = qp + lane;
     uint32_t c[K];
     int q[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const bool in = (int)lane < (int)len - 32 * k;
+        const uint32_t p = k * 32 + lane;
         c[k] = 0;
         q[k] = o.in_off;
-        if (in) { c[k] = spl[32 * k]; q[k] = (int)qpl[32 * k]; }
+        if (p < len) { c[k] = sp[p]; q[k] = (int)qp[p]; }
     }
-    // terminal 'N' runs (trim.cpp:1191-1216, uppercase only): decided by the first and the last base
+    uint32_t nm[K], any_n = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { nm[k] = __ballot_sync(0xffffffffu, c[k] == 'N'); any_n |= nm[k]; }
     uint32_t lead = 0, trail = len, run = 0;
-    const bool edge_n = len && (sp[0] == 'N' || sp[len - 1] == 'N');
-    if (edge_n) {
-        uint32_t nm[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) nm[k] = __ballot_sync(0xffffffffu, c[k] == 'N');
-        bool open = true;
+    if (any_n) {
+        bool last_n = false;
+        uint32_t n_count = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            if (open && (uint32_t)(k * 32) < len) {
-                const uint32_t nb = min(32u, len - k * 32);
-                const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-                const uint32_t inv = ~nm[k] & valid;
-                if (inv) { lead += __ffs(inv) - 1; open = false; }
-                else lead += nb;
+            if ((uint32_t)k == ((len - 1) >> 5)) last_n = (nm[k] >> ((len - 1) & 31)) & 1u;
+            n_count += __popc(nm[k]);
+        }
+        if ((nm[0] & 1u) || last_n) {                            // terminal 'N' runs (trim.cpp:1191-1216)
+            bool open = true;
+            lead = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (open && (uint32_t)(k * 32) < len) {
+                    const uint32_t nb = min(32u, len - k * 32);
+                    const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+                    const uint32_t inv = ~nm[k] & valid;
+                    if (inv) { lead += __ffs(inv) - 1; open = false; }
+                    else lead += nb;
+                }
+            }
+            open = true;
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) {
+                if (open && (uint32_t)(k * 32) < len) {
+                    const uint32_t nb = min(32u, len - k * 32);
+                    const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+                    const uint32_t inv = ~nm[k] & valid;
+                    if (inv) { trail = k * 32 + (31 - __clz(inv)) + 1; open = false; }
+                    else trail = k * 32;
+                }
+            }
+            if (lead >= len) trail = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint32_t p = k * 32 + lane;
+                if (p < lead || p >= trail) q[k] = o.in_off;
             }
         }
-        open = true;
+        if (n_count >= o.max_poly_n) {                           // candidate for the N filter: longest run of the whole read
+            RunTracker rt;
 #pragma unroll
-        for (int k = K - 1; k >= 0; --k) {
-            if (open && (uint32_t)(k * 32) < len) {
-                const uint32_t nb = min(32u, len - k * 32);
-                const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-                const uint32_t inv = ~nm[k] & valid;
-                if (inv) { trail = k * 32 + (31 - __clz(inv)) + 1; open = false; }
-                else trail = k * 32;
-            }
-        }
-        if (lead >= len) trail = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const uint32_t p = k * 32 + lane;
-            if (p < lead || p >= trail) q[k] = o.in_off;
+            for (int k = 0; k < K; ++k)
+                if ((uint32_t)(k * 32) < len) rt.feed(nm[k]);
+            run = rt.best;
         }
     }
-    int sum_q = 0, max_qv = 0;
-    uint32_t p_atc = 0, p_gn = 0;
-    uint32_t *pq = H.preq() + lane;
+    int sum_q = 0;
+    uint32_t packed = 0;
+    bool bad_q = false;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const bool in = (int)lane < (int)len - 32 * k;
-        const uint4 e = H.lut4()[c[k]];
-        const int qv = max(0, q[k] - o.in_off);
-        sum_q += q[k];
-        max_qv = max(max_qv, qv);
-        p_atc += e.y;
-        p_gn += e.z;
-        if (ACC) { if (k < 5) acc[k] += e.w; }
-        else if (in && (e.x >> 28) < 5) atomicAdd(&H.preb()[(e.x >> 28) * R + k * 32 + lane], 1u);
-        if (in) atomicAdd(pq + qv * R + 32 * k, 1u);       // qv > 41 only happens on the error path (whole batch rejected)
+        if ((uint32_t)(k * 32) < len) {
+            const uint32_t p = k * 32 + lane;
+            if (p < len) {
+                const uint32_t e = H.lut()[c[k]];
+                const uint32_t code = e >> 28;
+                const int qv = max(0, q[k] - o.in_off);
+                sum_q += q[k];
+                packed += e & 0x1ffffffu;
+                bad_q |= qv > FQ_MAX_QUALITY_SCORE;
+                if (qv <= FQ_MAX_QUALITY_SCORE) atomicAdd(&H.preq()[qv * R + p], 1u);
+                if (code < 5) atomicAdd(&H.preb()[code * R + p], 1u);
+            }
+        }
     }
-    max_qv = __reduce_max_sync(0xffffffffu, max_qv);
-    if (max_qv > FQ_MAX_QUALITY_SCORE) { err |= kErrQualGt41; err_rec = min(err_rec, r); }
-    out_sum = warp_sum_i(sum_q) - o.in_off * (int)(32 * K - len);     // out-of-range lanes added the offset char
-    out_atc = warp_sum(p_atc);
-    out_gn = warp_sum(p_gn);
-    // candidate for the N filter (count_poly_n needs at least -n 'N's): longest run of the whole read
-    if (f10(out_gn, 1) >= o.max_poly_n) {
-        RunTracker rt;
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-            if ((uint32_t)(k * 32) < len) rt.feed(__ballot_sync(0xffffffffu, c[k] == 'N'));
-        run = rt.best;
-    }
+    if (__any_sync(0xffffffffu, bad_q)) { err |= kErrQualGt41; err_rec = min(err_rec, r); }
+    out_sum = warp_sum_i(sum_q);
+    out_atc = warp_sum(unpack5(packed, 0) | (unpack5(packed, 1) << 10) | (unpack5(packed, 2) << 20));
+    out_gn = warp_sum(unpack5(packed, 3) | (unpack5(packed, 4) << 10));
     out_lead = lead;
     out_trail = trail;
     out_run = run;
-}
-
-// Per-position base counts of a 32-read group (6-bit fields A,T,C,G,N per chunk register) -> shared histogram.
-__device__ __forceinline__ void flush_base_acc(const KernelCtx &kc, uint32_t (&acc)[5])
-{
-    const uint32_t R = kc.H.rows;
-    uint32_t *pb = kc.H.preb() + kc.lane;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        if (acc[k]) {
-#pragma unroll
-            for (int code = 0; code < 5; ++code) {
-                const uint32_t v = (acc[k] >> (6 * code)) & 63u;
-                if (v) atomicAdd(pb + code * R + 32 * k, v);
-            }
-            acc[k] = 0;
-        }
-    }
 }
 
 // Cooperative pass over one read for the "removed" histograms.
@@ -530,7 +507,7 @@ __device__ __forceinline__ void removed_pass(const KernelCtx &kc, int mode, cons
         int qc = (int)qp[p];
         if (p < lead || p >= trail) qc = o.in_off;
         const int qv = max(0, qc - o.in_off);
-        const uint32_t code = H.lut()[4 * c] >> 28;
+        const uint32_t code = H.lut()[c] >> 28;
         const bool lowg = inside && o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q;
         if (mode == 0) {
             if (!inside) {
@@ -721,7 +698,7 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
         if (in) sum_q += qc;
         const int qv = max(0, qc - o.in_off);
         bad_q |= in && (qv > FQ_MAX_QUALITY_SCORE);
-        const int bc = in ? (int)(H.lut()[4 * c] >> 28) : 5;
+        const int bc = in ? (int)(H.lut()[c] >> 28) : 5;
         if (in && qv <= FQ_MAX_QUALITY_SCORE) {
             if (p < R) atomicAdd(&H.preq()[qv * R + p], 1u);
             else gadd(&S[L.pre_q + (size_t)qv * L.rows + p], 1);
@@ -767,7 +744,7 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
             if (in) sum_w += qc;
             const int qv = max(0, qc - o.in_off);
             max_qv = max(max_qv, in ? qv : 0);
-            const int bc = in ? (int)(H.lut()[4 * c] >> 28) : 5;
+            const int bc = in ? (int)(H.lut()[c] >> 28) : 5;
             const bool lowg = in && o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q;
             rt.feed(__ballot_sync(0xffffffffu, c == 'N'));
             n_lowg += __popc(__ballot_sync(0xffffffffu, lowg));
@@ -801,7 +778,7 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
             const uint32_t c = sp[p];
             const int qv = qa(p);
             if (!inside) {
-                const int bc = (int)(H.lut()[4 * c] >> 28);
+                const int bc = (int)(H.lut()[c] >> 28);
                 if (qv <= FQ_MAX_QUALITY_SCORE) {
                     if (p < R) atomicAdd(&H.remq()[qv * R + p], 1u);
                     else gadd(&S[L.rem_q + (size_t)qv * L.rows + p], 1);
@@ -830,15 +807,21 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
     }
 }
 
-constexpr int kTrimThreads = 512;
+#ifndef FQ_TRIM_THREADS
+#define FQ_TRIM_THREADS 512
+#endif
+#ifndef FQ_TRIM_MIN_CTAS
+#define FQ_TRIM_MIN_CTAS 2
+#endif
+constexpr int kTrimThreads = FQ_TRIM_THREADS;
 
-__global__ void __launch_bounds__(kTrimThreads, 2) k_trim(const TrimArgs a, const DevOpts o)
+__global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const TrimArgs a, const DevOpts o)
 {
     SmemHist H{a.smem_rows, a.comp_key_len};
     const size_t n_words = SmemHist::words(a.smem_rows, a.comp_key_len);
     for (size_t i = threadIdx.x; i < n_words; i += blockDim.x) g_smem[i] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint4 *>(H.lut())[i] = lut_entry(i);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) H.lut()[i] = lut_entry(i);
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
@@ -850,7 +833,6 @@ __global__ void __launch_bounds__(kTrimThreads, 2) k_trim(const TrimArgs a, cons
     const uint32_t R = H.rows;
     const KernelCtx kc{a, o, H, S, lane};
     LaneAcc acc;
-    uint32_t bacc[5] = {0, 0, 0, 0, 0};        // per-position base counts of the current 32-read group
     uint32_t err = 0, err_rec = 0xffffffffu;
     const bool need_max = o.in_off != o.out_off && o.out_off + FQ_MAX_QUALITY_SCORE > 127;   // re-encode can overflow
 
@@ -880,8 +862,8 @@ __global__ void __launch_bounds__(kTrimThreads, 2) k_trim(const TrimArgs a, cons
             int s_sum = 0;
             uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
             bool generic = false;
-            if (len <= 160 && len <= R) phase1<5, true>(kc, sp, qp, len, rj, bacc, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
-            else if (len <= 320 && len <= R) phase1<10, false>(kc, sp, qp, len, rj, bacc, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
+            if (len <= 160 && len <= R) phase1<5>(kc, sp, qp, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
+            else if (len <= 320 && len <= R) phase1<10>(kc, sp, qp, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
             else {
                 const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
                 process_generic(kc, mj, rj, rcj);
@@ -892,8 +874,6 @@ __global__ void __launch_bounds__(kTrimThreads, 2) k_trim(const TrimArgs a, cons
                 me.done = generic;
             }
         }
-
-        flush_base_acc(kc, bacc);
 
         // ---- phase 2a: one lane per read: PRE scalar statistics and the window
         const uint8_t *sp_mine = raw_mine + me.rc.seq;
