@@ -139,6 +139,7 @@ __device__ __forceinline__ void copy_span(uint8_t *dst, const uint8_t *src, uint
     const uint32_t body = (n - head) >> 4;
     const uint8_t *s = src + head;
     uint8_t *d = dst + head;
+#pragma unroll 4
     for (uint32_t c = lane; c < body; c += 32) {
         const uint8_t *sc = s + 16 * c;
         const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sc) & 3u) * 8u;
@@ -225,11 +226,54 @@ __device__ __forceinline__ void write_raw(uint8_t *dst, const uint8_t *raw, cons
     if (lane == 3) dst[q1] = '\n';
 }
 
+// Everything one lane knows about its record (pair) for emission.
+struct LaneRec {
+    Rec rc[2];
+    uint2 res[2];
+    bool canon[2], valid[2], plain[2];
+    uint32_t tsize[2];      // bytes of the trimmed record
+};
+
+__device__ __forceinline__ LaneRec lane_record(const EmitArgs &a, const DevOpts &o, uint32_t r)
+{
+    LaneRec L{};
+    if (r >= a.n_rec) return L;
+    const int n_mates = o.paired ? 2 : 1;
+    const bool requal = o.in_off != o.out_off;
+    for (int m = 0; m < n_mates; ++m) {
+        L.rc[m] = a.rec[m][r];
+        L.res[m] = a.res[m][r];
+        L.canon[m] = a.canon[m][r] != 0;
+        const uint32_t fl = L.res[m].y >> kResLenBits, wl = L.res[m].y & kResLenMask;
+        L.valid[m] = (fl & FQ_RR_VALID) != 0;
+        L.tsize[m] = header_len(a.raw[m], L.rc[m], L.canon[m]) + 2 * wl + 5;
+        // untouched canonical record: the emitted bytes are the raw bytes
+        L.plain[m] = L.valid[m] && L.canon[m] && L.res[m].x == 0 && wl == L.rc[m].len && !(fl & kFlagMasked) && !requal && o.replace_q == 0;
+    }
+    return L;
+}
+
+// Copy every run of consecutive lanes flagged in `mask` as ONE contiguous span: consecutive canonical
+// records are adjacent in the raw input and, when they go to the same stream, adjacent in the output.
+__device__ __forceinline__ void copy_runs(uint32_t mask, uint8_t *out, const uint8_t *raw, uint32_t src_mine, uint32_t size_mine,
+                                          uint32_t dst_mine, uint32_t lane)
+{
+    while (mask) {
+        const int first = __ffs(mask) - 1;
+        const uint32_t rest = ~(mask >> first);
+        const int run = rest ? __ffs(rest) - 1 : 32 - first;          // lanes first .. first+run-1
+        const int last = first + run - 1;
+        const uint32_t src = __shfl_sync(0xffffffffu, src_mine, first);
+        const uint32_t dst = __shfl_sync(0xffffffffu, dst_mine, first);
+        const uint32_t end = __shfl_sync(0xffffffffu, src_mine + size_mine, last);
+        copy_span(out + dst, raw + src, end - src, lane);
+        mask &= (run + first >= 32) ? 0u : ~((1u << (first + run)) - 1u);
+    }
+}
+
 __global__ void __launch_bounds__(kTile) k_emit(const EmitArgs a, const DevOpts o)
 {
-    __shared__ uint32_t s_off[4][kTile];
     __shared__ uint32_t s_wsum[4][kTile / 32];
-    __shared__ uint8_t s_valid[kTile];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kTile + threadIdx.x;
     uint32_t sz[4], wl[2];
@@ -248,45 +292,79 @@ __global__ void __launch_bounds__(kTile) k_emit(const EmitArgs a, const DevOpts 
         if (lane == 31) s_wsum[s][wid] = x;
     }
     __syncthreads();
+    uint32_t off[4];        // where this lane's record starts in each stream
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         uint32_t before = a.tile_sum[(size_t)s * a.n_tiles + blockIdx.x];
         for (uint32_t w = 0; w < wid; ++w) before += s_wsum[s][w];
-        s_off[s][threadIdx.x] = before + inc[s] - sz[s];
+        off[s] = before + inc[s] - sz[s];
     }
-    s_valid[threadIdx.x] = (uint8_t)((valid[0] ? 1 : 0) | (valid[1] ? 2 : 0));
-    __syncthreads();
     if (o.qc_only) return;
+    const LaneRec L = lane_record(a, o, r);
+    const bool in = r < a.n_rec;
 
-    // warp w copies records w*32 .. w*32+31 of the tile, one after the other
-    for (uint32_t k = 0; k < 32; ++k) {
-        const uint32_t t = wid * 32 + k;
-        const uint32_t rr = blockIdx.x * kTile + t;
-        if (rr >= a.n_rec) break;
-        const uint32_t vm = s_valid[t];
-        const bool v0 = vm & 1, v1 = (vm & 2) != 0;
-        if (o.paired) {
-            const Rec r0 = a.rec[0][rr], r1 = a.rec[1][rr];
-            const uint2 e0 = a.res[0][rr], e1 = a.res[1][rr];
-            const bool c0 = a.canon[0][rr] != 0, c1 = a.canon[1][rr] != 0;
-            if (v0 && v1) {
-                write_trimmed(a.out[0] + s_off[0][t], a.raw[0], r0, c0, e0.x, e0.y & kResLenMask, e0.y >> kResLenBits, o, lane);
-                write_trimmed(a.out[1] + s_off[1][t], a.raw[1], r1, c1, e1.x, e1.y & kResLenMask, e1.y >> kResLenBits, o, lane);
+    if (o.paired) {
+        const bool both = in && L.valid[0] && L.valid[1];
+        // block copies: runs of untouched pairs, mate by mate
+        copy_runs(__ballot_sync(0xffffffffu, both && L.plain[0]), a.out[0], a.raw[0], L.rc[0].hdr, L.tsize[0], off[0], lane);
+        copy_runs(__ballot_sync(0xffffffffu, both && L.plain[1]), a.out[1], a.raw[1], L.rc[1].hdr, L.tsize[1], off[1], lane);
+        // everything else, record by record
+        const bool single0 = in && ((both && !L.plain[0]) || (!both && L.valid[0]));
+        const bool single1 = in && ((both && !L.plain[1]) || (!both && L.valid[1]));
+        const bool disc = in && o.discard && !both && (!L.valid[0] || !L.valid[1]);
+        uint32_t todo = __ballot_sync(0xffffffffu, single0 || single1 || disc);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            Rec rc[2];
+            uint2 e[2];
+            bool cn[2], v[2], pl[2];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                rc[m].hdr = __shfl_sync(0xffffffffu, L.rc[m].hdr, j);
+                rc[m].seq = __shfl_sync(0xffffffffu, L.rc[m].seq, j);
+                rc[m].qual = __shfl_sync(0xffffffffu, L.rc[m].qual, j);
+                rc[m].len = __shfl_sync(0xffffffffu, L.rc[m].len, j);
+                e[m].x = __shfl_sync(0xffffffffu, L.res[m].x, j);
+                e[m].y = __shfl_sync(0xffffffffu, L.res[m].y, j);
+                cn[m] = __shfl_sync(0xffffffffu, (int)L.canon[m], j) != 0;
+                v[m] = __shfl_sync(0xffffffffu, (int)L.valid[m], j) != 0;
+                pl[m] = __shfl_sync(0xffffffffu, (int)L.plain[m], j) != 0;
+            }
+            uint32_t o4[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) o4[s] = __shfl_sync(0xffffffffu, off[s], j);
+            if (v[0] && v[1]) {
+                if (!pl[0]) write_trimmed(a.out[0] + o4[0], a.raw[0], rc[0], cn[0], e[0].x, e[0].y & kResLenMask, e[0].y >> kResLenBits, o, lane);
+                if (!pl[1]) write_trimmed(a.out[1] + o4[1], a.raw[1], rc[1], cn[1], e[1].x, e[1].y & kResLenMask, e[1].y >> kResLenBits, o, lane);
             } else {
-                if (v0) write_trimmed(a.out[2] + s_off[2][t], a.raw[0], r0, c0, e0.x, e0.y & kResLenMask, e0.y >> kResLenBits, o, lane);
-                else if (v1) write_trimmed(a.out[2] + s_off[2][t], a.raw[1], r1, c1, e1.x, e1.y & kResLenMask, e1.y >> kResLenBits, o, lane);
+                if (v[0]) write_trimmed(a.out[2] + o4[2], a.raw[0], rc[0], cn[0], e[0].x, e[0].y & kResLenMask, e[0].y >> kResLenBits, o, lane);
+                else if (v[1]) write_trimmed(a.out[2] + o4[2], a.raw[1], rc[1], cn[1], e[1].x, e[1].y & kResLenMask, e[1].y >> kResLenBits, o, lane);
                 if (o.discard) {
-                    uint32_t off = s_off[3][t];
-                    if (!v0) { write_raw(a.out[3] + off, a.raw[0], r0, c0, lane); off += header_len(a.raw[0], r0, c0) + 2 * r0.len + 5; }
-                    if (!v1) write_raw(a.out[3] + off, a.raw[1], r1, c1, lane);
+                    uint32_t d = o4[3];
+                    if (!v[0]) { write_raw(a.out[3] + d, a.raw[0], rc[0], cn[0], lane); d += header_len(a.raw[0], rc[0], cn[0]) + 2 * rc[0].len + 5; }
+                    if (!v[1]) write_raw(a.out[3] + d, a.raw[1], rc[1], cn[1], lane);
                 }
             }
-        } else {
-            const Rec r0 = a.rec[0][rr];
-            const uint2 e0 = a.res[0][rr];
-            const bool c0 = a.canon[0][rr] != 0;
-            if (v0) write_trimmed(a.out[2] + s_off[2][t], a.raw[0], r0, c0, e0.x, e0.y & kResLenMask, e0.y >> kResLenBits, o, lane);
-            else if (o.discard) write_raw(a.out[3] + s_off[3][t], a.raw[0], r0, c0, lane);
+        }
+    } else {
+        copy_runs(__ballot_sync(0xffffffffu, in && L.plain[0]), a.out[2], a.raw[0], L.rc[0].hdr, L.tsize[0], off[2], lane);
+        const bool single = in && L.valid[0] && !L.plain[0];
+        const bool disc = in && o.discard && !L.valid[0];
+        uint32_t todo = __ballot_sync(0xffffffffu, single || disc);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            Rec rc;
+            rc.hdr = __shfl_sync(0xffffffffu, L.rc[0].hdr, j);
+            rc.seq = __shfl_sync(0xffffffffu, L.rc[0].seq, j);
+            rc.qual = __shfl_sync(0xffffffffu, L.rc[0].qual, j);
+            rc.len = __shfl_sync(0xffffffffu, L.rc[0].len, j);
+            const uint32_t ex = __shfl_sync(0xffffffffu, L.res[0].x, j), ey = __shfl_sync(0xffffffffu, L.res[0].y, j);
+            const bool cn = __shfl_sync(0xffffffffu, (int)L.canon[0], j) != 0, v = __shfl_sync(0xffffffffu, (int)L.valid[0], j) != 0;
+            const uint32_t o2 = __shfl_sync(0xffffffffu, off[2], j), o3 = __shfl_sync(0xffffffffu, off[3], j);
+            if (v) write_trimmed(a.out[2] + o2, a.raw[0], rc, cn, ex, ey & kResLenMask, ey >> kResLenBits, o, lane);
+            else write_raw(a.out[3] + o3, a.raw[0], rc, cn, lane);
         }
     }
 }
