@@ -128,37 +128,62 @@ __global__ void __launch_bounds__(128) k_scan_tiles(uint32_t *tile_sum, uint32_t
 // Warp-cooperative copy of n bytes between arbitrarily aligned addresses.  The body is written
 // as 16-byte aligned stores; each store gathers its bytes from five aligned 32-bit source words
 // with funnel shifts (the source is L1/L2 resident raw input, neighbouring lanes share words).
-__device__ __forceinline__ void copy_span(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane)
+__device__ __forceinline__ uint4 gather16(const uint8_t *sc)
+{
+    // 16 bytes starting at the arbitrarily aligned address sc, from five aligned 32-bit words
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sc) & 3u) * 8u;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sc) & ~(uintptr_t)3);
+    const uint32_t w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
+    const uint32_t w4 = sh ? __ldg(sw + 4) : 0u;          // only bytes below src + n are ever consumed from it
+    uint4 v;
+    v.x = __funnelshift_r(w0, w1, sh);
+    v.y = __funnelshift_r(w1, w2, sh);
+    v.z = __funnelshift_r(w2, w3, sh);
+    v.w = __funnelshift_r(w3, w4, sh);
+    return v;
+}
+
+// `lane` / W: position and size of the cooperating lane group (a whole warp, or an 8-lane sub-group).
+template <uint32_t W = 32>
+__device__ __forceinline__ void copy_span(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n, uint32_t lane)
 {
     if (n < 48) {
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        for (uint32_t i = lane; i < n; i += W) dst[i] = src[i];
         return;
     }
     const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
-    if (lane < head) dst[lane] = src[lane];
+    for (uint32_t i = lane; i < head; i += W) dst[i] = src[i];
     const uint32_t body = (n - head) >> 4;
     const uint8_t *s = src + head;
     uint8_t *d = dst + head;
-#pragma unroll 4
-    for (uint32_t c = lane; c < body; c += 32) {
-        const uint8_t *sc = s + 16 * c;
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sc) & 3u) * 8u;
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sc) & ~(uintptr_t)3);
-        const uint32_t w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
-        const uint32_t w4 = sh ? __ldg(sw + 4) : 0u;          // only bytes below src + n are ever consumed from it
-        uint4 v;
-        v.x = __funnelshift_r(w0, w1, sh);
-        v.y = __funnelshift_r(w1, w2, sh);
-        v.z = __funnelshift_r(w2, w3, sh);
-        v.w = __funnelshift_r(w3, w4, sh);
-        *reinterpret_cast<uint4 *>(d + 16 * c) = v;
+    uint32_t c = lane;
+    // four 16-byte chunks per lane per round: all loads are issued before the first store, so a warp keeps
+    // 2 KiB in flight (the compiler cannot hoist loads over stores through possibly aliasing pointers)
+    for (; c + 3 * W < body; c += 4 * W) {
+        const uint4 v0 = gather16(s + 16 * c), v1 = gather16(s + 16 * (c + W)), v2 = gather16(s + 16 * (c + 2 * W)), v3 = gather16(s + 16 * (c + 3 * W));
+        *reinterpret_cast<uint4 *>(d + 16 * c) = v0;
+        *reinterpret_cast<uint4 *>(d + 16 * (c + W)) = v1;
+        *reinterpret_cast<uint4 *>(d + 16 * (c + 2 * W)) = v2;
+        *reinterpret_cast<uint4 *>(d + 16 * (c + 3 * W)) = v3;
     }
-    for (uint32_t i = head + 16 * body + lane; i < n; i += 32) dst[i] = src[i];
+    {
+        // up to three more chunks for this lane
+        const bool p0 = c < body, p1 = c + W < body, p2 = c + 2 * W < body;
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
+        if (p0) v0 = gather16(s + 16 * c);
+        if (p1) v1 = gather16(s + 16 * (c + W));
+        if (p2) v2 = gather16(s + 16 * (c + 2 * W));
+        if (p0) *reinterpret_cast<uint4 *>(d + 16 * c) = v0;
+        if (p1) *reinterpret_cast<uint4 *>(d + 16 * (c + W)) = v1;
+        if (p2) *reinterpret_cast<uint4 *>(d + 16 * (c + 2 * W)) = v2;
+    }
+    for (uint32_t i = head + 16 * body + lane; i < n; i += W) dst[i] = src[i];
 }
 
 // Emit one surviving read: def \n seq \n + \n qual \n (write_read, fastq.cpp:127-138) with the
 // mutations trim_read leaves behind.  `plain`: the record is canonical, untrimmed and untouched,
 // so the output is its raw bytes.
+template <uint32_t W = 32>
 __device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, const Rec &rc, bool canon, uint32_t lo, uint32_t wl,
                                               uint32_t flags, const DevOpts &o, uint32_t lane)
 {
@@ -166,7 +191,7 @@ __device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, 
     const bool masked = (flags & kFlagMasked) != 0;
     const bool requal = o.in_off != o.out_off;
     if (canon && lo == 0 && wl == rc.len && !masked && !requal && o.replace_q == 0) {
-        copy_span(dst, raw + rc.hdr, hl + 2 * wl + 5, lane);
+        copy_span<W>(dst, raw + rc.hdr, hl + 2 * wl + 5, lane);
         return;
     }
     const uint8_t *sp = raw + rc.seq;
@@ -179,13 +204,13 @@ __device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, 
     }
     const uint32_t s0 = hl + 1, s1 = s0 + wl, q0 = s1 + 3, q1 = q0 + wl;
     // header (+ its '\n' and, when nothing was cut at the 5' end, the bases: one contiguous source run)
-    if (canon && lo == 0 && o.replace_q == 0) copy_span(dst, raw + rc.hdr, s1, lane);
+    if (canon && lo == 0 && o.replace_q == 0) copy_span<W>(dst, raw + rc.hdr, s1, lane);
     else {
-        copy_span(dst, raw + rc.hdr, hl, lane);
+        copy_span<W>(dst, raw + rc.hdr, hl, lane);
         if (lane == 0) dst[hl] = '\n';
-        if (o.replace_q == 0) copy_span(dst + s0, sp + lo, wl, lane);
+        if (o.replace_q == 0) copy_span<W>(dst + s0, sp + lo, wl, lane);
         else {
-            for (uint32_t i = lane; i < wl; i += 32) {          // G -> N below --replace_to_N_q (trim.cpp:390-403)
+            for (uint32_t i = lane; i < wl; i += W) {          // G -> N below --replace_to_N_q (trim.cpp:390-403)
                 const uint32_t p = lo + i;
                 uint32_t ch = sp[p];
                 if (ch == 'G') {
@@ -197,9 +222,9 @@ __device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, 
         }
     }
     if (lane < 3) dst[s1 + lane] = lane == 1 ? '+' : '\n';
-    if (!masked && !requal) copy_span(dst + q0, raw + rc.qual + lo, wl, lane);
+    if (!masked && !requal) copy_span<W>(dst + q0, raw + rc.qual + lo, wl, lane);
     else {
-        for (uint32_t i = lane; i < wl; i += 32) {
+        for (uint32_t i = lane; i < wl; i += W) {
             const uint32_t p = lo + i;
             int qc = (p < lead || p >= trail) ? o.in_off : (int)qp[p];
             if (requal) qc = max(0, qc - o.in_off) + o.out_off;  // trim.cpp:516-525
@@ -210,19 +235,20 @@ __device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, 
 }
 
 // Emit one discarded read: the raw, unmasked record (copy taken before trim(), FaQCs.cpp:279-285).
+template <uint32_t W = 32>
 __device__ __forceinline__ void write_raw(uint8_t *dst, const uint8_t *raw, const Rec &rc, bool canon, uint32_t lane)
 {
     const uint32_t hl = header_len(raw, rc, canon);
     if (canon) {
-        copy_span(dst, raw + rc.hdr, hl + 2 * rc.len + 5, lane);
+        copy_span<W>(dst, raw + rc.hdr, hl + 2 * rc.len + 5, lane);
         return;
     }
     const uint32_t s0 = hl + 1, s1 = s0 + rc.len, q0 = s1 + 3, q1 = q0 + rc.len;
-    copy_span(dst, raw + rc.hdr, hl, lane);
+    copy_span<W>(dst, raw + rc.hdr, hl, lane);
     if (lane == 0) dst[hl] = '\n';
-    copy_span(dst + s0, raw + rc.seq, rc.len, lane);
+    copy_span<W>(dst + s0, raw + rc.seq, rc.len, lane);
     if (lane < 3) dst[s1 + lane] = lane == 1 ? '+' : '\n';
-    copy_span(dst + q0, raw + rc.qual, rc.len, lane);
+    copy_span<W>(dst + q0, raw + rc.qual, rc.len, lane);
     if (lane == 3) dst[q1] = '\n';
 }
 
@@ -266,7 +292,7 @@ __device__ __forceinline__ void copy_runs(uint32_t mask, uint8_t *out, const uin
         const uint32_t src = __shfl_sync(0xffffffffu, src_mine, first);
         const uint32_t dst = __shfl_sync(0xffffffffu, dst_mine, first);
         const uint32_t end = __shfl_sync(0xffffffffu, src_mine + size_mine, last);
-        copy_span(out + dst, raw + src, end - src, lane);
+        copy_span<32>(out + dst, raw + src, end - src, lane);
         mask &= (run + first >= 32) ? 0u : ~((1u << (first + run)) - 1u);
     }
 }
@@ -313,37 +339,47 @@ __global__ void __launch_bounds__(kTile) k_emit(const EmitArgs a, const DevOpts 
         const bool single1 = in && ((both && !L.plain[1]) || (!both && L.valid[1]));
         const bool disc = in && o.discard && !both && (!L.valid[0] || !L.valid[1]);
         uint32_t todo = __ballot_sync(0xffffffffu, single0 || single1 || disc);
+        const uint32_t sub = lane & 7, grp = lane >> 3;
         while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
+            // four records at a time, one per 8-lane group: each record is a short chain of dependent
+            // load -> store round trips, so concurrency across records is what hides the latency
+            int j = -1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int b = todo ? __ffs(todo) - 1 : -1;
+                if (b >= 0) todo &= todo - 1;
+                if ((int)grp == g) j = b;
+            }
+            const int js = j < 0 ? 0 : j;
             Rec rc[2];
             uint2 e[2];
             bool cn[2], v[2], pl[2];
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-                rc[m].hdr = __shfl_sync(0xffffffffu, L.rc[m].hdr, j);
-                rc[m].seq = __shfl_sync(0xffffffffu, L.rc[m].seq, j);
-                rc[m].qual = __shfl_sync(0xffffffffu, L.rc[m].qual, j);
-                rc[m].len = __shfl_sync(0xffffffffu, L.rc[m].len, j);
-                e[m].x = __shfl_sync(0xffffffffu, L.res[m].x, j);
-                e[m].y = __shfl_sync(0xffffffffu, L.res[m].y, j);
-                cn[m] = __shfl_sync(0xffffffffu, (int)L.canon[m], j) != 0;
-                v[m] = __shfl_sync(0xffffffffu, (int)L.valid[m], j) != 0;
-                pl[m] = __shfl_sync(0xffffffffu, (int)L.plain[m], j) != 0;
+                rc[m].hdr = __shfl_sync(0xffffffffu, L.rc[m].hdr, js);
+                rc[m].seq = __shfl_sync(0xffffffffu, L.rc[m].seq, js);
+                rc[m].qual = __shfl_sync(0xffffffffu, L.rc[m].qual, js);
+                rc[m].len = __shfl_sync(0xffffffffu, L.rc[m].len, js);
+                e[m].x = __shfl_sync(0xffffffffu, L.res[m].x, js);
+                e[m].y = __shfl_sync(0xffffffffu, L.res[m].y, js);
+                cn[m] = __shfl_sync(0xffffffffu, (int)L.canon[m], js) != 0;
+                v[m] = __shfl_sync(0xffffffffu, (int)L.valid[m], js) != 0;
+                pl[m] = __shfl_sync(0xffffffffu, (int)L.plain[m], js) != 0;
             }
             uint32_t o4[4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) o4[s] = __shfl_sync(0xffffffffu, off[s], j);
+            for (int s = 0; s < 4; ++s) o4[s] = __shfl_sync(0xffffffffu, off[s], js);
+            if (j < 0) continue;
             if (v[0] && v[1]) {
-                if (!pl[0]) write_trimmed(a.out[0] + o4[0], a.raw[0], rc[0], cn[0], e[0].x, e[0].y & kResLenMask, e[0].y >> kResLenBits, o, lane);
-                if (!pl[1]) write_trimmed(a.out[1] + o4[1], a.raw[1], rc[1], cn[1], e[1].x, e[1].y & kResLenMask, e[1].y >> kResLenBits, o, lane);
+                if (!pl[0]) write_trimmed<8>(a.out[0] + o4[0], a.raw[0], rc[0], cn[0], e[0].x, e[0].y & kResLenMask, e[0].y >> kResLenBits, o, sub);
+                if (!pl[1]) write_trimmed<8>(a.out[1] + o4[1], a.raw[1], rc[1], cn[1], e[1].x, e[1].y & kResLenMask, e[1].y >> kResLenBits, o, sub);
             } else {
-                if (v[0]) write_trimmed(a.out[2] + o4[2], a.raw[0], rc[0], cn[0], e[0].x, e[0].y & kResLenMask, e[0].y >> kResLenBits, o, lane);
-                else if (v[1]) write_trimmed(a.out[2] + o4[2], a.raw[1], rc[1], cn[1], e[1].x, e[1].y & kResLenMask, e[1].y >> kResLenBits, o, lane);
+                if (v[0]) write_trimmed<8>(a.out[2] + o4[2], a.raw[0], rc[0], cn[0], e[0].x, e[0].y & kResLenMask, e[0].y >> kResLenBits, o, sub);
+                else if (v[1]) write_trimmed<8>(a.out[2] + o4[2], a.raw[1], rc[1], cn[1], e[1].x, e[1].y & kResLenMask, e[1].y >> kResLenBits, o, sub);
                 if (o.discard) {
                     uint32_t d = o4[3];
-                    if (!v[0]) { write_raw(a.out[3] + d, a.raw[0], rc[0], cn[0], lane); d += header_len(a.raw[0], rc[0], cn[0]) + 2 * rc[0].len + 5; }
-                    if (!v[1]) write_raw(a.out[3] + d, a.raw[1], rc[1], cn[1], lane);
+                    if (!v[0]) { write_raw<8>(a.out[3] + d, a.raw[0], rc[0], cn[0], sub); d += header_len(a.raw[0], rc[0], cn[0]) + 2 * rc[0].len + 5; }
+                    if (!v[1]) write_raw<8>(a.out[3] + d, a.raw[1], rc[1], cn[1], sub);
                 }
             }
         }
