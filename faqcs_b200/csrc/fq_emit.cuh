@@ -297,7 +297,10 @@ __device__ __forceinline__ void copy_runs(uint32_t mask, uint8_t *out, const uin
     }
 }
 
-__global__ void __launch_bounds__(kTile) k_emit(const EmitArgs a, const DevOpts o)
+#ifndef FQ_EMIT_MIN_CTAS
+#define FQ_EMIT_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs a, const DevOpts o)
 {
     __shared__ uint32_t s_wsum[4][kTile / 32];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
