@@ -36,6 +36,9 @@ struct AdapterArgs {
     BatchInfo *info;
     unsigned long long first_index;   // global index of record 0 (Q3 emulation)
     unsigned long long end_index;     // first_index + n_rec if this is the final batch, else ~0
+    uint32_t use_planes;              // bit-plane prefilter enabled (planes fit in shared memory)
+    uint32_t plane_words;             // total words of the adapter bit planes (incl. padding)
+    uint32_t has_gap;                 // some adapter contains '-'
 };
 
 // seq_overlap.cpp:372-411; 0xff = unknown base (the reference throws)
@@ -50,23 +53,98 @@ __device__ __forceinline__ uint32_t na_to_bits(uint32_t c)
     }
 }
 
+// Exact alignment of the warp's read (codes in s_read) against one adapter: the cell with the largest M,
+// ties to the last cell in (i outer, j inner) order.  Returns the score; start/stop only change if score > 0.
+__device__ __forceinline__ int exact_align(const uint8_t *s_read, uint32_t L, const uint8_t *t, uint32_t T, uint32_t lane, int &st_start, int &st_stop)
+{
+    int bM = 0, bi = 0, bj = 0, bst = 0;      // per-lane best over the diagonals this lane walks: (M, i, jj) lexicographic max
+    for (int d0 = -(int)(L - 1); d0 <= (int)T - 1; d0 += 32) {
+        const int d = d0 + (int)lane;
+        const int i_lo = max(0, -(d0 + 31));
+        const int i_hi = min((int)L - 1, (int)T - 1 - d0);
+        int M = 0, st = i_lo, gM = 0, gi = 0, gst = 0;
+        for (int i = i_lo; i <= i_hi; ++i) {
+            const int jj = i + d;
+            const uint32_t qi = s_read[i];
+            if ((unsigned)jj < T) {
+                const bool match = (qi & t[jj]) != 0;
+                st = (M < 0) ? i : st;
+                M = max(M, 0) + (match ? 1 : -1);
+                if (M >= gM && M > 0) { gM = M; gi = i; gst = st; }
+            } else {
+                M = 0;
+                st = i + 1;
+            }
+        }
+        const int gj = gi + d;
+        if (gM > bM || (gM == bM && gM > 0 && (gi > bi || (gi == bi && gj > bj)))) { bM = gM; bi = gi; bj = gj; bst = gst; }
+    }
+    const unsigned long long key = bM > 0 ? (((unsigned long long)bM << 48) | ((unsigned long long)bi << 24) | (unsigned long long)bj) : 0ull;
+    unsigned long long kmax = key;
+#pragma unroll
+    for (int k = 16; k; k >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, kmax, k);
+        kmax = other > kmax ? other : kmax;
+    }
+    if (!kmax) return 0;
+    const uint32_t win = __ballot_sync(0xffffffffu, key == kmax);
+    st_stop = (int)((kmax >> 24) & 0xffffffu);
+    st_start = __shfl_sync(0xffffffffu, bst, __ffs(win) - 1);
+    return (int)(kmax >> 48);
+}
+
+// Shared memory: [offsets n+1][plane offsets n+1][adapter codes][adapter bit planes][per warp: read codes, mask words, read planes]
+//
+// Prefilter (exact-safe): an adapter can only pass the threshold test num_match >= threshold (trim.cpp:1024-1027)
+// if SOME diagonal holds at least `threshold` matching positions, because num_match counts the matches inside
+// one diagonal segment.  Matches per diagonal are popcounts over base bit planes (A,C,G,T,gap: a read base
+// matches an adapter base iff their IUPAC bit sets intersect), 32 diagonals per round, one per lane.  Only
+// adapters that survive get the exact alignment; the stale range an all-mismatch adapter inherits (Q5) is
+// produced lazily by aligning the nearest earlier adapter that shares a base with the read.
 __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevOpts o, const AdapterSet A)
 {
     extern __shared__ uint32_t smem_u32[];
-    // layout: [adapter offsets n+1][adapter codes, padded to 4][per-warp: read codes (max_len padded to 4) + mask words]
     uint32_t *s_off = smem_u32;
-    uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_off + A.n + 1);
+    uint32_t *s_poff = s_off + A.n + 1;
+    uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_poff + A.n + 1);
     const uint32_t codes_pad = (A.total + 3) & ~3u;
     const uint32_t read_pad = (a.max_len + 3) & ~3u;
-    const uint32_t mask_words = (a.max_len + 31) >> 5;
+    const uint32_t mask_words = (a.max_len + 31) >> 5;         // also the number of words of a read bit plane
+    const uint32_t pad = a.use_planes ? mask_words + 1 : 0;    // zero words on both sides of every adapter plane
+    uint32_t *s_planes = reinterpret_cast<uint32_t *>(s_codes + codes_pad);
     const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *warp_base = s_codes + codes_pad + (size_t)warp_in_cta * (read_pad + 4 * mask_words);
-    uint8_t *s_read = warp_base;
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(warp_base + read_pad);
+    const uint32_t per_warp_words = read_pad / 4 + mask_words + (a.use_planes ? 5 * mask_words : 0);
+    uint32_t *warp_base = s_planes + a.plane_words + (size_t)warp_in_cta * per_warp_words;
+    uint8_t *s_read = reinterpret_cast<uint8_t *>(warp_base);
+    uint32_t *s_mask = warp_base + read_pad / 4;
+    uint32_t *s_rp = s_mask + mask_words;                      // read planes [5][mask_words]
 
     for (uint32_t i = threadIdx.x; i <= A.n; i += blockDim.x) s_off[i] = A.offset[i];
     for (uint32_t i = threadIdx.x; i < A.total; i += blockDim.x) s_codes[i] = A.codes[i];
     __syncthreads();
+    if (a.use_planes) {
+        // plane block of adapter j: 5 planes x (Wt_j + 2 * pad) words; offsets by a serial prefix (n is small)
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (uint32_t j = 0; j < A.n; ++j) {
+                s_poff[j] = acc;
+                acc += 5 * (((s_off[j + 1] - s_off[j]) + 31) / 32 + 2 * pad);
+            }
+            s_poff[A.n] = acc;
+        }
+        for (uint32_t i = threadIdx.x; i < a.plane_words; i += blockDim.x) s_planes[i] = 0;
+        __syncthreads();
+        for (uint32_t j = 0; j < A.n; ++j) {
+            const uint32_t T = s_off[j + 1] - s_off[j], stride = (T + 31) / 32 + 2 * pad;
+            for (uint32_t p = threadIdx.x; p < T; p += blockDim.x) {
+                const uint32_t code = s_codes[s_off[j] + p];
+#pragma unroll
+                for (int b = 0; b < 5; ++b)
+                    if ((code >> b) & 1u) atomicOr(&s_planes[s_poff[j] + b * stride + pad + (p >> 5)], 1u << (p & 31));
+            }
+        }
+        __syncthreads();
+    }
 
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -78,22 +156,34 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
         const Rec rc = a.rec[mate][r];
         const uint32_t L = rc.len;
         const uint8_t *sp = a.raw[mate] + rc.seq;
+        const uint32_t read_words = (L + 31) >> 5;
 
-        // pack_query (seq_overlap.h:370-411)
+        // pack_query (seq_overlap.h:370-411) + bit planes of the read
         bool unknown = false;
         uint32_t read_or = 0;
-        for (uint32_t p = lane; p < L; p += 32) {
-            const uint32_t b = na_to_bits(sp[p]);
-            unknown |= (b == 0xffu);
-            read_or |= b;
-            s_read[p] = (uint8_t)b;
+        for (uint32_t b0 = 0; b0 < L; b0 += 32) {
+            const uint32_t p = b0 + lane;
+            uint32_t code = 0;
+            if (p < L) {
+                code = na_to_bits(sp[p]);
+                unknown |= (code == 0xffu);
+                s_read[p] = (uint8_t)code;
+                if (code == 0xffu) code = 0;
+            }
+            read_or |= code;
+            if (a.use_planes) {
+#pragma unroll
+                for (int b = 0; b < 5; ++b) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, (code >> b) & 1u);
+                    if (lane == 0) s_rp[b * mask_words + (b0 >> 5)] = m;
+                }
+            }
         }
         for (uint32_t w = lane; w < mask_words; w += 32) s_mask[w] = 0;     // 1 = masked
         if (__any_sync(0xffffffffu, unknown)) {
             if (lane == 0) { atomicOr(&a.info->err, kErrUnknownBase); atomicMin(&a.info->err_record, r); }
         }
-#pragma unroll
-        for (int k = 16; k; k >>= 1) read_or |= __shfl_xor_sync(0xffffffffu, read_or, k);
+        read_or = __reduce_or_sync(0xffffffffu, read_or);
         __syncwarp();
 
         // Q3: which length feeds the match threshold (trim.cpp:985,996-1008,1074-1082)
@@ -116,58 +206,60 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
 
         int best_score = 0, best_adapter = -1;
         int st_start = 0, st_stop = 0;            // max_elem.M_start_i / stop_i survive across align() calls (Q5)
-        bool any_pass = false;
+        int pending = -1;                         // last adapter that shares a base with the read but was not aligned yet
 
         for (uint32_t j = 0; j < A.n; ++j) {
             const uint32_t T = s_off[j + 1] - s_off[j];
             const uint8_t *t = s_codes + s_off[j];
-            int score = 0;
-            if ((read_or & A.or_bits[j]) && L && T) {
-                // per-lane best over the diagonals this lane walks: (M, i, jj) lexicographic max
-                int bM = 0, bi = 0, bj = 0, bst = 0;
-                for (int d0 = -(int)(L - 1); d0 <= (int)T - 1; d0 += 32) {
-                    const int d = d0 + (int)lane;
-                    const int i_lo = max(0, -(d0 + 31));
-                    const int i_hi = min((int)L - 1, (int)T - 1 - d0);
-                    int M = 0, st = i_lo, gM = 0, gi = 0, gst = 0;
-                    for (int i = i_lo; i <= i_hi; ++i) {
-                        const int jj = i + d;
-                        const uint32_t qi = s_read[i];
-                        if ((unsigned)jj < T) {
-                            const bool match = (qi & t[jj]) != 0;
-                            st = (M < 0) ? i : st;
-                            M = max(M, 0) + (match ? 1 : -1);
-                            if (M >= gM && M > 0) { gM = M; gi = i; gst = st; }
-                        } else {
-                            M = 0;
-                            st = i + 1;
-                        }
-                    }
-                    const int gj = gi + d;
-                    if (gM > bM || (gM == bM && gM > 0 && (gi > bi || (gi == bi && gj > bj)))) { bM = gM; bi = gi; bj = gj; bst = gst; }
-                }
-                unsigned long long key = bM > 0 ? (((unsigned long long)bM << 48) | ((unsigned long long)bi << 24) | (unsigned long long)bj) : 0ull;
-                unsigned long long kmax = key;
-#pragma unroll
-                for (int k = 16; k; k >>= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, kmax, k);
-                    kmax = other > kmax ? other : kmax;
-                }
-                if (kmax) {
-                    const uint32_t win = __ballot_sync(0xffffffffu, key == kmax);
-                    const int src = __ffs(win) - 1;
-                    score = (int)(kmax >> 48);
-                    st_stop = (int)((kmax >> 24) & 0xffffffu);
-                    st_start = __shfl_sync(0xffffffffu, bst, src);
-                }
-            }
-            // trim.cpp:1021-1041
             const uint32_t tl = thr_min ? min(thr_len, T) : T;
             const int threshold = __float2int_rz(__fmul_rn(o.match_rate, (float)tl));
+            int score = 0;
+            const bool shared = (read_or & A.or_bits[j]) && L && T;
+            if (shared) {
+                bool candidate = true;
+                if (a.use_planes) {
+                    // matches on every diagonal, 32 diagonals per round
+                    const uint32_t Wt = (T + 31) / 32, stride = Wt + 2 * pad;
+                    const uint32_t *tp = s_planes + s_poff[j] + pad;
+                    int cmax = 0;
+                    for (int d0 = -(int)(L - 1); d0 <= (int)T - 1; d0 += 32) {
+                        const int d = d0 + (int)lane;
+                        // read words that can overlap the adapter on these 32 diagonals
+                        const int w_lo = max(0, (-(d0 + 31)) >> 5), w_hi = min((int)read_words - 1, ((int)T - 1 - d0) >> 5);
+                        int cnt = 0;
+                        for (int w = w_lo; w <= w_hi; ++w) {
+                            const int ofs = 32 * w + d;                  // adapter bit that faces read bit 32*w
+                            const int idx = ofs >> 5;                    // floor
+                            const uint32_t sh = (uint32_t)ofs & 31u;
+                            uint32_t m = 0;
+#pragma unroll
+                            for (int b = 0; b < 5; ++b) {
+                                if (b == 4 && !a.has_gap) break;
+                                const uint32_t *pl = tp + b * stride;
+                                m |= s_rp[b * mask_words + w] & __funnelshift_r(pl[idx], pl[idx + 1], sh);
+                            }
+                            cnt += __popc(m);
+                        }
+                        if (d > (int)T - 1) cnt = 0;
+                        cmax = max(cmax, cnt);
+                    }
+                    cmax = __reduce_max_sync(0xffffffffu, cmax);
+                    candidate = cmax >= threshold;
+                }
+                if (candidate) {
+                    score = exact_align(s_read, L, t, T, lane, st_start, st_stop);
+                    pending = -1;
+                } else pending = (int)j;            // cannot pass; its range matters only to a later all-mismatch adapter
+            } else if (pending >= 0) {
+                // all-mismatch adapter: it reports the range left by the previous alignment (Q5): produce it now
+                exact_align(s_read, L, s_codes + s_off[pending], s_off[pending + 1] - s_off[pending], lane, st_start, st_stop);
+                pending = -1;
+            }
+            if (shared && score == 0 && pending >= 0) continue;      // skipped by the prefilter: cannot pass
+            // trim.cpp:1021-1041
             const int match_length = st_stop - st_start + 1;
             const int num_match = (match_length + score) / 2;
             if (num_match >= threshold) {
-                any_pass = true;
                 for (uint32_t w = lane; w < mask_words; w += 32) {
                     const int lo_b = max(st_start, (int)(w << 5)), hi_b = min(st_stop, (int)(w << 5) + 31);
                     if (lo_b <= hi_b) {
@@ -185,8 +277,7 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
         if (best_score > 0) {
             // find_mask_range (trim.cpp:1144-1189) over runs instead of bits; every lane runs it redundantly
             uint32_t run_start = 0, run_len = 0, longest = 0, longest_start = 0;
-            const uint32_t read_words = (L + 31) >> 5;          // only the words this read owns
-            for (uint32_t w = 0; w < read_words; ++w) {
+            for (uint32_t w = 0; w < read_words; ++w) {      // only the words this read owns
                 const uint32_t nbits = min(32u, L - (w << 5));
                 uint32_t keep = ~s_mask[w];
                 if (nbits < 32) keep &= (1u << nbits) - 1u;
@@ -214,7 +305,6 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
                 atomicAdd(&a.stats[a.L.adapter_bases + best_adapter], (unsigned long long)(L - longest));
             }
         }
-        (void)any_pass;
         if (lane == 0) {
             a.adp[mate][r] = make_uint2(out_start, out_len);
             a.adp_best[mate][r] = best_score > 0 ? best_adapter : -1;

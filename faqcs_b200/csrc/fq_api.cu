@@ -385,14 +385,29 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         aa.info = info;
         aa.first_index = first_record_index;
         aa.end_index = is_final ? first_record_index + n : ~0ull;
-        const size_t fixed = (size_t)(ctx->aset.n + 1) * 4 + ((ctx->aset.total + 3) & ~3u);
-        const size_t per_warp = ((max_len + 3) & ~3u) + 4 * (size_t)((max_len + 31) >> 5);
+        // shared memory plan: offsets, codes, [adapter bit planes], per warp read codes + mask (+ read planes)
+        const uint32_t mask_words = (max_len + 31) >> 5;
+        uint32_t plane_words = 0, has_gap = 0;
+        for (uint32_t j = 0; j < ctx->aset.n; ++j) {
+            plane_words += 5 * (((uint32_t)ctx->adapter_seqs[j].size() + 31) / 32 + 2 * (mask_words + 1));
+            if (ctx->adapter_seqs[j].find('-') != std::string::npos) has_gap = 1;
+        }
+        const size_t base_fixed = (size_t)(ctx->aset.n + 1) * 8 + ((ctx->aset.total + 3) & ~3u);
+        const size_t per_warp_plain = ((max_len + 3) & ~3u) + 4 * (size_t)mask_words;
+        const size_t per_warp_planes = per_warp_plain + 20 * (size_t)mask_words;
+        aa.use_planes = base_fixed + (size_t)plane_words * 4 + 4 * per_warp_planes <= ctx->smem_optin ? 1 : 0;
+        aa.plane_words = aa.use_planes ? plane_words : 0;
+        aa.has_gap = has_gap;
+        const size_t fixed = base_fixed + (size_t)aa.plane_words * 4;
+        const size_t per_warp = aa.use_planes ? per_warp_planes : per_warp_plain;
         int warps = 8;
         while (warps > 1 && fixed + warps * per_warp > ctx->smem_optin) warps >>= 1;
         const size_t smem = fixed + warps * per_warp;
         if (smem > ctx->smem_optin) return fail(ctx, FQ_ERR_ARG, "adapter set + read length exceed shared memory");
         CK(cudaFuncSetAttribute(k_adapter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = std::max(1, std::min<int>((n * n_mates + warps - 1) / warps, ctx->sm_count * 8));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adapter, warps * 32, smem));
+        const int grid = std::max(1, std::min<int>((n * n_mates + warps - 1) / warps, ctx->sm_count * std::max(per_sm, 1)));
         k_adapter<<<grid, warps * 32, smem, ctx->stream>>>(aa, o, ctx->aset);
         ctx->launches++;
     }
