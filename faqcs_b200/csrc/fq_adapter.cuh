@@ -39,6 +39,7 @@ struct AdapterArgs {
     uint32_t use_planes;              // bit-plane prefilter enabled (planes fit in shared memory)
     uint32_t plane_words;             // total words of the adapter bit planes (incl. padding)
     uint32_t has_gap;                 // some adapter contains '-'
+    uint32_t rpad;                    // zero words on both sides of every read bit plane (longest adapter in words + 1)
 };
 
 // seq_overlap.cpp:372-411; 0xff = unknown base (the reference throws)
@@ -110,37 +111,38 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
     const uint32_t codes_pad = (A.total + 3) & ~3u;
     const uint32_t read_pad = (a.max_len + 3) & ~3u;
     const uint32_t mask_words = (a.max_len + 31) >> 5;         // also the number of words of a read bit plane
-    const uint32_t pad = a.use_planes ? mask_words + 1 : 0;    // zero words on both sides of every adapter plane
+    const uint32_t rstride = mask_words + 2 * a.rpad;          // words of one (zero padded) read bit plane
     uint32_t *s_planes = reinterpret_cast<uint32_t *>(s_codes + codes_pad);
     const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t per_warp_words = read_pad / 4 + mask_words + (a.use_planes ? 5 * mask_words : 0);
+    const uint32_t per_warp_words = read_pad / 4 + mask_words + (a.use_planes ? 5 * rstride : 0);
     uint32_t *warp_base = s_planes + a.plane_words + (size_t)warp_in_cta * per_warp_words;
     uint8_t *s_read = reinterpret_cast<uint8_t *>(warp_base);
     uint32_t *s_mask = warp_base + read_pad / 4;
-    uint32_t *s_rp = s_mask + mask_words;                      // read planes [5][mask_words]
+    uint32_t *s_rp = s_mask + mask_words;                      // read planes [5][rstride], data at word offset rpad
 
     for (uint32_t i = threadIdx.x; i <= A.n; i += blockDim.x) s_off[i] = A.offset[i];
     for (uint32_t i = threadIdx.x; i < A.total; i += blockDim.x) s_codes[i] = A.codes[i];
     __syncthreads();
     if (a.use_planes) {
-        // plane block of adapter j: 5 planes x (Wt_j + 2 * pad) words; offsets by a serial prefix (n is small)
+        // plane block of adapter j: 5 planes x Wt_j words; offsets by a serial prefix (n is small)
         if (threadIdx.x == 0) {
             uint32_t acc = 0;
             for (uint32_t j = 0; j < A.n; ++j) {
                 s_poff[j] = acc;
-                acc += 5 * (((s_off[j + 1] - s_off[j]) + 31) / 32 + 2 * pad);
+                acc += 5 * (((s_off[j + 1] - s_off[j]) + 31) / 32);
             }
             s_poff[A.n] = acc;
         }
         for (uint32_t i = threadIdx.x; i < a.plane_words; i += blockDim.x) s_planes[i] = 0;
+        for (uint32_t i = lane; i < 5 * rstride; i += 32) s_rp[i] = 0;       // the padding stays zero for the whole kernel
         __syncthreads();
         for (uint32_t j = 0; j < A.n; ++j) {
-            const uint32_t T = s_off[j + 1] - s_off[j], stride = (T + 31) / 32 + 2 * pad;
+            const uint32_t T = s_off[j + 1] - s_off[j], stride = (T + 31) / 32;
             for (uint32_t p = threadIdx.x; p < T; p += blockDim.x) {
                 const uint32_t code = s_codes[s_off[j] + p];
 #pragma unroll
                 for (int b = 0; b < 5; ++b)
-                    if ((code >> b) & 1u) atomicOr(&s_planes[s_poff[j] + b * stride + pad + (p >> 5)], 1u << (p & 31));
+                    if ((code >> b) & 1u) atomicOr(&s_planes[s_poff[j] + b * stride + (p >> 5)], 1u << (p & 31));
             }
         }
         __syncthreads();
@@ -175,10 +177,15 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
 #pragma unroll
                 for (int b = 0; b < 5; ++b) {
                     const uint32_t m = __ballot_sync(0xffffffffu, (code >> b) & 1u);
-                    if (lane == 0) s_rp[b * mask_words + (b0 >> 5)] = m;
+                    if (lane == 0) s_rp[b * rstride + a.rpad + (b0 >> 5)] = m;
                 }
             }
         }
+        if (a.use_planes)       // a shorter read after a longer one: clear the plane words it does not own
+            for (uint32_t i = lane; i < 5 * (mask_words - read_words); i += 32) {
+                const uint32_t b = i / (mask_words - read_words), w = read_words + i % (mask_words - read_words);
+                s_rp[b * rstride + a.rpad + w] = 0;
+            }
         for (uint32_t w = lane; w < mask_words; w += 32) s_mask[w] = 0;     // 1 = masked
         if (__any_sync(0xffffffffu, unknown)) {
             if (lane == 0) { atomicOr(&a.info->err, kErrUnknownBase); atomicMin(&a.info->err_record, r); }
@@ -218,29 +225,32 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
             if (shared) {
                 bool candidate = true;
                 if (a.use_planes) {
-                    // matches on every diagonal, 32 diagonals per round
-                    const uint32_t Wt = (T + 31) / 32, stride = Wt + 2 * pad;
-                    const uint32_t *tp = s_planes + s_poff[j] + pad;
+                    // matches on every diagonal that is long enough to reach the threshold, 32 diagonals per round.
+                    // Diagonal d pairs adapter position j with read position j - d: for each adapter word the
+                    // facing 32 read bits are pulled out of the (zero padded) read planes with a funnel shift.
+                    const uint32_t Wt = (T + 31) / 32;
+                    const uint32_t *tp = s_planes + s_poff[j];
+                    const uint32_t *rp = s_rp + a.rpad;
+                    const int need = max(threshold, 1);
+                    const int d_lo = max(-(int)(L - 1), need - (int)L), d_hi = min((int)T - 1, (int)T - need);
                     int cmax = 0;
-                    for (int d0 = -(int)(L - 1); d0 <= (int)T - 1; d0 += 32) {
+                    for (int d0 = d_lo; d0 <= d_hi; d0 += 32) {
                         const int d = d0 + (int)lane;
-                        // read words that can overlap the adapter on these 32 diagonals
-                        const int w_lo = max(0, (-(d0 + 31)) >> 5), w_hi = min((int)read_words - 1, ((int)T - 1 - d0) >> 5);
                         int cnt = 0;
-                        for (int w = w_lo; w <= w_hi; ++w) {
-                            const int ofs = 32 * w + d;                  // adapter bit that faces read bit 32*w
+                        for (uint32_t wa = 0; wa < Wt; ++wa) {
+                            const int ofs = 32 * (int)wa - d;            // read bit that faces adapter bit 32*wa
                             const int idx = ofs >> 5;                    // floor
                             const uint32_t sh = (uint32_t)ofs & 31u;
                             uint32_t m = 0;
 #pragma unroll
                             for (int b = 0; b < 5; ++b) {
                                 if (b == 4 && !a.has_gap) break;
-                                const uint32_t *pl = tp + b * stride;
-                                m |= s_rp[b * mask_words + w] & __funnelshift_r(pl[idx], pl[idx + 1], sh);
+                                const uint32_t *pl = rp + b * rstride;
+                                m |= tp[b * Wt + wa] & __funnelshift_r(pl[idx], pl[idx + 1], sh);
                             }
                             cnt += __popc(m);
                         }
-                        if (d > (int)T - 1) cnt = 0;
+                        if (d > d_hi) cnt = 0;
                         cmax = max(cmax, cnt);
                     }
                     cmax = __reduce_max_sync(0xffffffffu, cmax);

@@ -387,14 +387,17 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         aa.end_index = is_final ? first_record_index + n : ~0ull;
         // shared memory plan: offsets, codes, [adapter bit planes], per warp read codes + mask (+ read planes)
         const uint32_t mask_words = (max_len + 31) >> 5;
-        uint32_t plane_words = 0, has_gap = 0;
+        uint32_t plane_words = 0, has_gap = 0, rpad = 1;
         for (uint32_t j = 0; j < ctx->aset.n; ++j) {
-            plane_words += 5 * (((uint32_t)ctx->adapter_seqs[j].size() + 31) / 32 + 2 * (mask_words + 1));
+            const uint32_t wt = ((uint32_t)ctx->adapter_seqs[j].size() + 31) / 32;
+            plane_words += 5 * wt;
+            rpad = std::max(rpad, wt + 1);
             if (ctx->adapter_seqs[j].find('-') != std::string::npos) has_gap = 1;
         }
+        aa.rpad = rpad;
         const size_t base_fixed = (size_t)(ctx->aset.n + 1) * 8 + ((ctx->aset.total + 3) & ~3u);
         const size_t per_warp_plain = ((max_len + 3) & ~3u) + 4 * (size_t)mask_words;
-        const size_t per_warp_planes = per_warp_plain + 20 * (size_t)mask_words;
+        const size_t per_warp_planes = per_warp_plain + 20 * ((size_t)mask_words + 2 * rpad);
         aa.use_planes = base_fixed + (size_t)plane_words * 4 + 4 * per_warp_planes <= ctx->smem_optin ? 1 : 0;
         aa.plane_words = aa.use_planes ? plane_words : 0;
         aa.has_gap = has_gap;
