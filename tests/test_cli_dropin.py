@@ -85,3 +85,40 @@ def test_paired_then_unpaired_truncation_quirk():
     u = synth.c4(2000)
     outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "-u": ("u.fq", u.r1)}, ["--discard", "-q", "20"])
     assert_same_files(outs)            # Q11: the -u pass truncates QC.unpaired / QC.discard written by the paired pass
+
+
+def test_empty_input_prints_nan_layout():
+    # an empty file with --ascii 33 yields "Reads Length: -nan" etc.; both binaries must agree byte for byte
+    outs = run_both({"-u": ("empty.fq", b"")}, ["--ascii", "33"])
+    assert_same_files(outs)
+    assert b"-nan" in outs["ref"]["QC.stats.txt"]
+
+
+def _run(exe, args, tmp, tag):
+    out = os.path.join(tmp, tag)
+    return subprocess.run([exe, "-d", out, "-t", "2"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                          preexec_fn=lambda: signal.signal(signal.SIGPIPE, signal.SIG_IGN))
+
+
+def test_error_exits_match():
+    """Uneven pair files, a Q42 character and an undetectable offset: both binaries must fail (non-zero exit)."""
+    w = synth.c2(200)
+    tmp = tempfile.mkdtemp(prefix="faqcs_cli_err_")
+    try:
+        def put(name, data):
+            path = os.path.join(tmp, name)
+            open(path, "wb").write(bytes(data))
+            return path
+        r1, r2 = put("r1.fq", w.r1), put("r2.fq", w.r2)
+        cut = put("r2_short.fq", bytes(w.r2)[: w.r2.size // 2 - (w.r2.size // 2) % 339])
+        q42 = put("q42.fq", b"@a\n" + b"ACGT" * 20 + b"\n+\n" + b"K" * 79 + b"#\n")
+        allI = put("allI.fq", b"@a\n" + b"ACGT" * 20 + b"\n+\n" + b"I" * 80 + b"\n")
+        cases = [(["-1", r1, "-2", cut], "uneven"), (["-u", q42, "--ascii", "33"], "q42"), (["-u", allI], "offset")]
+        for args, tag in cases:
+            ref = _run(refcli.REF_BIN, args, tmp, "ref_" + tag)
+            gpu = _run(CLI, args, tmp, "gpu_" + tag)
+            assert ref.returncode != 0, (tag, "reference unexpectedly succeeded")
+            assert gpu.returncode != 0, (tag, gpu.stderr.decode()[-300:])
+        assert b"Unknown quality format!" in _run(CLI, ["-u", allI], tmp, "gpu_offset2").stderr
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
