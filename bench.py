@@ -360,6 +360,13 @@ def main():
         # algorithmic bytes of each segment: framing reads B_in, trim reads the seq+qual lines,
         # emit reads B_in and writes B_out; the headline figure charges the whole B_in + B_out to the dominant kernel
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+        traffic = None
+        try:        # measured DRAM bytes of the dominant kernel (ncu --set full capture, profiles/r1_traffic.json), scaled to this batch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            key = {"frame": "k_frame_lines", "trim": "k_trim", "emit": "k_emit"}[dom]
+            traffic = tj[key]["dram_bytes_per_input_byte"] * (n1 + n2)
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -372,7 +379,7 @@ def main():
                        "stats_allreduce_ms": allreduce_ms,
                        "whole_job_hbm_frac": (alg_bytes / (total_ms / args.steps / 1e3) / 1e9) / peak},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": {"frame": "k_count_lines+k_scatter_lines+k_build_records", "trim": "k_trim",
+                         "traffic": traffic, "kernel": {"frame": "k_count_lines+k_scatter_lines+k_build_records", "trim": "k_trim",
                                                      "emit": "k_route+k_scan_tiles+k_emit"}[dom],
                          "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "segments_ms": {k: v / args.steps for k, v in seg.items()}},

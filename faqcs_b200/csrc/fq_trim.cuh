@@ -466,8 +466,10 @@ __device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *sp, c
                 sum_q += q[k];
                 packed += e & 0x1ffffffu;
                 bad_q |= qv > FQ_MAX_QUALITY_SCORE;
+#ifndef FQ_EXP_NOATOM
                 if (qv <= FQ_MAX_QUALITY_SCORE) atomicAdd(&H.preq()[qv * R + p], 1u);
                 if (code < 5) atomicAdd(&H.preb()[code * R + p], 1u);
+#endif
             }
         }
     }
@@ -875,6 +877,9 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
             }
         }
 
+#ifdef FQ_EXP_PHASE1_ONLY
+        continue;
+#endif
         // ---- phase 2a: one lane per read: PRE scalar statistics and the window
         const uint8_t *sp_mine = raw_mine + me.rc.seq;
         const signed char *qp_mine = reinterpret_cast<const signed char *>(raw_mine + me.rc.qual);
