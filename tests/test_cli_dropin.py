@@ -122,3 +122,32 @@ def test_error_exits_match():
         assert b"Unknown quality format!" in _run(CLI, ["-u", allI], tmp, "gpu_offset2").stderr
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def test_phix_filter_with_thread_emulation():
+    """--phiX adds two 5386-nt targets; full SIMD groups and tail groups use different thresholds,
+    so this only matches because the -t dependent grouping is reproduced."""
+    rng = np.random.default_rng(44)
+    phix = open(os.path.join(ROOT, "faqcs_b200", "host", "phix174.inc")).read()
+    phix = "".join(l.strip().strip('"') for l in phix.splitlines() if l.startswith('"'))
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    recs = []
+    for i in range(1203):
+        L = int(rng.integers(60, 151))
+        kind = i % 4
+        if kind == 0:                                   # phiX read, forward strand, a few substitutions
+            p0 = int(rng.integers(0, len(phix) - L))
+            s = list(phix[p0:p0 + L])
+            for k in rng.integers(0, L, size=int(rng.integers(0, 6))):
+                s[k] = "ACGT"[int(rng.integers(0, 4))]
+            s = "".join(s)
+        elif kind == 1:                                 # reverse complement strand
+            p0 = int(rng.integers(0, len(phix) - L))
+            s = "".join(comp[c] for c in reversed(phix[p0:p0 + L]))
+        else:
+            s = "".join(rng.choice(list("ACGT"), size=L))
+        q = "".join(chr(33 + int(x)) for x in np.clip(rng.normal(32, 6, size=L), 2, 41).astype(int))
+        recs.append((f"@px{i}", s, q))
+    data = synth.fastq_bytes(recs)
+    for t in (1, 3):
+        assert_same_files(run_both({"-u": ("u.fq", data)}, ["--phiX", "--discard", "--min_L", "30"], threads=t))
