@@ -143,10 +143,11 @@ extern __shared__ uint32_t g_smem[];
 struct SmemHist {
     uint32_t rows, key;
     // [42][rows] pre / removed quality, [5][rows] pre / removed base, [rows] g2n, [rows+1] x2 length,
-    // [4][42] avg-Q hists, [32] filter counters, [256] LUT, [12] composition bin 0, [2][7][key+1] composition by count
+    // [4][42] avg-Q hists, [32] filter counters, [256] LUT, [256] x2 phase-1 LUTs (uint2), [rows] trash row,
+    // [12] composition bin 0, [2][7][key+1] composition by count
     __host__ __device__ static size_t words(uint32_t rows, uint32_t key)
     {
-        return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + 4 * kQualCols + 32 + 256 + 12 +
+        return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + 4 * kQualCols + 32 + 256 + 1024 + rows + 12 +
                (key == 0xffffffffu ? 0 : 14 * ((size_t)key + 1));
     }
     __device__ __forceinline__ uint32_t *preq() const { return g_smem; }
@@ -159,7 +160,14 @@ struct SmemHist {
     __device__ __forceinline__ uint32_t *qh() const { return postlen() + rows + 1; }
     __device__ __forceinline__ uint32_t *filt() const { return qh() + 4 * kQualCols; }
     __device__ __forceinline__ uint32_t *lut() const { return filt() + 32; }
-    __device__ __forceinline__ uint32_t *zero() const { return lut() + 256; }
+    // phase-1 tables: per byte value {byte offset of the histogram row to bump, payload}
+    //   base:    row = pre_b[class] (trash row for non-ACGTN), payload = 1 << (5 * class) (packed per-lane counters)
+    //   quality: row = pre_q[max(0, (signed char)ch - in_off)] (trash row above 41), payload = (int)(signed char)ch
+    __device__ __forceinline__ uint2 *lut_base() const { return reinterpret_cast<uint2 *>(lut() + 256); }
+    __device__ __forceinline__ uint2 *lut_qual() const { return lut_base() + 256; }
+    __device__ __forceinline__ uint32_t *trash() const { return lut() + 256 + 1024; }
+    __device__ __forceinline__ uint32_t trash_bytes() const { return (uint32_t)((2 * kQualCols + 2 * kBaseCols + 1) * rows + 2 * (rows + 1) + 4 * kQualCols + 32 + 256 + 1024) * 4u; }
+    __device__ __forceinline__ uint32_t *zero() const { return trash() + rows; }
     __device__ __forceinline__ uint32_t *compk() const { return zero() + 12; }
 };
 
@@ -391,15 +399,15 @@ __device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *sp, c
 {
     const DevOpts &o = kc.o;
     const SmemHist &H = kc.H;
-    const uint32_t lane = kc.lane, R = H.rows;
-    uint32_t c[K];
-    int q[K];
+    const uint32_t lane = kc.lane;
+    const uint8_t *spl = sp + lane, *qpl = reinterpret_cast<const uint8_t *>(qp) + lane;
+    uint32_t c[K], q[K];            // raw bytes
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t p = k * 32 + lane;
         c[k] = 0;
-        q[k] = o.in_off;
-        if (p < len) { c[k] = sp[p]; q[k] = (int)qp[p]; }
+        q[k] = (uint32_t)o.in_off;
+        if (p < len) { c[k] = __ldg(spl + k * 32); q[k] = __ldg(qpl + k * 32); }
     }
     uint32_t nm[K], any_n = 0;
 #pragma unroll
@@ -441,7 +449,7 @@ __device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *sp, c
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const uint32_t p = k * 32 + lane;
-                if (p < lead || p >= trail) q[k] = o.in_off;
+                if (p < lead || p >= trail) q[k] = (uint32_t)o.in_off;
             }
         }
         if (n_count >= o.max_poly_n) {                           // candidate for the N filter: longest run of the whole read
@@ -455,20 +463,21 @@ __device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *sp, c
     int sum_q = 0;
     uint32_t packed = 0;
     bool bad_q = false;
+    const uint2 *const lb = H.lut_base(), *const lq = H.lut_qual();
+    char *const col = reinterpret_cast<char *>(g_smem) + 4 * lane;      // this lane's position column; chunk k adds 128 bytes
+    const uint32_t trash = H.trash_bytes();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if ((uint32_t)(k * 32) < len) {
             const uint32_t p = k * 32 + lane;
             if (p < len) {
-                const uint32_t e = H.lut()[c[k]];
-                const uint32_t code = e >> 28;
-                const int qv = max(0, q[k] - o.in_off);
-                sum_q += q[k];
-                packed += e & 0x1ffffffu;
-                bad_q |= qv > FQ_MAX_QUALITY_SCORE;
+                const uint2 eb = lb[c[k]], eq = lq[q[k]];
+                sum_q += (int)eq.y;
+                packed += eb.y;
+                bad_q |= eq.x == trash;
 #ifndef FQ_EXP_NOATOM
-                if (qv <= FQ_MAX_QUALITY_SCORE) atomicAdd(&H.preq()[qv * R + p], 1u);
-                if (code < 5) atomicAdd(&H.preb()[code * R + p], 1u);
+                atomicAdd(reinterpret_cast<uint32_t *>(col + eq.x + k * 128), 1u);
+                atomicAdd(reinterpret_cast<uint32_t *>(col + eb.x + k * 128), 1u);
 #endif
             }
         }
@@ -823,7 +832,13 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
     const size_t n_words = SmemHist::words(a.smem_rows, a.comp_key_len);
     for (size_t i = threadIdx.x; i < n_words; i += blockDim.x) g_smem[i] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) H.lut()[i] = lut_entry(i);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        H.lut()[i] = lut_entry(i);
+        const int code = base_code_slow(i);
+        H.lut_base()[i] = code < 5 ? make_uint2((uint32_t)((2 * kQualCols + code) * a.smem_rows) * 4u, 1u << (5 * code)) : make_uint2(H.trash_bytes(), 0u);
+        const int ch = (int)(signed char)i, qv = max(0, ch - o.in_off);
+        H.lut_qual()[i] = make_uint2(qv <= FQ_MAX_QUALITY_SCORE ? (uint32_t)(qv * a.smem_rows) * 4u : H.trash_bytes(), (uint32_t)ch);
+    }
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
