@@ -140,14 +140,15 @@ __device__ __forceinline__ uint32_t bwa_plus_trim(const QualAt &qa, uint32_t lo,
 // Shared-memory block of one CTA, addressed by word offsets from the dynamic shared base
 // (offsets are functions of `rows` alone, so the layout costs two registers, not twelve pointers).
 extern __shared__ uint32_t g_smem[];
+constexpr uint32_t kTrashWords = 320;      // phase 1 handles reads of up to 320 bases; every position needs a dump slot
 struct SmemHist {
     uint32_t rows, key;
     // [42][rows] pre / removed quality, [5][rows] pre / removed base, [rows] g2n, [rows+1] x2 length,
-    // [4][42] avg-Q hists, [32] filter counters, [256] LUT, [256] x2 phase-1 LUTs (uint2), [rows] trash row,
+    // [4][42] avg-Q hists, [32] filter counters, [256] LUT, [256] x2 phase-1 LUTs (uint2), [320] trash row,
     // [12] composition bin 0, [2][7][key+1] composition by count
     __host__ __device__ static size_t words(uint32_t rows, uint32_t key)
     {
-        return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + 4 * kQualCols + 32 + 256 + 1024 + rows + 12 +
+        return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + 4 * kQualCols + 32 + 256 + 1024 + kTrashWords + 12 +
                (key == 0xffffffffu ? 0 : 14 * ((size_t)key + 1));
     }
     __device__ __forceinline__ uint32_t *preq() const { return g_smem; }
@@ -167,7 +168,7 @@ struct SmemHist {
     __device__ __forceinline__ uint2 *lut_qual() const { return lut_base() + 256; }
     __device__ __forceinline__ uint32_t *trash() const { return lut() + 256 + 1024; }
     __device__ __forceinline__ uint32_t trash_bytes() const { return (uint32_t)((2 * kQualCols + 2 * kBaseCols + 1) * rows + 2 * (rows + 1) + 4 * kQualCols + 32 + 256 + 1024) * 4u; }
-    __device__ __forceinline__ uint32_t *zero() const { return trash() + rows; }
+    __device__ __forceinline__ uint32_t *zero() const { return trash() + kTrashWords; }
     __device__ __forceinline__ uint32_t *compk() const { return zero() + 12; }
 };
 
@@ -389,25 +390,39 @@ struct LaneRead {
     bool done;              // already fully processed (generic path) or out of range
 };
 
+// Predicated byte load / shared-memory increment as single predicated instructions (the compiler would branch).
+__device__ __forceinline__ uint32_t ldg_u8_if(const uint8_t *p, bool pred, uint32_t dflt)
+{
+    uint32_t v = dflt;
+    asm("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.global.nc.u8 %0, [%1]; }" : "+r"(v) : "l"(p), "r"((uint32_t)pred));
+    return v;
+}
+// `one` must be a run-time 1: with an immediate the assembler picks the warp-aggregating form, which needs a
+// convergence region (three more instructions) around every single increment.
+// (A predicated shared atomic is turned into a branch as well, so lanes past the end of the read add 0 instead.)
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t f10(uint32_t packed, int field) { return (packed >> (10 * field)) & 1023u; }
 
 // Phase 1 for the read owned by lane j: PRE matrices + per-read summaries.
 template <int K>
-__device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *sp, const signed char *qp, uint32_t len, uint32_t r,
+__device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *raw, uint32_t seq, uint32_t qual, uint32_t len, uint32_t r,
                                        int &out_sum, uint32_t &out_atc, uint32_t &out_gn, uint32_t &out_lead, uint32_t &out_trail,
                                        uint32_t &out_run, uint32_t &err, uint32_t &err_rec)
 {
     const DevOpts &o = kc.o;
     const SmemHist &H = kc.H;
     const uint32_t lane = kc.lane;
-    const uint8_t *spl = sp + lane, *qpl = reinterpret_cast<const uint8_t *>(qp) + lane;
-    uint32_t c[K], q[K];            // raw bytes
+    const uint8_t *const spl = raw + (seq + lane), *const qpl = raw + (qual + lane);
+    uint32_t c[K], q[K];            // raw bytes; lanes past the end hold a non-base and the zero-quality character
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const uint32_t p = k * 32 + lane;
-        c[k] = 0;
-        q[k] = (uint32_t)o.in_off;
-        if (p < len) { c[k] = __ldg(spl + k * 32); q[k] = __ldg(qpl + k * 32); }
+        const bool in = (uint32_t)(k * 32) + lane < len;
+        c[k] = ldg_u8_if(spl + k * 32, in, 0u);
+        q[k] = ldg_u8_if(qpl + k * 32, in, (uint32_t)o.in_off);
     }
     uint32_t nm[K], any_n = 0;
 #pragma unroll
@@ -460,30 +475,34 @@ __device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *sp, c
             run = rt.best;
         }
     }
+    // Branch-free: every lane looks both bytes up; a lane past the end holds (non-base, zero quality), whose payloads
+    // add nothing to the class counters and `in_off` to the quality sum (taken out again below); only the two
+    // histogram bumps are predicated.
     int sum_q = 0;
-    uint32_t packed = 0;
-    bool bad_q = false;
+    uint32_t packed = 0, max_row = 0;
     const uint2 *const lb = H.lut_base(), *const lq = H.lut_qual();
-    char *const col = reinterpret_cast<char *>(g_smem) + 4 * lane;      // this lane's position column; chunk k adds 128 bytes
-    const uint32_t trash = H.trash_bytes();
+    const uint32_t col = (uint32_t)__cvta_generic_to_shared(g_smem) + 4 * lane;      // this lane's position column; chunk k adds 128 bytes
+    uint32_t n_chunks = 0;
+    const uint32_t one = min(kc.a.n_mates, 1u);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        if ((uint32_t)(k * 32) < len) {
-            const uint32_t p = k * 32 + lane;
-            if (p < len) {
-                const uint2 eb = lb[c[k]], eq = lq[q[k]];
-                sum_q += (int)eq.y;
-                packed += eb.y;
-                bad_q |= eq.x == trash;
+        if (K <= 5 || (uint32_t)(k * 32) < len) {
+            const uint2 eb = lb[c[k]], eq = lq[q[k]];
+            sum_q += (int)eq.y;
+            packed += eb.y;
+            max_row = max(max_row, eq.x);
+            ++n_chunks;
 #ifndef FQ_EXP_NOATOM
-                atomicAdd(reinterpret_cast<uint32_t *>(col + eq.x + k * 128), 1u);
-                atomicAdd(reinterpret_cast<uint32_t *>(col + eb.x + k * 128), 1u);
+            const bool in = (uint32_t)(k * 32) + lane < len;
+            const uint32_t inc = in ? one : 0u;
+            red_shared_add(col + eq.x + k * 128, inc);
+            red_shared_add(col + eb.x + k * 128, inc);
 #endif
-            }
         }
     }
-    if (__any_sync(0xffffffffu, bad_q)) { err |= kErrQualGt41; err_rec = min(err_rec, r); }
-    out_sum = warp_sum_i(sum_q);
+    // the trash row lies above every quality row: reaching it means a score above 41 (fastq.h:31-33)
+    if (__any_sync(0xffffffffu, max_row == H.trash_bytes())) { err |= kErrQualGt41; err_rec = min(err_rec, r); }
+    out_sum = warp_sum_i(sum_q) - o.in_off * (int)(n_chunks * 32 - len);
     out_atc = warp_sum(unpack5(packed, 0) | (unpack5(packed, 1) << 10) | (unpack5(packed, 2) << 20));
     out_gn = warp_sum(unpack5(packed, 3) | (unpack5(packed, 4) << 10));
     out_lead = lead;
@@ -874,13 +893,12 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
             const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
             const uint32_t rj = base + j - mj * a.n_rec;
             const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
-            const uint8_t *sp = rawj + seq;
-            const signed char *qp = reinterpret_cast<const signed char *>(rawj + qual);
             int s_sum = 0;
             uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
             bool generic = false;
-            if (len <= 160 && len <= R) phase1<5>(kc, sp, qp, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
-            else if (len <= 320 && len <= R) phase1<10>(kc, sp, qp, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
+            if (len <= 128 && len <= R) phase1<4>(kc, rawj, seq, qual, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
+            else if (len <= 160 && len <= R) phase1<5>(kc, rawj, seq, qual, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
+            else if (len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
             else {
                 const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
                 process_generic(kc, mj, rj, rcj);
