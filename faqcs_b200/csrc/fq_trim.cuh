@@ -390,12 +390,18 @@ struct LaneRead {
     bool done;              // already fully processed (generic path) or out of range
 };
 
-// Predicated byte load / shared-memory increment as single predicated instructions (the compiler would branch).
-__device__ __forceinline__ uint32_t ldg_u8_if(const uint8_t *p, bool pred, uint32_t dflt)
+// One chunk of phase-1 input for this lane: base and quality byte of position p (if p < len, else the given
+// defaults) and the histogram increment (one / 0), as one compare, two predicated loads and a select.
+__device__ __forceinline__ void load_chunk(const uint8_t *sp, const uint8_t *qp, uint32_t p, uint32_t len, uint32_t one, uint32_t &c,
+                                           uint32_t &q, uint32_t &inc)
 {
-    uint32_t v = dflt;
-    asm("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.global.nc.u8 %0, [%1]; }" : "+r"(v) : "l"(p), "r"((uint32_t)pred));
-    return v;
+    asm("{ .reg .pred p;\n\t"
+        "setp.lt.u32 p, %3, %4;\n\t"
+        "@p ld.global.nc.u8 %0, [%5];\n\t"
+        "@p ld.global.nc.u8 %1, [%6];\n\t"
+        "selp.u32 %2, %7, 0, p; }"
+        : "+r"(c), "+r"(q), "=r"(inc)
+        : "r"(p), "r"(len), "l"(sp), "l"(qp), "r"(one));
 }
 // `one` must be a run-time 1: with an immediate the assembler picks the warp-aggregating form, which needs a
 // convergence region (three more instructions) around every single increment.
@@ -409,26 +415,47 @@ __device__ __forceinline__ uint32_t f10(uint32_t packed, int field) { return (pa
 
 // Phase 1 for the read owned by lane j: PRE matrices + per-read summaries.
 template <int K>
-__device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *raw, uint32_t seq, uint32_t qual, uint32_t len, uint32_t r,
+__device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *raw, uint32_t seq, uint32_t qual, uint32_t len,
                                        int &out_sum, uint32_t &out_atc, uint32_t &out_gn, uint32_t &out_lead, uint32_t &out_trail,
-                                       uint32_t &out_run, uint32_t &err, uint32_t &err_rec)
+                                       uint32_t &out_run, uint32_t &max_row)
 {
     const DevOpts &o = kc.o;
     const SmemHist &H = kc.H;
     const uint32_t lane = kc.lane;
     const uint8_t *const spl = raw + (seq + lane), *const qpl = raw + (qual + lane);
-    uint32_t c[K], q[K];            // raw bytes; lanes past the end hold a non-base and the zero-quality character
+    const uint32_t one = min(kc.a.n_mates, 1u);
+    uint32_t c[K], q[K], inc[K];    // raw bytes; lanes past the end hold a non-base and the zero-quality character
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const bool in = (uint32_t)(k * 32) + lane < len;
-        c[k] = ldg_u8_if(spl + k * 32, in, 0u);
-        q[k] = ldg_u8_if(qpl + k * 32, in, (uint32_t)o.in_off);
+        c[k] = 0;
+        q[k] = (uint32_t)o.in_off;
+        load_chunk(spl + k * 32, qpl + k * 32, (uint32_t)(k * 32) + lane, len, one, c[k], q[k], inc[k]);
     }
-    uint32_t nm[K], any_n = 0;
+    // Branch-free from here: every lane looks both bytes up; a lane past the end holds (non-base, zero quality),
+    // whose payloads add nothing to the class counters and `in_off` to the quality sum (taken out again below),
+    // and its histogram increments are 0.
+    const uint2 *const lb = H.lut_base(), *const lq = H.lut_qual();
+    const uint32_t col = (uint32_t)__cvta_generic_to_shared(g_smem) + 4 * lane;      // this lane's position column; chunk k adds 128 bytes
+    uint32_t packed = 0, n_chunks = 0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { nm[k] = __ballot_sync(0xffffffffu, c[k] == 'N'); any_n |= nm[k]; }
+    for (int k = 0; k < K; ++k) {
+        if (K <= 5 || (uint32_t)(k * 32) < len) {
+            const uint2 eb = lb[c[k]];
+            packed += eb.y;
+            ++n_chunks;
+#ifndef FQ_EXP_NOATOM
+            red_shared_add(col + eb.x + k * 128, inc[k]);
+#endif
+        }
+    }
+    out_atc = warp_sum(unpack5(packed, 0) | (unpack5(packed, 1) << 10) | (unpack5(packed, 2) << 20));
+    out_gn = warp_sum(unpack5(packed, 3) | (unpack5(packed, 4) << 10));
+    const bool any_n = (out_gn >> 10) != 0;          // some 'N' or 'n' in the read
     uint32_t lead = 0, trail = len, run = 0;
     if (any_n) {
+        uint32_t nm[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) nm[k] = __ballot_sync(0xffffffffu, c[k] == 'N');
         bool last_n = false;
         uint32_t n_count = 0;
 #pragma unroll
@@ -475,36 +502,19 @@ __device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *raw, 
             run = rt.best;
         }
     }
-    // Branch-free: every lane looks both bytes up; a lane past the end holds (non-base, zero quality), whose payloads
-    // add nothing to the class counters and `in_off` to the quality sum (taken out again below); only the two
-    // histogram bumps are predicated.
     int sum_q = 0;
-    uint32_t packed = 0, max_row = 0;
-    const uint2 *const lb = H.lut_base(), *const lq = H.lut_qual();
-    const uint32_t col = (uint32_t)__cvta_generic_to_shared(g_smem) + 4 * lane;      // this lane's position column; chunk k adds 128 bytes
-    uint32_t n_chunks = 0;
-    const uint32_t one = min(kc.a.n_mates, 1u);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if (K <= 5 || (uint32_t)(k * 32) < len) {
-            const uint2 eb = lb[c[k]], eq = lq[q[k]];
+            const uint2 eq = lq[q[k]];
             sum_q += (int)eq.y;
-            packed += eb.y;
-            max_row = max(max_row, eq.x);
-            ++n_chunks;
+            max_row = max(max_row, eq.x);       // the trash row lies above every quality row: reaching it means a score above 41
 #ifndef FQ_EXP_NOATOM
-            const bool in = (uint32_t)(k * 32) + lane < len;
-            const uint32_t inc = in ? one : 0u;
-            red_shared_add(col + eq.x + k * 128, inc);
-            red_shared_add(col + eb.x + k * 128, inc);
+            red_shared_add(col + eq.x + k * 128, inc[k]);
 #endif
         }
     }
-    // the trash row lies above every quality row: reaching it means a score above 41 (fastq.h:31-33)
-    if (__any_sync(0xffffffffu, max_row == H.trash_bytes())) { err |= kErrQualGt41; err_rec = min(err_rec, r); }
     out_sum = warp_sum_i(sum_q) - o.in_off * (int)(n_chunks * 32 - len);
-    out_atc = warp_sum(unpack5(packed, 0) | (unpack5(packed, 1) << 10) | (unpack5(packed, 2) << 20));
-    out_gn = warp_sum(unpack5(packed, 3) | (unpack5(packed, 4) << 10));
     out_lead = lead;
     out_trail = trail;
     out_run = run;
@@ -886,6 +896,7 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
 
         // ---- phase 1: cooperative per-base pass, read by read
         const uint32_t n_here = min(32u, total - base);
+        uint32_t max_row = 0;           // highest quality row any base of this group was counted in
         for (uint32_t j = 0; j < n_here; ++j) {
             const uint32_t len = __shfl_sync(0xffffffffu, me.rc.len, j);
             const uint32_t seq = __shfl_sync(0xffffffffu, me.rc.seq, j);
@@ -896,9 +907,9 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
             int s_sum = 0;
             uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
             bool generic = false;
-            if (len <= 128 && len <= R) phase1<4>(kc, rawj, seq, qual, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
-            else if (len <= 160 && len <= R) phase1<5>(kc, rawj, seq, qual, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
-            else if (len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, rj, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, err, err_rec);
+            if (len <= 128 && len <= R) phase1<4>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            else if (len <= 160 && len <= R) phase1<5>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            else if (len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
             else {
                 const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
                 process_generic(kc, mj, rj, rcj);
@@ -910,6 +921,24 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
             }
         }
 
+        if (__any_sync(0xffffffffu, max_row == H.trash_bytes())) {
+            // a quality score above 41 (fastq.h:31-33): find the first offending read of the group
+            for (uint32_t j = 0; j < n_here; ++j) {
+                const uint32_t lenj = __shfl_sync(0xffffffffu, me.rc.len, j), qual = __shfl_sync(0xffffffffu, me.rc.qual, j);
+                const uint32_t lead = __shfl_sync(0xffffffffu, me.lead, j), trail = __shfl_sync(0xffffffffu, me.trail, j);
+                const bool skip = __shfl_sync(0xffffffffu, (int)me.done, j) != 0;      // generic path reports its own errors
+                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
+                const signed char *qp = reinterpret_cast<const signed char *>((mj ? a.raw[1] : a.raw[0]) + qual);
+                bool bad = false;
+                for (uint32_t p = lane; p < lenj && !skip; p += 32)
+                    bad |= p >= lead && p < trail && (int)qp[p] - o.in_off > FQ_MAX_QUALITY_SCORE;
+                if (__any_sync(0xffffffffu, bad)) {
+                    err |= kErrQualGt41;
+                    err_rec = min(err_rec, base + j - mj * a.n_rec);
+                    break;
+                }
+            }
+        }
 #ifdef FQ_EXP_PHASE1_ONLY
         continue;
 #endif
