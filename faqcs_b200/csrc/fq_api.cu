@@ -463,6 +463,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     ea.filter_off = ctx->L.filter;
     for (int m = 0; m < n_mates; ++m) {
         ea.raw[m] = m ? d_r2 : d_r1;
+        ea.raw_bytes[m] = m ? n2 : n1;
         ea.rec[m] = ctx->d_rec[m].as<Rec>();
         ea.res[m] = ctx->d_res[m].as<uint2>();
         ea.canon[m] = ctx->d_canon[m].as<uint8_t>();
@@ -479,7 +480,8 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     k_scan_tiles<<<1, 128, 0, ctx->stream>>>(ea.tile_sum, ea.n_tiles, info);
     ctx->launches += 2;
     if (!o.qc_only) {
-        k_emit<<<ea.n_tiles, kTile, 0, ctx->stream>>>(ea, o);
+        CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem));
+        k_emit<<<ea.n_tiles, kTile, kEmitSmem, ctx->stream>>>(ea, o);
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));

@@ -17,6 +17,7 @@ constexpr uint32_t kTile = 256;     // records per route/emit tile
 
 struct EmitArgs {
     const uint8_t *raw[2];
+    uint64_t raw_bytes[2];
     const Rec *rec[2];
     const uint2 *res[2];
     const uint8_t *canon[2];     // 1 = LF line ends + bare '+' line (raw bytes == write_read output)
@@ -127,14 +128,15 @@ __global__ void __launch_bounds__(128) k_scan_tiles(uint32_t *tile_sum, uint32_t
 
 // Warp-cooperative copy of n bytes between arbitrarily aligned addresses.  The body is written
 // as 16-byte aligned stores; each store gathers its bytes from five aligned 32-bit source words
-// with funnel shifts (the source is L1/L2 resident raw input, neighbouring lanes share words).
+// with funnel shifts.  The source is a generic pointer: normally the warp's staged slab in shared
+// memory (k_emit), global memory when a slab does not fit.
 __device__ __forceinline__ uint4 gather16(const uint8_t *sc)
 {
     // 16 bytes starting at the arbitrarily aligned address sc, from five aligned 32-bit words
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sc) & 3u) * 8u;
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sc) & ~(uintptr_t)3);
-    const uint32_t w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
-    const uint32_t w4 = sh ? __ldg(sw + 4) : 0u;          // only bytes below src + n are ever consumed from it
+    const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2], w3 = sw[3];
+    const uint32_t w4 = sh ? sw[4] : 0u;                  // only bytes below src + n are ever consumed from it
     uint4 v;
     v.x = __funnelshift_r(w0, w1, sh);
     v.y = __funnelshift_r(w1, w2, sh);
@@ -297,8 +299,26 @@ __device__ __forceinline__ void copy_runs(uint32_t mask, uint8_t *out, const uin
     }
 }
 
+// ---- k_emit -------------------------------------------------------------------------------------
+// One warp owns 32 consecutive records.  Their raw bytes are one contiguous slab of the input
+// (~10 KiB for 150-base reads), which the warp first copies asynchronously (cp.async, 16 bytes per
+// request, no register staging) into its private shared-memory buffer.  Everything after that reads
+// shared memory: the chains "descriptor -> header bytes -> bases -> qualities" that made the copy
+// latency-bound on global memory now cost tens of cycles per link, and the only global traffic left
+// is the coalesced slab load and the 16-byte stores.
+constexpr uint32_t kEmitSlab = 12 * 1024;               // staging bytes per warp
+constexpr uint32_t kEmitSmem = (kTile / 32) * kEmitSlab;
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+extern __shared__ __align__(16) uint8_t g_emit_smem[];
+
 #ifndef FQ_EMIT_MIN_CTAS
-#define FQ_EMIT_MIN_CTAS 4
+#define FQ_EMIT_MIN_CTAS 2
 #endif
 __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs a, const DevOpts o)
 {
@@ -331,21 +351,48 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
     if (o.qc_only) return;
     const LaneRec L = lane_record(a, o, r);
     const bool in = r < a.n_rec;
+    const uint32_t in_mask = __ballot_sync(0xffffffffu, in);
+    if (in_mask == 0) return;
+    const int last_lane = 31 - __clz(in_mask);
+    const bool both = o.paired && in && L.valid[0] && L.valid[1];
+    uint8_t *const slab = g_emit_smem + (size_t)wid * kEmitSlab;
+    const uint32_t slab_s = (uint32_t)__cvta_generic_to_shared(slab);
+    const int n_mates = o.paired ? 2 : 1;
 
-    if (o.paired) {
-        const bool both = in && L.valid[0] && L.valid[1];
-        // block copies: runs of untouched pairs, mate by mate
-        copy_runs(__ballot_sync(0xffffffffu, both && L.plain[0]), a.out[0], a.raw[0], L.rc[0].hdr, L.tsize[0], off[0], lane);
-        copy_runs(__ballot_sync(0xffffffffu, both && L.plain[1]), a.out[1], a.raw[1], L.rc[1].hdr, L.tsize[1], off[1], lane);
-        // everything else, record by record
-        const bool single0 = in && ((both && !L.plain[0]) || (!both && L.valid[0]));
-        const bool single1 = in && ((both && !L.plain[1]) || (!both && L.valid[1]));
-        const bool disc = in && o.discard && !both && (!L.valid[0] || !L.valid[1]);
-        uint32_t todo = __ballot_sync(0xffffffffu, single0 || single1 || disc);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (m >= n_mates) break;
+        // ---- stage this warp's slab of mate m
+        const uint32_t lo = __shfl_sync(0xffffffffu, L.rc[m].hdr, 0) & ~15u;
+        const uint64_t end = min((uint64_t)__shfl_sync(0xffffffffu, L.rc[m].qual + L.rc[m].len, last_lane) + 1, a.raw_bytes[m]);
+        const uint32_t hi = (uint32_t)((end + 15) & ~(uint64_t)15);
+        const uint8_t *src = a.raw[m];                         // src[offset] is the byte at raw offset `offset`
+        if (hi - lo <= kEmitSlab) {
+            __syncwarp();                                      // everyone is done reading the previous slab
+            for (uint32_t c = lo + 16 * lane; c < hi; c += 16 * 32) cp_async16(slab_s + (c - lo), a.raw[m] + c);
+            cp_async_wait_all();
+            __syncwarp();
+            src = slab - lo;
+        }
+        // ---- runs of untouched records of a surviving pair (or, unpaired input, of surviving reads): block copies
+        const int s_main = o.paired ? m : 2;
+        const bool main = o.paired ? both : (in && L.valid[0]);
+        copy_runs(__ballot_sync(0xffffffffu, main && L.plain[m]), a.out[s_main], src, L.rc[m].hdr, L.tsize[m], off[s_main], lane);
+        // ---- everything else of this mate, four records at a time (one per 8-lane group)
+        const bool trimmed = in && L.valid[m] && !(main && L.plain[m]);                  // needs write_trimmed
+        const bool disc = in && o.discard && !L.valid[m] && !(o.paired && both);          // raw copy to the discard stream
+        // destination of this mate's record
+        uint32_t dst = 0;
+        int s_dst = 0;
+        if (trimmed) { s_dst = main ? s_main : 2; dst = off[s_dst]; }
+        else if (disc) {
+            s_dst = 3;
+            dst = off[3];
+            if (m == 1 && !L.valid[0]) dst += header_len(a.raw[0], L.rc[0], L.canon[0]) + 2 * L.rc[0].len + 5;
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, trimmed || disc);
         const uint32_t sub = lane & 7, grp = lane >> 3;
         while (todo) {
-            // four records at a time, one per 8-lane group: each record is a short chain of dependent
-            // load -> store round trips, so concurrency across records is what hides the latency
             int j = -1;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -354,56 +401,20 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
                 if ((int)grp == g) j = b;
             }
             const int js = j < 0 ? 0 : j;
-            Rec rc[2];
-            uint2 e[2];
-            bool cn[2], v[2], pl[2];
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                rc[m].hdr = __shfl_sync(0xffffffffu, L.rc[m].hdr, js);
-                rc[m].seq = __shfl_sync(0xffffffffu, L.rc[m].seq, js);
-                rc[m].qual = __shfl_sync(0xffffffffu, L.rc[m].qual, js);
-                rc[m].len = __shfl_sync(0xffffffffu, L.rc[m].len, js);
-                e[m].x = __shfl_sync(0xffffffffu, L.res[m].x, js);
-                e[m].y = __shfl_sync(0xffffffffu, L.res[m].y, js);
-                cn[m] = __shfl_sync(0xffffffffu, (int)L.canon[m], js) != 0;
-                v[m] = __shfl_sync(0xffffffffu, (int)L.valid[m], js) != 0;
-                pl[m] = __shfl_sync(0xffffffffu, (int)L.plain[m], js) != 0;
-            }
-            uint32_t o4[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) o4[s] = __shfl_sync(0xffffffffu, off[s], js);
-            if (j < 0) continue;
-            if (v[0] && v[1]) {
-                if (!pl[0]) write_trimmed<8>(a.out[0] + o4[0], a.raw[0], rc[0], cn[0], e[0].x, e[0].y & kResLenMask, e[0].y >> kResLenBits, o, sub);
-                if (!pl[1]) write_trimmed<8>(a.out[1] + o4[1], a.raw[1], rc[1], cn[1], e[1].x, e[1].y & kResLenMask, e[1].y >> kResLenBits, o, sub);
-            } else {
-                if (v[0]) write_trimmed<8>(a.out[2] + o4[2], a.raw[0], rc[0], cn[0], e[0].x, e[0].y & kResLenMask, e[0].y >> kResLenBits, o, sub);
-                else if (v[1]) write_trimmed<8>(a.out[2] + o4[2], a.raw[1], rc[1], cn[1], e[1].x, e[1].y & kResLenMask, e[1].y >> kResLenBits, o, sub);
-                if (o.discard) {
-                    uint32_t d = o4[3];
-                    if (!v[0]) { write_raw<8>(a.out[3] + d, a.raw[0], rc[0], cn[0], sub); d += header_len(a.raw[0], rc[0], cn[0]) + 2 * rc[0].len + 5; }
-                    if (!v[1]) write_raw<8>(a.out[3] + d, a.raw[1], rc[1], cn[1], sub);
-                }
-            }
-        }
-    } else {
-        copy_runs(__ballot_sync(0xffffffffu, in && L.plain[0]), a.out[2], a.raw[0], L.rc[0].hdr, L.tsize[0], off[2], lane);
-        const bool single = in && L.valid[0] && !L.plain[0];
-        const bool disc = in && o.discard && !L.valid[0];
-        uint32_t todo = __ballot_sync(0xffffffffu, single || disc);
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
             Rec rc;
-            rc.hdr = __shfl_sync(0xffffffffu, L.rc[0].hdr, j);
-            rc.seq = __shfl_sync(0xffffffffu, L.rc[0].seq, j);
-            rc.qual = __shfl_sync(0xffffffffu, L.rc[0].qual, j);
-            rc.len = __shfl_sync(0xffffffffu, L.rc[0].len, j);
-            const uint32_t ex = __shfl_sync(0xffffffffu, L.res[0].x, j), ey = __shfl_sync(0xffffffffu, L.res[0].y, j);
-            const bool cn = __shfl_sync(0xffffffffu, (int)L.canon[0], j) != 0, v = __shfl_sync(0xffffffffu, (int)L.valid[0], j) != 0;
-            const uint32_t o2 = __shfl_sync(0xffffffffu, off[2], j), o3 = __shfl_sync(0xffffffffu, off[3], j);
-            if (v) write_trimmed(a.out[2] + o2, a.raw[0], rc, cn, ex, ey & kResLenMask, ey >> kResLenBits, o, lane);
-            else write_raw(a.out[3] + o3, a.raw[0], rc, cn, lane);
+            rc.hdr = __shfl_sync(0xffffffffu, L.rc[m].hdr, js);
+            rc.seq = __shfl_sync(0xffffffffu, L.rc[m].seq, js);
+            rc.qual = __shfl_sync(0xffffffffu, L.rc[m].qual, js);
+            rc.len = __shfl_sync(0xffffffffu, L.rc[m].len, js);
+            const uint32_t ex = __shfl_sync(0xffffffffu, L.res[m].x, js), ey = __shfl_sync(0xffffffffu, L.res[m].y, js);
+            const bool cn = __shfl_sync(0xffffffffu, (int)L.canon[m], js) != 0;
+            const bool tr = __shfl_sync(0xffffffffu, (int)trimmed, js) != 0;
+            const uint32_t d = __shfl_sync(0xffffffffu, dst, js);
+            const int sd = __shfl_sync(0xffffffffu, s_dst, js);
+            if (j < 0) continue;
+            uint8_t *const outp = (sd == 0 ? a.out[0] : sd == 1 ? a.out[1] : sd == 2 ? a.out[2] : a.out[3]) + d;
+            if (tr) write_trimmed<8>(outp, src, rc, cn, ex, ey & kResLenMask, ey >> kResLenBits, o, sub);
+            else write_raw<8>(outp, src, rc, cn, sub);
         }
     }
 }
