@@ -306,14 +306,31 @@ __device__ __forceinline__ void copy_runs(uint32_t mask, uint8_t *out, const uin
 // shared memory: the chains "descriptor -> header bytes -> bases -> qualities" that made the copy
 // latency-bound on global memory now cost tens of cycles per link, and the only global traffic left
 // is the coalesced slab load and the 16-byte stores.
-constexpr uint32_t kEmitSlab = 12 * 1024;               // staging bytes per warp
+#ifndef FQ_EMIT_PARTS
+#define FQ_EMIT_PARTS 1
+#endif
+#ifndef FQ_EMIT_SLAB
+#define FQ_EMIT_SLAB (12 * 1024)
+#endif
+constexpr uint32_t kEmitParts = FQ_EMIT_PARTS;          // a warp stages its 32 records in this many rounds
+constexpr uint32_t kEmitSlab = FQ_EMIT_SLAB;            // staging bytes per warp
 constexpr uint32_t kEmitSmem = (kTile / 32) * kEmitSlab;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group(int n)      // n is a compile-time constant after unrolling
+{
+    switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
 
 extern __shared__ __align__(16) uint8_t g_emit_smem[];
 
@@ -353,69 +370,98 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
     const bool in = r < a.n_rec;
     const uint32_t in_mask = __ballot_sync(0xffffffffu, in);
     if (in_mask == 0) return;
-    const int last_lane = 31 - __clz(in_mask);
     const bool both = o.paired && in && L.valid[0] && L.valid[1];
     uint8_t *const slab = g_emit_smem + (size_t)wid * kEmitSlab;
     const uint32_t slab_s = (uint32_t)__cvta_generic_to_shared(slab);
     const int n_mates = o.paired ? 2 : 1;
 
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        if (m >= n_mates) break;
-        // ---- stage this warp's slab of mate m
-        const uint32_t lo = __shfl_sync(0xffffffffu, L.rc[m].hdr, 0) & ~15u;
-        const uint64_t end = min((uint64_t)__shfl_sync(0xffffffffu, L.rc[m].qual + L.rc[m].len, last_lane) + 1, a.raw_bytes[m]);
-        const uint32_t hi = (uint32_t)((end + 15) & ~(uint64_t)15);
-        const uint8_t *src = a.raw[m];                         // src[offset] is the byte at raw offset `offset`
-        if (hi - lo <= kEmitSlab) {
-            __syncwarp();                                      // everyone is done reading the previous slab
-            for (uint32_t c = lo + 16 * lane; c < hi; c += 16 * 32) cp_async16(slab_s + (c - lo), a.raw[m] + c);
-            cp_async_wait_all();
-            __syncwarp();
-            src = slab - lo;
+    // Software pipeline over n_mates * P stages (mate, part): the slab of a stage is the raw bytes of 32 / P
+    // consecutive records.  P buffers rotate; while stage t is being written out, the loads of stages
+    // t+1 .. t+P-1 are in flight.  The loop is deliberately NOT unrolled (one copy of the body: instruction cache).
+    constexpr int P = (int)kEmitParts;
+    constexpr uint32_t kBuf = kEmitSlab / kEmitParts;
+    const int n_stages = n_mates * P;
+    // per-stage view of this lane's record
+    struct Mate { Rec rc; uint2 res; bool canon, valid, plain; uint32_t tsize; };
+    auto mate_of = [&](int m) -> Mate {
+        return m ? Mate{L.rc[1], L.res[1], L.canon[1], L.valid[1], L.plain[1], L.tsize[1]} : Mate{L.rc[0], L.res[0], L.canon[0], L.valid[0], L.plain[0], L.tsize[0]};
+    };
+    auto extent = [&](int t, const Rec &rc, uint32_t &lo, uint32_t &hi, uint32_t &part_mask) -> bool {
+        const int m = t / P, part = t % P;
+        part_mask = (P == 1 ? 0xffffffffu : ((1u << (32 / P)) - 1u) << (part * (32 / P))) & in_mask;
+        lo = hi = 0;
+        if (part_mask == 0) return false;
+        const int first_lane = __ffs(part_mask) - 1, last_lane = 31 - __clz(part_mask);
+        lo = __shfl_sync(0xffffffffu, rc.hdr, first_lane) & ~15u;
+        const uint64_t end = min((uint64_t)__shfl_sync(0xffffffffu, rc.qual + rc.len, last_lane) + 1, m ? a.raw_bytes[1] : a.raw_bytes[0]);
+        hi = (uint32_t)((end + 15) & ~(uint64_t)15);
+        return true;
+    };
+    auto issue = [&](int t) {
+        uint32_t lo, hi, pm;
+        const Rec rc = (t / P) ? L.rc[1] : L.rc[0];
+        if (extent(t, rc, lo, hi, pm) && hi - lo <= kBuf) {
+            const uint32_t dst = slab_s + (uint32_t)(t % P) * kBuf;
+            const uint8_t *g = (t / P) ? a.raw[1] : a.raw[0];
+            for (uint32_t c = lo + 16 * lane; c < hi; c += 16 * 32) cp_async16(dst + (c - lo), g + c);
         }
-        // ---- runs of untouched records of a surviving pair (or, unpaired input, of surviving reads): block copies
-        const int s_main = o.paired ? m : 2;
-        const bool main = o.paired ? both : (in && L.valid[0]);
-        copy_runs(__ballot_sync(0xffffffffu, main && L.plain[m]), a.out[s_main], src, L.rc[m].hdr, L.tsize[m], off[s_main], lane);
-        // ---- everything else of this mate, four records at a time (one per 8-lane group)
-        const bool trimmed = in && L.valid[m] && !(main && L.plain[m]);                  // needs write_trimmed
-        const bool disc = in && o.discard && !L.valid[m] && !(o.paired && both);          // raw copy to the discard stream
-        // destination of this mate's record
-        uint32_t dst = 0;
-        int s_dst = 0;
-        if (trimmed) { s_dst = main ? s_main : 2; dst = off[s_dst]; }
-        else if (disc) {
-            s_dst = 3;
-            dst = off[3];
-            if (m == 1 && !L.valid[0]) dst += header_len(a.raw[0], L.rc[0], L.canon[0]) + 2 * L.rc[0].len + 5;
-        }
-        uint32_t todo = __ballot_sync(0xffffffffu, trimmed || disc);
-        const uint32_t sub = lane & 7, grp = lane >> 3;
-        while (todo) {
-            int j = -1;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int b = todo ? __ffs(todo) - 1 : -1;
-                if (b >= 0) todo &= todo - 1;
-                if ((int)grp == g) j = b;
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (int t = 0; t < P && t < n_stages; ++t) issue(t);
+#pragma unroll 1
+    for (int t = 0; t < n_stages; ++t) {
+        const int m = t / P;
+        cp_async_wait_group(min(n_stages - 1 - t, P - 1));
+        __syncwarp();
+        const Mate M = mate_of(m);
+        uint32_t lo, hi, part_mask;
+        if (extent(t, M.rc, lo, hi, part_mask)) {
+            const bool mine = (part_mask >> lane) & 1u;
+            const uint8_t *src = hi - lo <= kBuf ? slab + (uint32_t)(t % P) * kBuf - lo : (m ? a.raw[1] : a.raw[0]);    // src[offset] = byte at raw offset `offset`
+            // ---- runs of untouched records of a surviving pair (or, unpaired input, of surviving reads): block copies
+            const int s_main = o.paired ? m : 2;
+            const bool main = mine && (o.paired ? both : M.valid);
+            uint8_t *const out_main = s_main == 0 ? a.out[0] : s_main == 1 ? a.out[1] : a.out[2];
+            const uint32_t off_main = s_main == 0 ? off[0] : s_main == 1 ? off[1] : off[2];
+            copy_runs(__ballot_sync(0xffffffffu, main && M.plain), out_main, src, M.rc.hdr, M.tsize, off_main, lane);
+            // ---- everything else of this mate, four records at a time (one per 8-lane group)
+            const bool trimmed = mine && M.valid && !(main && M.plain);                // needs write_trimmed
+            const bool disc = mine && o.discard && !M.valid;                           // raw copy to the discard stream
+            uint8_t *dstp = nullptr;                                                    // where this mate's record goes
+            if (trimmed) dstp = main ? out_main + off_main : a.out[2] + off[2];
+            else if (disc) {
+                dstp = a.out[3] + off[3];
+                if (m == 1 && !L.valid[0]) dstp += header_len(a.raw[0], L.rc[0], L.canon[0]) + 2 * L.rc[0].len + 5;
             }
-            const int js = j < 0 ? 0 : j;
-            Rec rc;
-            rc.hdr = __shfl_sync(0xffffffffu, L.rc[m].hdr, js);
-            rc.seq = __shfl_sync(0xffffffffu, L.rc[m].seq, js);
-            rc.qual = __shfl_sync(0xffffffffu, L.rc[m].qual, js);
-            rc.len = __shfl_sync(0xffffffffu, L.rc[m].len, js);
-            const uint32_t ex = __shfl_sync(0xffffffffu, L.res[m].x, js), ey = __shfl_sync(0xffffffffu, L.res[m].y, js);
-            const bool cn = __shfl_sync(0xffffffffu, (int)L.canon[m], js) != 0;
-            const bool tr = __shfl_sync(0xffffffffu, (int)trimmed, js) != 0;
-            const uint32_t d = __shfl_sync(0xffffffffu, dst, js);
-            const int sd = __shfl_sync(0xffffffffu, s_dst, js);
-            if (j < 0) continue;
-            uint8_t *const outp = (sd == 0 ? a.out[0] : sd == 1 ? a.out[1] : sd == 2 ? a.out[2] : a.out[3]) + d;
-            if (tr) write_trimmed<8>(outp, src, rc, cn, ex, ey & kResLenMask, ey >> kResLenBits, o, sub);
-            else write_raw<8>(outp, src, rc, cn, sub);
+            uint32_t todo = __ballot_sync(0xffffffffu, trimmed || disc);
+            const uint32_t sub = lane & 7, grp = lane >> 3;
+            while (todo) {
+                int j = -1;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int b = todo ? __ffs(todo) - 1 : -1;
+                    if (b >= 0) todo &= todo - 1;
+                    if ((int)grp == g) j = b;
+                }
+                const int js = j < 0 ? 0 : j;
+                Rec rc;
+                rc.hdr = __shfl_sync(0xffffffffu, M.rc.hdr, js);
+                rc.seq = __shfl_sync(0xffffffffu, M.rc.seq, js);
+                rc.qual = __shfl_sync(0xffffffffu, M.rc.qual, js);
+                rc.len = __shfl_sync(0xffffffffu, M.rc.len, js);
+                const uint32_t ex = __shfl_sync(0xffffffffu, M.res.x, js), ey = __shfl_sync(0xffffffffu, M.res.y, js);
+                const bool cn = __shfl_sync(0xffffffffu, (int)M.canon, js) != 0;
+                const bool tr = __shfl_sync(0xffffffffu, (int)trimmed, js) != 0;
+                const unsigned long long dp = __shfl_sync(0xffffffffu, (unsigned long long)dstp, js);
+                if (j < 0) continue;
+                uint8_t *const outp = reinterpret_cast<uint8_t *>(dp);
+                if (tr) write_trimmed<8>(outp, src, rc, cn, ex, ey & kResLenMask, ey >> kResLenBits, o, sub);
+                else write_raw<8>(outp, src, rc, cn, sub);
+            }
         }
+        __syncwarp();                                          // everyone is done reading this buffer
+        if (t + P < n_stages) issue(t + P);
     }
 }
 
