@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block-pairs", type=int, default=250_000, help="pairs generated on the host (numpy)")
     ap.add_argument("--batch-pairs", type=int, default=2_000_000, help="pairs per step (block replicated in HBM)")
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default: --steps; 0 disables)")
     ap.add_argument("--cpu-pairs", type=int, default=500_000, help="sample size of the cpu_baseline leg")
     ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -310,6 +310,8 @@ def main():
 
     # ---- end-to-end: pinned host buffers in, host buffers out (fq_process_host)
     e2e = None
+    if args.e2e_steps is None:
+        args.e2e_steps = args.steps
     if args.e2e_steps > 0 and args.workload == "c2":
         h1, h2 = eng.host_alloc(n1), eng.host_alloc(n2)
         for k in range(reps):
