@@ -6,21 +6,27 @@
 // are out of scope.
 //
 //   faqcs_b200 -1 r1.fq -2 r2.fq -d outdir [FaQCs flags]        extra: --device N, --batch_mb N
+#include <fcntl.h>
 #include <getopt.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <cerrno>
+#include <chrono>
 #include <climits>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <functional>
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -48,7 +54,7 @@ struct Cli {
     unsigned split_size = 1000000, replace_to_N_q = 0;
     vector<pair<string, string>> adapter;
     int device = 0;
-    size_t batch_mb = 256;
+    size_t batch_mb = 64;
     bool has_paired() const { return !input_read1_file.empty(); }       // has_paired() tests read1 twice, FaQCs.h:135-138
     bool has_unpaired() const { return !input_unpaired_file.empty(); }
 };
@@ -129,7 +135,7 @@ static void usage()
     cerr << "\t--split_size\t\t<INT> (kept for compatibility)\n\t--qc_only\t\t<bool> no Filters, no Trimming, report numbers.\n\t--discard\t\t<bool> Output discarded reads\n";
     cerr << "\t--substitute\t\t<bool> (not implemented, as in FaQCs)\n\t--trim_only\t\t<bool> No quality report. Output trimmed reads only.\n\t--replace_to_N_q\t<INT> Replace base G to N when below this quality score (default:0, off)\n";
     cerr << "\t--5trim_off\t\t<bool> Turn off trimming from 5'end.\n\t--debug\t\t\t<bool> Keep intermediate files\n\t--version\t\t<bool> Print the version and exit\n";
-    cerr << "GPU:\n\t--device\t\t<INT> CUDA device (default 0)\n\t--batch_mb\t\t<INT> MiB of FASTQ per mate per batch (default 256)\n";
+    cerr << "GPU:\n\t--device\t\t<INT> CUDA device (default 0)\n\t--batch_mb\t\t<INT> MiB of FASTQ per mate per batch (default 64)\n";
 }
 
 static void parse_options(int argc, char *argv[], Cli &o)
@@ -288,22 +294,95 @@ static void parse_options(int argc, char *argv[], Cli &o)
     }
 }
 
-// ---- input: gz or plain, whole records per batch -------------------------------------------------
-struct Source {
-    gzFile f = nullptr;
-    bool eof = false;
-    vector<uint8_t> carry;       // bytes read but not yet submitted (tail of the previous fill)
-    bool open(const string &fn) { f = gzopen(fn.c_str(), "r"); if (f) gzbuffer(f, 1 << 20); return f != nullptr; }
-    void close() { if (f) gzclose(f); f = nullptr; }
-    // fill buf[0..cap) starting with the carry; returns bytes available
-    size_t fill(uint8_t *buf, size_t cap)
+// ---- host pipeline: reader threads -> GPU -> writer threads --------------------
+// A worker thread that runs posted jobs in order; wait_idle() rethrows the first error a job raised.
+class Worker {
+    thread th;
+    mutex mu;
+    condition_variable cv, cv_idle;
+    deque<function<void()>> jobs;
+    size_t busy = 0;
+    bool stop = false;
+    const char *err = nullptr;
+    void loop()
     {
-        size_t n = carry.size();
-        if (n) memcpy(buf, carry.data(), n);
-        carry.clear();
+        for (;;) {
+            function<void()> job;
+            {
+                unique_lock<mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !jobs.empty(); });
+                if (jobs.empty()) return;
+                job = move(jobs.front());
+                jobs.pop_front();
+            }
+            try { job(); } catch (const char *e) { lock_guard<mutex> lk(mu); if (!err) err = e; }
+            {
+                lock_guard<mutex> lk(mu);
+                --busy;
+            }
+            cv_idle.notify_all();
+        }
+    }
+public:
+    Worker() : th([this] { loop(); }) {}
+    ~Worker()
+    {
+        { lock_guard<mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        th.join();
+    }
+    void post(function<void()> f)
+    {
+        { lock_guard<mutex> lk(mu); jobs.push_back(move(f)); ++busy; }
+        cv.notify_all();
+    }
+    void wait_idle()
+    {
+        unique_lock<mutex> lk(mu);
+        cv_idle.wait(lk, [&] { return busy == 0; });
+        if (err) { const char *e = err; err = nullptr; throw e; }
+    }
+};
+
+// ---- input: gz or plain, whole records per batch -------------------------------------------------
+// Plain files are read with read(2) straight into the pinned batch buffer; gzip input (magic 1f 8b) goes
+// through zlib like the reference's reader (fastq.cpp:8-30).
+struct Source {
+    int fd = -1;
+    gzFile gz = nullptr;
+    bool eof = false;
+    bool open(const string &fn)
+    {
+        fd = ::open(fn.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        unsigned char magic[2] = {0, 0};
+        const ssize_t got = ::read(fd, magic, 2);
+        lseek(fd, 0, SEEK_SET);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            gz = gzdopen(fd, "r");
+            if (!gz) return false;
+            gzbuffer(gz, 1 << 20);
+        }
+        return true;
+    }
+    void close()
+    {
+        if (gz) gzclose(gz);
+        else if (fd >= 0) ::close(fd);
+        gz = nullptr;
+        fd = -1;
+    }
+    // append to buf[have..cap); returns the bytes now in buf
+    size_t fill(uint8_t *buf, size_t have, size_t cap)
+    {
+        size_t n = have;
         while (!eof && n < cap) {
-            const int got = gzread(f, buf + n, (unsigned)min<size_t>(cap - n, 1u << 30));
-            if (got < 0) throw "fastq.cpp:next_read: Unable to read header";
+            const size_t want = min<size_t>(cap - n, 1u << 30);
+            const ssize_t got = gz ? (ssize_t)gzread(gz, buf + n, (unsigned)want) : ::read(fd, buf + n, want);
+            if (got < 0) {
+                if (!gz && errno == EINTR) continue;
+                throw "fastq.cpp:next_read: Unable to read header";
+            }
             if (got == 0) { eof = true; break; }
             n += (size_t)got;
         }
@@ -311,21 +390,22 @@ struct Source {
     }
 };
 
-// offset just past the k-th complete record (4 lines) in buf[0..n); also counts the complete records
-static size_t count_records(const uint8_t *buf, size_t n, vector<size_t> *ends_every, size_t every)
+static size_t count_newlines(const uint8_t *buf, size_t n)
 {
-    size_t lines = 0, recs = 0;
-    const uint8_t *p = buf, *end = buf + n;
-    while (p < end) {
-        const uint8_t *nl = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
-        if (!nl) break;
-        p = nl + 1;
-        if ((++lines & 3) == 0) {
-            ++recs;
-            if (ends_every && recs % every == 0) ends_every->push_back((size_t)(p - buf));
-        }
+    size_t c = 0;
+    for (size_t i = 0; i < n; ++i) c += buf[i] == '\n';      // vectorised by the compiler
+    return c;
+}
+// offset just past the keep-th of the `total` newlines in buf[0..n): walks back from the end
+static size_t offset_after_line(const uint8_t *buf, size_t n, size_t total, size_t keep)
+{
+    const uint8_t *q = buf + n;
+    for (size_t i = total; i >= keep; --i) {
+        q = (const uint8_t *)memrchr(buf, '\n', (size_t)(q - buf));
+        if (!q) return n;
+        if (i == keep) break;
     }
-    return recs;
+    return (size_t)(q - buf) + 1;
 }
 static size_t offset_of_record(const uint8_t *buf, size_t n, size_t k)
 {
@@ -350,27 +430,44 @@ struct Run {
     void check(fq_status st) { if (st != FQ_OK) throw string(fq_last_error(ctx)); }
 };
 
-static FILE *open_out(const string &fn, const char *what)
+static int open_out(const string &fn, const char *what)
 {
-    FILE *f = fopen(fn.c_str(), "wb");
-    if (!f) { cerr << "Unable to open " << fn << " for writing " << what << endl; throw "I/O error"; }
-    setvbuf(f, nullptr, _IOFBF, 8 << 20);
-    return f;
+    const int fd = ::open(fn.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) { cerr << "Unable to open " << fn << " for writing " << what << endl; throw "I/O error"; }
+    return fd;
+}
+static void write_all(int fd, const uint8_t *p, size_t n)
+{
+    while (n) {
+        const ssize_t w = ::write(fd, p, min<size_t>(n, 1u << 30));
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            throw "I/O error while writing the trimmed reads";
+        }
+        p += w;
+        n -= (size_t)w;
+    }
 }
 
+static double now_s() { return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // process_paired (FaQCs.cpp:153-538) / process_unpaired (:540-757): read -> GPU -> four ordered writers.
+// One reader thread per input file fills the pinned buffer of the next batch while the GPU works on the
+// current one; one writer thread per output file drains the previous batch.
 static void process(Run &R, bool paired)
 {
     Cli &o = R.o;
-    Source s1, s2;
+    const bool timing = getenv("FAQCS_B200_TIMING") != nullptr;
+    const int n_mates = paired ? 2 : 1;
+    Source src[2];
     if (paired) {
-        if (!s1.open(o.input_read1_file)) { cerr << "Unable to open " << o.input_read1_file << " for loading read one sequences" << endl; throw "I/O error"; }
-        if (!s2.open(o.input_read2_file)) { cerr << "Unable to open " << o.input_read2_file << " for loading read two sequences" << endl; throw "I/O error"; }
-    } else if (!s1.open(o.input_unpaired_file)) {
+        if (!src[0].open(o.input_read1_file)) { cerr << "Unable to open " << o.input_read1_file << " for loading read one sequences" << endl; throw "I/O error"; }
+        if (!src[1].open(o.input_read2_file)) { cerr << "Unable to open " << o.input_read2_file << " for loading read two sequences" << endl; throw "I/O error"; }
+    } else if (!src[0].open(o.input_unpaired_file)) {
         cerr << "Unable to open " << o.input_unpaired_file << " for loading unpaired read sequences" << endl;
         throw "I/O error";
     }
-    FILE *fout[4] = {nullptr, nullptr, nullptr, nullptr};
+    int fout[4] = {-1, -1, -1, -1};
     if (!o.qc_only) {
         if (paired) {
             fout[0] = open_out(o.trimmed_read1_file, "read one sequences");
@@ -382,60 +479,101 @@ static void process(Run &R, bool paired)
     const size_t cap = o.batch_mb << 20;
     uint8_t *buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [slot][mate], pinned
     for (int k = 0; k < 2; ++k)
-        for (int m = 0; m < (paired ? 2 : 1); ++m)
+        for (int m = 0; m < n_mates; ++m)
             if (!(buf[k][m] = (uint8_t *)fq_host_alloc(cap))) throw "unable to allocate pinned host memory";
     const bool emulate = o.filter_adapter || o.filter_phiX;             // Q3: keep batches on 32768-record boundaries
-    uint64_t first_index = 0, pending_ticket = 0;
-    bool have_pending = false;
-    auto drain = [&](uint64_t ticket) {
-        fq_batch_out out;
-        R.check(fq_wait(R.ctx, ticket, &out));
-        for (int s = 0; s < 4; ++s)
-            if (fout[s] && out.bytes[s]) fwrite(out.data[s], 1, out.bytes[s], fout[s]);
-    };
-    for (int slot = 0;; slot ^= 1) {
-        size_t n1 = s1.fill(buf[slot][0], cap), n2 = paired ? s2.fill(buf[slot][1], cap) : 0;
-        const bool at_eof = s1.eof && (!paired || s2.eof);
-        size_t use1 = n1, use2 = n2;
-        if (!at_eof) {
-            size_t r1 = count_records(buf[slot][0], n1, nullptr, 1), r2 = paired ? count_records(buf[slot][1], n2, nullptr, 1) : r1;
-            size_t nrec = min(r1, r2);
-            if (emulate && nrec >= FQ_REF_BATCH) nrec -= nrec % FQ_REF_BATCH;
-            if (nrec == 0) throw "record larger than the batch buffer: raise --batch_mb";
-            use1 = offset_of_record(buf[slot][0], n1, nrec);
-            if (paired) use2 = offset_of_record(buf[slot][1], n2, nrec);
-            s1.carry.assign(buf[slot][0] + use1, buf[slot][0] + n1);
-            if (paired) s2.carry.assign(buf[slot][1] + use2, buf[slot][1] + n2);
+    struct Filled { size_t n = 0, lines = 0; } filled[2];
+    double t_read = 0, t_gpu = 0, t_write_wait = 0, t_cut = 0;
+    {
+        Worker readers[2], writers[4];
+        auto post_fill = [&](int slot, int m, size_t have) {
+            readers[m].post([&, slot, m, have] {
+                filled[m].n = src[m].fill(buf[slot][m], have, cap);
+                filled[m].lines = count_newlines(buf[slot][m], filled[m].n);
+            });
+        };
+        for (int m = 0; m < n_mates; ++m) post_fill(0, m, 0);
+        uint64_t first_index = 0, pending_ticket = 0;
+        bool have_pending = false;
+        auto drain = [&](uint64_t ticket) {
+            fq_batch_out out;
+            R.check(fq_wait(R.ctx, ticket, &out));
+            for (int s = 0; s < 4; ++s)
+                if (fout[s] >= 0 && out.bytes[s]) {
+                    const uint8_t *p = out.data[s];
+                    const size_t n = out.bytes[s];
+                    const int fd = fout[s];
+                    writers[s].post([fd, p, n] { write_all(fd, p, n); });
+                }
+        };
+        for (int slot = 0;; slot ^= 1) {
+            double t0 = now_s();
+            for (int m = 0; m < n_mates; ++m) readers[m].wait_idle();
+            t_read += now_s() - t0;
+            t0 = now_s();
+            const size_t n1 = filled[0].n, n2 = paired ? filled[1].n : 0;
+            const bool at_eof = src[0].eof && (!paired || src[1].eof);
+            size_t use1 = n1, use2 = n2, nrec = filled[0].lines / 4;
+            if (!at_eof) {
+                const size_t r1 = filled[0].lines / 4, r2 = paired ? filled[1].lines / 4 : r1;
+                nrec = min(r1, r2);
+                if (emulate && nrec >= FQ_REF_BATCH) nrec -= nrec % FQ_REF_BATCH;
+                if (nrec == 0) throw "record larger than the batch buffer: raise --batch_mb";
+                use1 = offset_after_line(buf[slot][0], n1, filled[0].lines, 4 * nrec);
+                if (paired) use2 = offset_after_line(buf[slot][1], n2, filled[1].lines, 4 * nrec);
+                // the tails open the next batch; its buffers are free (their batch has been run)
+                memcpy(buf[slot ^ 1][0], buf[slot][0] + use1, n1 - use1);
+                post_fill(slot ^ 1, 0, n1 - use1);
+                if (paired) {
+                    memcpy(buf[slot ^ 1][1], buf[slot][1] + use2, n2 - use2);
+                    post_fill(slot ^ 1, 1, n2 - use2);
+                }
+            }
+            if (R.first_batch) {
+                // A1 on the first 32768 records (FaQCs.cpp:261-277, 393-414, 609-619, 669-683); an empty input throws
+                const size_t a1 = offset_of_record(buf[slot][0], use1, FQ_REF_BATCH), a2 = paired ? offset_of_record(buf[slot][1], use2, FQ_REF_BATCH) : 0;
+                int32_t off = 0, q = 0;
+                const int q_before = o.quality;
+                R.check(fq_autodetect(R.ctx, buf[slot][0], a1, paired ? buf[slot][1] : nullptr, a2, &off, &q));
+                o.input_quality_offset = (char)off;
+                o.quality = (char)q;
+                if (q != q_before) cerr << "The input looks like NextSeq data and the quality level (-q) is adjusted to 20 for trimming." << endl;
+                R.first_batch = false;
+            }
+            t_cut += now_s() - t0;
+            if (use1 || use2 || at_eof) {
+                uint64_t ticket = 0;
+                // this batch's outputs reuse the host slot of the batch two tickets back: its writes must be done
+                t0 = now_s();
+                for (Worker &w : writers) w.wait_idle();
+                t_write_wait += now_s() - t0;
+                t0 = now_s();
+                R.check(fq_submit_host(R.ctx, buf[slot][0], use1, paired ? buf[slot][1] : nullptr, use2, first_index, at_eof ? 1 : 0, &ticket));
+                R.check(fq_run(R.ctx, ticket));
+                if (have_pending) drain(pending_ticket);
+                t_gpu += now_s() - t0;
+                pending_ticket = ticket;
+                have_pending = true;
+                first_index += nrec;
+            }
+            if (at_eof) break;
         }
-        if (R.first_batch) {
-            // A1 on the first 32768 records (FaQCs.cpp:261-277, 393-414, 609-619, 669-683); an empty input throws
-            const size_t a1 = offset_of_record(buf[slot][0], use1, FQ_REF_BATCH), a2 = paired ? offset_of_record(buf[slot][1], use2, FQ_REF_BATCH) : 0;
-            int32_t off = 0, q = 0;
-            const int q_before = o.quality;
-            R.check(fq_autodetect(R.ctx, buf[slot][0], a1, paired ? buf[slot][1] : nullptr, a2, &off, &q));
-            o.input_quality_offset = (char)off;
-            o.quality = (char)q;
-            if (q != q_before) cerr << "The input looks like NextSeq data and the quality level (-q) is adjusted to 20 for trimming." << endl;
-            R.first_batch = false;
+        if (have_pending) {
+            for (Worker &w : writers) w.wait_idle();
+            drain(pending_ticket);
         }
-        uint64_t ticket = 0;
-        if (use1 || use2 || at_eof) {
-            R.check(fq_submit_host(R.ctx, buf[slot][0], use1, paired ? buf[slot][1] : nullptr, use2, first_index, at_eof ? 1 : 0, &ticket));
-            R.check(fq_run(R.ctx, ticket));
-            if (have_pending) drain(pending_ticket);
-            pending_ticket = ticket;
-            have_pending = true;
-            // records of this batch (for first_record_index): count on the host side
-            first_index += count_records(buf[slot][0], use1, nullptr, 1);
-        }
-        if (at_eof) break;
+        const double t0 = now_s();
+        for (Worker &w : writers) w.wait_idle();
+        t_write_wait += now_s() - t0;
     }
-    if (have_pending) drain(pending_ticket);
+    if (timing)
+        cerr << "[timing] waiting for readers " << t_read << " s, cut/autodetect " << t_cut << " s, submit+run+wait " << t_gpu
+             << " s, waiting for writers " << t_write_wait << " s" << endl;
     for (int k = 0; k < 2; ++k)
         for (int m = 0; m < 2; ++m) fq_host_free(buf[k][m]);
-    for (FILE *f : fout) if (f) fclose(f);
-    s1.close();
-    s2.close();
+    for (int fd : fout) if (fd >= 0) ::close(fd);
+    src[0].close();
+    src[1].close();
 }
 
 // write_stats (FaQCs.cpp:759-1034): same expressions, same stream state.
@@ -608,7 +746,10 @@ int main(int argc, char *argv[])
         f.filter_adapter = o.filter_adapter || o.filter_phiX; f.discard_output = o.discard_output;
         f.num_thread = o.num_thread ? o.num_thread : max(1u, thread::hardware_concurrency());     // -t 0 = all cores (options.cpp:124)
         f.n_adapters = (uint32_t)adapters.size(); f.adapters = adapters.data();
+        const bool timing = getenv("FAQCS_B200_TIMING") != nullptr;
+        const double t_start = now_s();
         if (fq_create(&f, o.device, &ctx) != FQ_OK) throw string(fq_last_error(nullptr));
+        const double t_created = now_s();
         Run R(o);
         R.ctx = ctx;
         if (o.has_paired()) process(R, true);
@@ -616,11 +757,16 @@ int main(int argc, char *argv[])
             R.first_batch = true;      // offset detection only if still unknown; the NextSeq check runs per input (FaQCs.cpp:586,673-683)
             process(R, false);
         }
+        const double t_processed = now_s();
         fq_stats_view v;
         if (fq_stats(ctx, &v) != FQ_OK) throw string(fq_last_error(ctx));
         write_stats(v, o);
         if (!o.trim_only && o.debug) write_debug_files(v, o);    // the reference deletes these unless --debug (plot.cpp:517-537)
+        const double t_stats = now_s();
         fq_destroy(ctx);
+        if (timing)
+            cerr << "[timing] fq_create " << t_created - t_start << " s, process " << t_processed - t_created << " s, stats files "
+                 << t_stats - t_processed << " s, fq_destroy " << now_s() - t_stats << " s" << endl;
     } catch (const char *error) {
         cerr << "Caught the error " << error << endl;
         if (ctx) fq_destroy(ctx);
