@@ -61,6 +61,19 @@ def test_paired_defaults_discard_small_batches():
     assert len(outs["ref"]) == 15          # 4 fastq + stats + 10 data files
 
 
+def test_paired_mates_of_different_length_many_batches():
+    """Mate 2 records are shorter than mate 1 records, so every batch cut leaves tails of different sizes in the
+    two reader buffers (host pipeline); gzip for one mate, plain for the other."""
+    w = synth.c2(30000)
+    rec = bytes(w.r2).split(b"\n")
+    short = bytearray()
+    for i in range(0, len(rec) - 1, 4):
+        short += rec[i] + b"\n" + rec[i + 1][:90] + b"\n+\n" + rec[i + 3][:90] + b"\n"
+    outs = run_both({"-1": ("r1.fq.gz", w.r1), "-2": ("r2.fq", np.frombuffer(bytes(short), dtype=np.uint8))}, ["--discard"], threads=3,
+                    extra_cli=["--batch_mb", "1"])
+    assert_same_files(outs)
+
+
 def test_unpaired_gz_ascii64_hard():
     w = synth.c5(20000)
     outs = run_both({"-u": ("u.fq.gz", w.r1)}, ["--mode", "HARD", "-q", "20", "--avg_q", "25", "--replace_to_N_q", "10", "--discard"])
