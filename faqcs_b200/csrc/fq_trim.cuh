@@ -848,10 +848,10 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
 }
 
 #ifndef FQ_TRIM_THREADS
-#define FQ_TRIM_THREADS 512
+#define FQ_TRIM_THREADS 1024
 #endif
 #ifndef FQ_TRIM_MIN_CTAS
-#define FQ_TRIM_MIN_CTAS 2
+#define FQ_TRIM_MIN_CTAS 1
 #endif
 constexpr int kTrimThreads = FQ_TRIM_THREADS;
 
@@ -943,7 +943,6 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
         continue;
 #endif
         // ---- phase 2a: one lane per read: PRE scalar statistics and the window
-        const uint8_t *sp_mine = raw_mine + me.rc.seq;
         const signed char *qp_mine = reinterpret_cast<const signed char *>(raw_mine + me.rc.qual);
         const uint32_t len = me.rc.len;
         const QualAt qa{qp_mine, me.lead, me.trail, o.in_off};
