@@ -65,3 +65,20 @@ def test_c3_adapters_polya_artifacts_t1():
 def test_c3_adapters_qc_only():
     w = synth.c3(1000)
     check(w, Options(filter_adapter=True, qc_only=True, num_thread=2), threads=2, polyA=True)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_reads_and_options(seed):
+    """Random option sets over records with lower case, IUPAC letters, N runs, Q2 tails, lengths 1..420, '+name'
+    third lines and (one seed in five) CRLF line ends: the oracle must reproduce the reference byte for byte."""
+    from fuzz import fuzz_bytes, fuzz_options, fuzz_reads
+    rng = np.random.default_rng(2000 + seed)
+    in_off = 64 if seed % 4 == 3 else 33
+    paired = seed % 2 == 0
+    eol = "\r\n" if seed % 5 == 4 else "\n"
+    r1 = fuzz_bytes(fuzz_reads(rng, 600, in_off, "1" if paired else None), rng, eol)
+    r2 = fuzz_bytes(fuzz_reads(rng, 600, in_off, "2"), rng, eol) if paired else None
+    kw = fuzz_options(rng, in_off, adapters=seed % 3 == 1)
+    polyA = bool(kw.pop("adapters", None))
+    threads = kw.get("num_thread", 0) or 2
+    check(synth.Workload("fuzz", r1, r2, []), Options(**kw), threads=threads, polyA=polyA)
