@@ -456,6 +456,11 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     EmitArgs ea{};
     ea.n_rec = n;
     ea.n_tiles = (n + kTile - 1) / kTile;
+    {   // rounds in which a warp stages its 32 records: the smallest split whose average slab leaves 8 % headroom
+        const double avg = (double)std::max(n1, n2) / (double)std::max<uint32_t>(n, 1u);
+        ea.parts = 1;
+        while (ea.parts < 8 && (32.0 / ea.parts) * avg * 1.08 + 32.0 > (double)kEmitSlab) ea.parts *= 2;
+    }
     CK(ctx->d_tile.ensure((size_t)ea.n_tiles * 4 * 4));
     ea.tile_sum = ctx->d_tile.as<uint32_t>();
     ea.info = info;

@@ -22,6 +22,7 @@ struct EmitArgs {
     const uint2 *res[2];
     const uint8_t *canon[2];     // 1 = LF line ends + bare '+' line (raw bytes == write_read output)
     uint32_t n_rec;
+    uint32_t parts;              // k_emit stages the 32 records of a warp in this many rounds (1, 2, 4, 8)
     uint32_t n_tiles;
     uint32_t *tile_sum;          // [4][n_tiles] -> exclusive bases after k_scan_tiles (u32: < 4 GiB per stream per batch)
     uint8_t *out[4];
@@ -306,13 +307,9 @@ __device__ __forceinline__ void copy_runs(uint32_t mask, uint8_t *out, const uin
 // shared memory: the chains "descriptor -> header bytes -> bases -> qualities" that made the copy
 // latency-bound on global memory now cost tens of cycles per link, and the only global traffic left
 // is the coalesced slab load and the 16-byte stores.
-#ifndef FQ_EMIT_PARTS
-#define FQ_EMIT_PARTS 1
-#endif
 #ifndef FQ_EMIT_SLAB
 #define FQ_EMIT_SLAB (12 * 1024)
 #endif
-constexpr uint32_t kEmitParts = FQ_EMIT_PARTS;          // a warp stages its 32 records in this many rounds
 constexpr uint32_t kEmitSlab = FQ_EMIT_SLAB;            // staging bytes per warp
 constexpr uint32_t kEmitSmem = (kTile / 32) * kEmitSlab;
 
@@ -320,17 +317,7 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_group(int n)      // n is a compile-time constant after unrolling
-{
-    switch (n) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-    }
-}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 extern __shared__ __align__(16) uint8_t g_emit_smem[];
 
@@ -375,11 +362,11 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
     const uint32_t slab_s = (uint32_t)__cvta_generic_to_shared(slab);
     const int n_mates = o.paired ? 2 : 1;
 
-    // Software pipeline over n_mates * P stages (mate, part): the slab of a stage is the raw bytes of 32 / P
-    // consecutive records.  P buffers rotate; while stage t is being written out, the loads of stages
-    // t+1 .. t+P-1 are in flight.  The loop is deliberately NOT unrolled (one copy of the body: instruction cache).
-    constexpr int P = (int)kEmitParts;
-    constexpr uint32_t kBuf = kEmitSlab / kEmitParts;
+    // n_mates * P stages (mate, part): the slab of a stage is the raw bytes of 32 / P consecutive records; the host
+    // picks P (1, 2, 4 or 8) so that a stage normally fits the buffer, a stage that does not reads global memory.
+    // The loop is deliberately NOT unrolled (one copy of the body: instruction cache).  Splitting a slab that fits
+    // into pipelined parts was measured and is slower (per-stage overhead), so P is 1 whenever possible.
+    const int P = (int)a.parts;
     const int n_stages = n_mates * P;
     // per-stage view of this lane's record
     struct Mate { Rec rc; uint2 res; bool canon, valid, plain; uint32_t tsize; };
@@ -388,7 +375,8 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
     };
     auto extent = [&](int t, const Rec &rc, uint32_t &lo, uint32_t &hi, uint32_t &part_mask) -> bool {
         const int m = t / P, part = t % P;
-        part_mask = (P == 1 ? 0xffffffffu : ((1u << (32 / P)) - 1u) << (part * (32 / P))) & in_mask;
+        const uint32_t per = 32u / (uint32_t)P;
+        part_mask = (P == 1 ? 0xffffffffu : ((1u << per) - 1u) << (part * per)) & in_mask;
         lo = hi = 0;
         if (part_mask == 0) return false;
         const int first_lane = __ffs(part_mask) - 1, last_lane = 31 - __clz(part_mask);
@@ -397,28 +385,21 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
         hi = (uint32_t)((end + 15) & ~(uint64_t)15);
         return true;
     };
-    auto issue = [&](int t) {
-        uint32_t lo, hi, pm;
-        const Rec rc = (t / P) ? L.rc[1] : L.rc[0];
-        if (extent(t, rc, lo, hi, pm) && hi - lo <= kBuf) {
-            const uint32_t dst = slab_s + (uint32_t)(t % P) * kBuf;
-            const uint8_t *g = (t / P) ? a.raw[1] : a.raw[0];
-            for (uint32_t c = lo + 16 * lane; c < hi; c += 16 * 32) cp_async16(dst + (c - lo), g + c);
-        }
-        cp_async_commit();
-    };
-#pragma unroll 1
-    for (int t = 0; t < P && t < n_stages; ++t) issue(t);
 #pragma unroll 1
     for (int t = 0; t < n_stages; ++t) {
         const int m = t / P;
-        cp_async_wait_group(min(n_stages - 1 - t, P - 1));
-        __syncwarp();
         const Mate M = mate_of(m);
         uint32_t lo, hi, part_mask;
         if (extent(t, M.rc, lo, hi, part_mask)) {
             const bool mine = (part_mask >> lane) & 1u;
-            const uint8_t *src = hi - lo <= kBuf ? slab + (uint32_t)(t % P) * kBuf - lo : (m ? a.raw[1] : a.raw[0]);    // src[offset] = byte at raw offset `offset`
+            const uint8_t *src = m ? a.raw[1] : a.raw[0];      // src[offset] = byte at raw offset `offset`
+            if (hi - lo <= kEmitSlab) {
+                __syncwarp();                                  // everyone is done reading the previous slab
+                for (uint32_t c = lo + 16 * lane; c < hi; c += 16 * 32) cp_async16(slab_s + (c - lo), src + c);
+                cp_async_wait_all();
+                __syncwarp();
+                src = slab - lo;
+            }
             // ---- runs of untouched records of a surviving pair (or, unpaired input, of surviving reads): block copies
             const int s_main = o.paired ? m : 2;
             const bool main = mine && (o.paired ? both : M.valid);
@@ -460,8 +441,6 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
                 else write_raw<8>(outp, src, rc, cn, sub);
             }
         }
-        __syncwarp();                                          // everyone is done reading this buffer
-        if (t + P < n_stages) issue(t + P);
     }
 }
 
