@@ -91,13 +91,14 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__
     uint32_t *out = nl_seg + (size_t)w * seg_cap;
     uint32_t rank0 = 0, any_cr = 0, cr_eol = 0;
     for (uint64_t chunk_base = seg_lo; chunk_base < seg_hi; chunk_base += kChunkBytes) {
-        // vector k of lane l covers bytes chunk_base + (k*32 + l)*16 .. +16
-        uint32_t m16[4] = {0, 0, 0, 0};                 // two 16-bit newline masks per register
-        uint32_t cA = 0, cB = 0, cC = 0;                // per-vector newline counts, 10-bit fields (k = 0..2, 3..5, 6..7)
+        // lane l owns the 128 contiguous bytes chunk_base + l*128 ..: its eight 16-byte vectors are one cache line,
+        // its newline mask is 128 contiguous bits, and ranks follow from ONE warp scan of the per-lane counts
+        uint32_t m16[4] = {0, 0, 0, 0};                 // two 16-bit newline masks per register, memory order
+        const uint64_t lane_base = chunk_base + (uint64_t)lane * 128;
         uint4 v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint64_t off = chunk_base + (uint64_t)(k * 32 + lane) * 16;
+            const uint64_t off = lane_base + (uint64_t)k * 16;
             v[k] = make_uint4(0, 0, 0, 0);
             if (off + 16 <= seg_hi) v[k] = __ldg(reinterpret_cast<const uint4 *>(raw + off));
             else if (off < seg_hi) {
@@ -111,24 +112,16 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__
             const uint32_t m = eq_mask16(v[k], 0x0a0a0a0au);
             any_cr |= has_byte(v[k].x, 0x0d0d0d0du) | has_byte(v[k].y, 0x0d0d0d0du) | has_byte(v[k].z, 0x0d0d0d0du) | has_byte(v[k].w, 0x0d0d0d0du);
             m16[k >> 1] |= m << (16 * (k & 1));
-            const uint32_t c = __popc(m);
-            if (k < 3) cA |= c << (10 * k);
-            else if (k < 6) cB |= c << (10 * (k - 3));
-            else cC |= c << (10 * (k - 6));
         }
-        const uint32_t iA = warp_incl_scan(cA, lane), iB = warp_incl_scan(cB, lane), iC = warp_incl_scan(cC, lane);
-        const uint32_t tA = __shfl_sync(0xffffffffu, iA, 31), tB = __shfl_sync(0xffffffffu, iB, 31), tC = __shfl_sync(0xffffffffu, iC, 31);
-        // ranks are ordered by (vector k, lane, byte)
+        const uint32_t cnt = __popc(m16[0]) + __popc(m16[1]) + __popc(m16[2]) + __popc(m16[3]);
+        const uint32_t incl = warp_incl_scan(cnt, lane);
+        uint32_t rank = rank0 + incl - cnt;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t incl = k < 3 ? (iA >> (10 * k)) & 1023u : k < 6 ? (iB >> (10 * (k - 3))) & 1023u : (iC >> (10 * (k - 6))) & 1023u;
-            const uint32_t tot = k < 3 ? (tA >> (10 * k)) & 1023u : k < 6 ? (tB >> (10 * (k - 3))) & 1023u : (tC >> (10 * (k - 6))) & 1023u;
-            uint32_t m = (m16[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-            uint32_t rank = rank0 + incl - __popc(m);
-            const uint64_t off = chunk_base + (uint64_t)(k * 32 + lane) * 16;
+        for (int w4 = 0; w4 < 4; ++w4) {
+            uint32_t m = m16[w4];
             while (m) {
                 const int b = __ffs(m) - 1;
-                const uint64_t pos = off + b;
+                const uint64_t pos = lane_base + (uint64_t)(w4 * 32 + b);
                 const uint32_t prev = pos ? raw[pos - 1] : 0;         // L1 resident: just loaded
                 uint32_t e = (uint32_t)pos;
                 if (prev == '\r') { e |= kNlCr; ++cr_eol; }
@@ -137,8 +130,8 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__
                 ++rank;
                 m &= m - 1;
             }
-            rank0 += tot;
         }
+        rank0 += __shfl_sync(0xffffffffu, incl, 31);
     }
     any_cr = __reduce_or_sync(0xffffffffu, any_cr);
     cr_eol = __reduce_add_sync(0xffffffffu, cr_eol);
