@@ -51,8 +51,9 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
 // 4-bit mask (bit b = byte b) of the bytes of w equal to the byte replicated in c4.
 __device__ __forceinline__ uint32_t eq_nibble(uint32_t w, uint32_t c4)
 {
-    // 0x80 flags -> bits 0,8,16,24 -> gathered into bits 21..24 by one multiply (no colliding partial products)
-    return (((zero_bytes(w ^ c4) >> 7) * 0x00204081u) >> 21) & 0xfu;
+    // 0x80 flags sit at bits 7,15,23,31; times (1 + 2^7 + 2^14 + 2^21) they meet in bits 28..31: the ten partial
+    // products land on ten different bits, so nothing carries
+    return (zero_bytes(w ^ c4) * 0x00204081u) >> 28;
 }
 __device__ __forceinline__ uint32_t eq_mask16(const uint4 &v, uint32_t c4)
 {
