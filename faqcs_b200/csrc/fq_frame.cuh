@@ -95,17 +95,23 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__
         // lane l owns the 128 contiguous bytes chunk_base + l*128 ..: its eight 16-byte vectors are one cache line,
         // its newline mask is 128 contiguous bits, and ranks follow from ONE warp scan of the per-lane counts
         uint32_t m16[4] = {0, 0, 0, 0};                 // two 16-bit newline masks per register, memory order
-        const uint64_t lane_base = chunk_base + (uint64_t)lane * 128;
+        const uint32_t lane_base = (uint32_t)chunk_base + lane * 128;         // a batch is < 1 GiB per mate
         uint4 v[8];
+        if (chunk_base + kChunkBytes <= seg_hi) {       // whole chunk inside the segment (warp-uniform): plain vector loads
+            const uint4 *src = reinterpret_cast<const uint4 *>(raw + lane_base);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint64_t off = lane_base + (uint64_t)k * 16;
-            v[k] = make_uint4(0, 0, 0, 0);
-            if (off + 16 <= seg_hi) v[k] = __ldg(reinterpret_cast<const uint4 *>(raw + off));
-            else if (off < seg_hi) {
-                uint32_t x[4] = {0, 0, 0, 0};
-                for (uint32_t b = 0; b < 16 && off + b < seg_hi; ++b) x[b >> 2] |= (uint32_t)raw[off + b] << (8 * (b & 3));
-                v[k] = make_uint4(x[0], x[1], x[2], x[3]);
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(src + k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint64_t off = (uint64_t)lane_base + (uint64_t)k * 16;
+                v[k] = make_uint4(0, 0, 0, 0);
+                if (off + 16 <= seg_hi) v[k] = __ldg(reinterpret_cast<const uint4 *>(raw + off));
+                else if (off < seg_hi) {
+                    uint32_t x[4] = {0, 0, 0, 0};
+                    for (uint32_t b = 0; b < 16 && off + b < seg_hi; ++b) x[b >> 2] |= (uint32_t)raw[off + b] << (8 * (b & 3));
+                    v[k] = make_uint4(x[0], x[1], x[2], x[3]);
+                }
             }
         }
 #pragma unroll
@@ -121,12 +127,10 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__
         for (int w4 = 0; w4 < 4; ++w4) {
             uint32_t m = m16[w4];
             while (m) {
-                const int b = __ffs(m) - 1;
-                const uint64_t pos = lane_base + (uint64_t)(w4 * 32 + b);
+                const uint32_t pos = lane_base + (uint32_t)(w4 * 32) + (uint32_t)(__ffs(m) - 1);
                 const uint32_t prev = pos ? raw[pos - 1] : 0;         // L1 resident: just loaded
-                uint32_t e = (uint32_t)pos;
-                if (prev == '\r') { e |= kNlCr; ++cr_eol; }
-                if (prev == '+') e |= kNlPlus;
+                const uint32_t e = pos | (prev == '\r' ? kNlCr : 0u) | (prev == '+' ? kNlPlus : 0u);
+                cr_eol += prev == '\r';
                 if (rank < seg_cap) out[rank] = e;
                 ++rank;
                 m &= m - 1;
