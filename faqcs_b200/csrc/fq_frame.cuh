@@ -80,7 +80,10 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane)
 // it writes the offsets of its '\n' bytes, in order, to its own region nl_seg[w * seg_cap ...]
 // and its line count to seg_count[w].  A tiny scan (k_scan_segments) then turns the counts into
 // global line bases and k_build_records maps global line numbers to (segment, local index).
-__global__ void __launch_bounds__(kFrameThreads) k_frame_lines(const uint8_t *__restrict__ raw, uint64_t n, uint32_t seg_bytes, uint32_t n_seg,
+#ifndef FQ_FRAME_MIN_CTAS
+#define FQ_FRAME_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kFrameThreads, FQ_FRAME_MIN_CTAS) k_frame_lines(const uint8_t *__restrict__ raw, uint64_t n, uint32_t seg_bytes, uint32_t n_seg,
                                                                uint32_t *__restrict__ nl_seg, uint32_t seg_cap, uint32_t *__restrict__ seg_count,
                                                                BatchInfo *info, int mate)
 {
