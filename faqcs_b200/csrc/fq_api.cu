@@ -357,7 +357,9 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     if (st != FQ_OK) return st;
     unsigned long long *S = ctx->d_stats.as<unsigned long long>();
 
-    if (paired && ctx->check_pair_ids) {
+    // read ids of the two mates (FaQCs.cpp:383-389): k_emit compares them while both headers pass through it;
+    // --qc_only emits nothing, so it keeps the stand-alone kernel
+    if (paired && ctx->check_pair_ids && o.qc_only) {
         k_check_pair_ids<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_r1, ctx->d_rec[0].as<Rec>(), d_r2, ctx->d_rec[1].as<Rec>(), n, info);
         ctx->launches++;
     }
@@ -456,6 +458,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     EmitArgs ea{};
     ea.n_rec = n;
     ea.n_tiles = (n + kTile - 1) / kTile;
+    ea.check_ids = paired && ctx->check_pair_ids && !o.qc_only;
     {   // rounds in which a warp stages its 32 records: the smallest split whose average slab leaves 8 % headroom
         const double avg = (double)std::max(n1, n2) / (double)std::max<uint32_t>(n, 1u);
         ea.parts = 1;

@@ -9,6 +9,7 @@
 // replacement, quality re-encoding).  Discarded reads are copied raw.
 #pragma once
 #include "fq_common.cuh"
+#include "fq_frame.cuh"
 #include "fq_trim.cuh"
 
 namespace fq {
@@ -23,6 +24,7 @@ struct EmitArgs {
     const uint8_t *canon[2];     // 1 = LF line ends + bare '+' line (raw bytes == write_read output)
     uint32_t n_rec;
     uint32_t parts;              // k_emit stages the 32 records of a warp in this many rounds (1, 2, 4, 8)
+    uint32_t check_ids;          // k_emit also compares the read ids of the two mates (FaQCs.cpp:383-389)
     uint32_t n_tiles;
     uint32_t *tile_sum;          // [4][n_tiles] -> exclusive bases after k_scan_tiles (u32: < 4 GiB per stream per batch)
     uint8_t *out[4];
@@ -399,6 +401,13 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
                 cp_async_wait_all();
                 __syncwarp();
                 src = slab - lo;
+            }
+            if (m == 1 && a.check_ids && mine) {
+                // mate 2's header sits in shared memory now; mate 1's was staged a moment ago and is read back from L2
+                if (pair_ids_differ(a.raw[0] + L.rc[0].hdr, L.rc[0].seq - L.rc[0].hdr - 1, src + M.rc.hdr, M.rc.seq - M.rc.hdr - 1)) {
+                    atomicOr(&a.info->err, kErrPairId);
+                    atomicMin(&a.info->err_record, r);
+                }
             }
             // ---- runs of untouched records of a surviving pair (or, unpaired input, of surviving reads): block copies
             const int s_main = o.paired ? m : 2;

@@ -277,15 +277,15 @@ __global__ void __launch_bounds__(256) k_detect_offset(const uint8_t *__restrict
 // parse_id(r1.def) == parse_id(r2.def) (trim.cpp:188-222, FaQCs.cpp:383-389).  One thread per pair.
 // Headers are read as aligned 32-bit words (funnel-shifted to the header start): the common
 // case -- ids equal up to the first space -- is decided after ~|id|/4 word compares.
-__device__ __forceinline__ uint32_t load_word_at(const uint8_t *p)
+__device__ __forceinline__ uint32_t load_word_at(const uint8_t *p)       // generic pointer: global or shared memory
 {
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
     const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-    const uint32_t lo = __ldg(w);
-    const uint32_t hi = sh ? __ldg(w + 1) : 0u;
+    const uint32_t lo = w[0];
+    const uint32_t hi = sh ? w[1] : 0u;
     return __funnelshift_r(lo, hi, sh);
 }
-
+// parse_id (trim.cpp:188-222): the id ends at the first space; a trailing "/1", ".2" ... is not part of it.
 __device__ __forceinline__ uint32_t id_length(const uint8_t *h, uint32_t n)
 {
     uint32_t loc = 0;
@@ -293,17 +293,11 @@ __device__ __forceinline__ uint32_t id_length(const uint8_t *h, uint32_t n)
     if (loc > 1 && h[loc - 1] >= '0' && h[loc - 1] <= '9' && (h[loc - 2] == '.' || h[loc - 2] == '/')) loc -= 2;
     return loc;
 }
-
-__global__ void __launch_bounds__(256) k_check_pair_ids(const uint8_t *__restrict__ raw1, const Rec *__restrict__ rec1,
-                                                        const uint8_t *__restrict__ raw2, const Rec *__restrict__ rec2,
-                                                        uint32_t n_rec, BatchInfo *info)
+// parse_id equality (trim.cpp:188-222, FaQCs.cpp:383-389) of two header lines of na / nb bytes (line end excluded,
+// a CR of a CRLF end possibly included).  Fast path: both headers agree word by word up to and including a space
+// (no '/1' '.1' suffix before it); the exact byte path only when a word differs before the first space.
+__device__ __forceinline__ bool pair_ids_differ(const uint8_t *ha, uint32_t na, const uint8_t *hb, uint32_t nb)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rec) return;
-    const Rec a = rec1[r], b = rec2[r];
-    uint32_t na = a.seq - a.hdr - 1, nb = b.seq - b.hdr - 1;
-    const uint8_t *ha = raw1 + a.hdr, *hb = raw2 + b.hdr;
-    // fast path: both headers agree word by word up to and including a space (no '/1' '.1' suffix before it)
     {
         const uint32_t m = min(na, nb);
         bool decided = false, same = false;
@@ -316,14 +310,23 @@ __global__ void __launch_bounds__(256) k_check_pair_ids(const uint8_t *__restric
             if (fs < fd) { same = true; decided = true; }        // identical up to and including the first space
             else if (fd < 4) decided = true;                     // differ before a space: let the exact path decide
         }
-        if (decided && same) return;
+        if (decided && same) return false;
     }
     if (na && ha[na - 1] == '\r') --na;
     if (nb && hb[nb - 1] == '\r') --nb;
     const uint32_t la = id_length(ha, na), lb = id_length(hb, nb);
     bool same = (la == lb);
     for (uint32_t i = 0; same && i < la; ++i) same = (ha[i] == hb[i]);
-    if (!same) {
+    return !same;
+}
+__global__ void __launch_bounds__(256) k_check_pair_ids(const uint8_t *__restrict__ raw1, const Rec *__restrict__ rec1,
+                                                        const uint8_t *__restrict__ raw2, const Rec *__restrict__ rec2,
+                                                        uint32_t n_rec, BatchInfo *info)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const Rec a = rec1[r], b = rec2[r];
+    if (pair_ids_differ(raw1 + a.hdr, a.seq - a.hdr - 1, raw2 + b.hdr, b.seq - b.hdr - 1)) {
         atomicOr(&info->err, kErrPairId);
         atomicMin(&info->err_record, r);
     }
