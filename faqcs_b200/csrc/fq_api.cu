@@ -485,7 +485,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         }
     }
     k_route<<<ea.n_tiles, kTile, 0, ctx->stream>>>(ea, o);
-    k_scan_tiles<<<1, 128, 0, ctx->stream>>>(ea.tile_sum, ea.n_tiles, info);
+    k_scan_tiles<<<4, 1024, 0, ctx->stream>>>(ea.tile_sum, ea.n_tiles, info);
     ctx->launches += 2;
     if (!o.qc_only) {
         CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem));

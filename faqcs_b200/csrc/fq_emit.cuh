@@ -108,14 +108,18 @@ __global__ void __launch_bounds__(kTile) k_route(const EmitArgs a, const DevOpts
     }
 }
 
-// Exclusive scan of the four tile-sum rows; totals go to info->out_bytes.  One CTA, warp w scans stream w.
-__global__ void __launch_bounds__(128) k_scan_tiles(uint32_t *tile_sum, uint32_t n_tiles, BatchInfo *info)
+// Exclusive scan of the four tile-sum rows; totals go to info->out_bytes.  One 1024-thread CTA per stream,
+// 1024 tiles per round (warp scans + a scan of the 32 warp totals).
+__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t *tile_sum, uint32_t n_tiles, BatchInfo *info)
 {
-    const uint32_t lane = threadIdx.x & 31, s = threadIdx.x >> 5;
+    __shared__ uint32_t s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, s = blockIdx.x;
     uint32_t *row = tile_sum + (size_t)s * n_tiles;
-    unsigned long long carry = 0;
-    for (uint32_t base = 0; base < n_tiles; base += 32) {
-        const uint32_t i = base + lane;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
         const uint32_t v = i < n_tiles ? row[i] : 0;
         uint32_t x = v;
 #pragma unroll
@@ -123,10 +127,25 @@ __global__ void __launch_bounds__(128) k_scan_tiles(uint32_t *tile_sum, uint32_t
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, k);
             if (lane >= (uint32_t)k) x += y;
         }
-        if (i < n_tiles) row[i] = (uint32_t)(carry + x - v);
-        carry += __shfl_sync(0xffffffffu, x, 31);
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t t = s_warp[lane];
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, t, k);
+                if (lane >= (uint32_t)k) t += y;
+            }
+            s_warp[lane] = t;
+        }
+        __syncthreads();
+        const unsigned long long before = s_carry + (wid ? s_warp[wid - 1] : 0u) + (x - v);
+        if (i < n_tiles) row[i] = (uint32_t)before;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + v;
+        __syncthreads();
     }
-    if (lane == 0) info->out_bytes[s] = carry;
+    if (threadIdx.x == 0) info->out_bytes[s] = s_carry;
 }
 
 // Warp-cooperative copy of n bytes between arbitrarily aligned addresses.  The body is written
