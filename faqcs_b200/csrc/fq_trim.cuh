@@ -897,12 +897,12 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
         // ---- phase 1: cooperative per-base pass, read by read
         const uint32_t n_here = min(32u, total - base);
         uint32_t max_row = 0;           // highest quality row any base of this group was counted in
+        const uint32_t split = base < a.n_rec ? min(32u, a.n_rec - base) : 0u;     // reads j >= split belong to mate 2
         for (uint32_t j = 0; j < n_here; ++j) {
             const uint32_t len = __shfl_sync(0xffffffffu, me.rc.len, j);
             const uint32_t seq = __shfl_sync(0xffffffffu, me.rc.seq, j);
             const uint32_t qual = __shfl_sync(0xffffffffu, me.rc.qual, j);
-            const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
-            const uint32_t rj = base + j - mj * a.n_rec;
+            const uint32_t mj = j >= split ? 1 : 0;
             const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
             int s_sum = 0;
             uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
             else if (len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
             else {
                 const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
-                process_generic(kc, mj, rj, rcj);
+                process_generic(kc, mj, base + j - mj * a.n_rec, rcj);
                 generic = true;
             }
             if (lane == j) {
