@@ -193,6 +193,29 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Several ranks per host: run this rank (and allocate its pinned buffers) on the CPUs next to its GPU, so the
+    end-to-end leg's H2D / D2H traffic does not cross sockets.  Returns the previous affinity (restored before the
+    reference binary is timed on all cores) or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return old
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,6 +248,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: faqcs_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity0 = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -393,6 +417,8 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline:
+            if affinity0:
+                os.sched_setaffinity(0, affinity0)
             line["cpu_baseline"] = cpu_baseline(args.cpu_pairs)
         print(json.dumps(line))
     eng.close()
