@@ -443,13 +443,16 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         rows = std::min(rows, ctx->L.rows);
         ta.smem_rows = rows;
         const size_t smem = SmemHist::words(rows, ta.comp_key_len) * 4;
-        CK(cudaFuncSetAttribute(k_trim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // instance with only the phase-1 width(s) this batch needs (smaller hot loop)
+        using TrimKernel = void (*)(const TrimArgs, const DevOpts);
+        const TrimKernel kern = max_len <= 128 ? (TrimKernel)k_trim<4> : max_len <= 160 ? (TrimKernel)k_trim<5> : (TrimKernel)k_trim<0>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int threads = kTrimThreads;
         int per_sm = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trim, threads, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         per_sm = std::max(per_sm, 1);
         const int grid = std::max(1, std::min<int>((n * n_mates + 15) / 16, ctx->sm_count * per_sm));
-        k_trim<<<grid, threads, smem, ctx->stream>>>(ta, o);
+        kern<<<grid, threads, smem, ctx->stream>>>(ta, o);
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -855,6 +855,11 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
 #endif
 constexpr int kTrimThreads = FQ_TRIM_THREADS;
 
+// KSEL: which register-resident phase-1 widths this instance carries (the host picks it from the batch's longest read):
+//   4: reads <= 128 bases, 5: reads <= 160 bases, 0: all widths (4, 5 and 10 chunks of 32 bases).  Longer reads always
+//   take the chunked generic path.  Specialised instances keep the hot loop small: the kernel is issue-bound and its
+//   instruction-cache misses are measurable (C2: 1.50 -> 1.46 ms without the unused widths).
+template <int KSEL>
 __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const TrimArgs a, const DevOpts o)
 {
     SmemHist H{a.smem_rows, a.comp_key_len};
@@ -907,9 +912,9 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
             int s_sum = 0;
             uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
             bool generic = false;
-            if (len <= 128 && len <= R) phase1<4>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else if (len <= 160 && len <= R) phase1<5>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else if (len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            if ((KSEL == 0 || KSEL == 4) && len <= 128 && len <= R) phase1<4>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            else if ((KSEL == 0 || KSEL == 5) && len <= 160 && len <= R) phase1<5>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            else if (KSEL == 0 && len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
             else {
                 const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
                 process_generic(kc, mj, base + j - mj * a.n_rec, rcj);
