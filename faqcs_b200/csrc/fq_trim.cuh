@@ -859,9 +859,21 @@ constexpr int kTrimThreads = FQ_TRIM_THREADS;
 //   4: reads <= 128 bases, 5: reads <= 160 bases, 0: all widths (4, 5 and 10 chunks of 32 bases).  Longer reads always
 //   take the chunked generic path.  Specialised instances keep the hot loop small: the kernel is issue-bound and its
 //   instruction-cache misses are measurable (C2: 1.50 -> 1.46 ms without the unused widths).
-template <int KSEL>
-__global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const TrimArgs a, const DevOpts o)
+// PLAIN: the option set of a default run (BWA_plus, no 5'/3' clip, no adapters, no G->N replacement, no re-encoding,
+//   not --qc_only) is baked in, so every branch on those options disappears from the instance.
+template <int KSEL, bool PLAIN>
+__global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const TrimArgs a, const DevOpts o_in)
 {
+    DevOpts o = o_in;
+    if (PLAIN) {
+        o.mode = FQ_MODE_BWA_PLUS;
+        o.trim_5 = 0;
+        o.trim_3 = 0;
+        o.replace_q = 0;
+        o.qc_only = 0;
+        o.filter_adapter = 0;
+        o.out_off = o.in_off;
+    }
     SmemHist H{a.smem_rows, a.comp_key_len};
     const size_t n_words = SmemHist::words(a.smem_rows, a.comp_key_len);
     for (size_t i = threadIdx.x; i < n_words; i += blockDim.x) g_smem[i] = 0;
