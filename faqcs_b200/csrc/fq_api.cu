@@ -493,8 +493,10 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     k_scan_tiles<<<4, 1024, 0, ctx->stream>>>(ea.tile_sum, ea.n_tiles, info);
     ctx->launches += 2;
     if (!o.qc_only) {
-        CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem));
-        k_emit<<<ea.n_tiles, kTile, kEmitSmem, ctx->stream>>>(ea, o);
+        using EmitKernel = void (*)(const EmitArgs, const DevOpts);
+        const EmitKernel kern = (!o.replace_q && o.in_off == o.out_off) ? (EmitKernel)k_emit<true> : (EmitKernel)k_emit<false>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem));
+        kern<<<ea.n_tiles, kTile, kEmitSmem, ctx->stream>>>(ea, o);
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));

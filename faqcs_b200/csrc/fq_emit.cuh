@@ -345,8 +345,16 @@ extern __shared__ __align__(16) uint8_t g_emit_smem[];
 #ifndef FQ_EMIT_MIN_CTAS
 #define FQ_EMIT_MIN_CTAS 2
 #endif
-__global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs a, const DevOpts o)
+// PLAIN: no quality re-encoding and no G->N replacement (the default run): those branches of write_trimmed are compiled out.
+template <bool PLAIN>
+__global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs a, const DevOpts o_in)
 {
+    DevOpts o = o_in;
+    if (PLAIN) {
+        o.replace_q = 0;
+        o.out_off = o.in_off;
+        o.qc_only = 0;
+    }
     __shared__ uint32_t s_wsum[4][kTile / 32];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kTile + threadIdx.x;
