@@ -446,8 +446,10 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         // instance with only the phase-1 width(s) this batch needs (smaller hot loop)
         using TrimKernel = void (*)(const TrimArgs, const DevOpts);
         const bool plain = o.mode == FQ_MODE_BWA_PLUS && !o.trim_5 && !o.trim_3 && !o.replace_q && !o.qc_only && !o.filter_adapter && o.in_off == o.out_off;
-        const TrimKernel kern = plain ? (max_len <= 128 ? (TrimKernel)k_trim<4, true> : max_len <= 160 ? (TrimKernel)k_trim<5, true> : (TrimKernel)k_trim<0, true>)
-                                      : (max_len <= 128 ? (TrimKernel)k_trim<4, false> : max_len <= 160 ? (TrimKernel)k_trim<5, false> : (TrimKernel)k_trim<0, false>);
+        // width-specialised instances have no generic path: every read of the batch must fit the shared-memory rows
+        const int ksel = rows < max_len ? 0 : max_len <= 128 ? 4 : max_len <= 160 ? 5 : 0;
+        const TrimKernel kern = plain ? (ksel == 4 ? (TrimKernel)k_trim<4, true> : ksel == 5 ? (TrimKernel)k_trim<5, true> : (TrimKernel)k_trim<0, true>)
+                                      : (ksel == 4 ? (TrimKernel)k_trim<4, false> : ksel == 5 ? (TrimKernel)k_trim<5, false> : (TrimKernel)k_trim<0, false>);
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int threads = kTrimThreads;
         int per_sm = 1;

@@ -924,9 +924,13 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
             int s_sum = 0;
             uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
             bool generic = false;
-            if ((KSEL == 0 || KSEL == 4) && len <= 128 && len <= R) phase1<4>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else if ((KSEL == 0 || KSEL == 5) && len <= 160 && len <= R) phase1<5>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else if (KSEL == 0 && len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            // KSEL 4 / 5: the host launches these instances only for batches whose longest read fits the width, so
+            // the generic path (and its code) is not part of them
+            if (KSEL == 4) phase1<4>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            else if (KSEL == 5) phase1<5>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            else if (len <= 128 && len <= R) phase1<4>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            else if (len <= 160 && len <= R) phase1<5>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
+            else if (len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
             else {
                 const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
                 process_generic(kc, mj, base + j - mj * a.n_rec, rcj);
