@@ -344,6 +344,15 @@ public:
     }
 };
 
+constexpr int kIoThreads = 4;      // pread threads per plain input file (writes to one file serialise on its inode lock)
+
+static size_t count_newlines(const uint8_t *buf, size_t n)
+{
+    size_t c = 0;
+    for (size_t i = 0; i < n; ++i) c += buf[i] == '\n';      // vectorised by the compiler
+    return c;
+}
+
 // ---- input: gz or plain, whole records per batch -------------------------------------------------
 // Plain files are read with read(2) straight into the pinned batch buffer; gzip input (magic 1f 8b) goes
 // through zlib like the reference's reader (fastq.cpp:8-30).
@@ -363,6 +372,7 @@ struct Source {
             if (!gz) return false;
             gzbuffer(gz, 1 << 20);
         }
+        detect_sliced();
         return true;
     }
     void close()
@@ -372,10 +382,50 @@ struct Source {
         gz = nullptr;
         fd = -1;
     }
-    // append to buf[have..cap); returns the bytes now in buf
-    size_t fill(uint8_t *buf, size_t have, size_t cap)
+    // Regular plain file: the byte range of a batch is known up front, so it is read by kIoThreads threads with
+    // pread into disjoint slices of the buffer (a single read(2) stream is a single-core page-cache copy).
+    bool sliced = false;
+    off_t pos = 0, size = 0;
+    void detect_sliced()
+    {
+        struct stat st;
+        if (!gz && fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) { sliced = true; size = st.st_size; pos = 0; }
+    }
+    // append to buf[have..cap); returns the bytes now in buf and the newlines in the appended part
+    size_t fill(uint8_t *buf, size_t have, size_t cap, size_t *new_lines)
     {
         size_t n = have;
+        if (sliced) {
+            const size_t want = (size_t)min<off_t>((off_t)(cap - have), size - pos);
+            const int nt = want >= (8u << 20) ? kIoThreads : 1;
+            const size_t per = (want + nt - 1) / nt;
+            vector<thread> th;
+            vector<size_t> lines(nt, 0);
+            vector<int> bad(nt, 0);
+            for (int t = 0; t < nt; ++t) {
+                const size_t lo = min(want, per * t), hi = min(want, per * (t + 1));
+                auto job = [this, buf, have, lo, hi, t, &lines, &bad] {
+                    size_t done = lo;
+                    while (done < hi) {
+                        const ssize_t got = pread(fd, buf + have + done, hi - done, pos + (off_t)done);
+                        if (got < 0 && errno == EINTR) continue;
+                        if (got <= 0) { bad[t] = 1; return; }       // the file shrank or an I/O error
+                        done += (size_t)got;
+                    }
+                    lines[t] = count_newlines(buf + have + lo, hi - lo);
+                };
+                if (t + 1 < nt) th.emplace_back(job); else job();
+            }
+            for (thread &x : th) x.join();
+            for (int t = 0; t < nt; ++t) {
+                if (bad[t]) throw "fastq.cpp:next_read: Unable to read header";
+                *new_lines += lines[t];
+            }
+            pos += (off_t)want;
+            n += want;
+            if (pos >= size) eof = true;
+            return n;
+        }
         while (!eof && n < cap) {
             const size_t want = min<size_t>(cap - n, 1u << 30);
             const ssize_t got = gz ? (ssize_t)gzread(gz, buf + n, (unsigned)want) : ::read(fd, buf + n, want);
@@ -386,16 +436,11 @@ struct Source {
             if (got == 0) { eof = true; break; }
             n += (size_t)got;
         }
+        *new_lines += count_newlines(buf + have, n - have);
         return n;
     }
 };
 
-static size_t count_newlines(const uint8_t *buf, size_t n)
-{
-    size_t c = 0;
-    for (size_t i = 0; i < n; ++i) c += buf[i] == '\n';      // vectorised by the compiler
-    return c;
-}
 // offset just past the keep-th of the `total` newlines in buf[0..n): walks back from the end
 static size_t offset_after_line(const uint8_t *buf, size_t n, size_t total, size_t keep)
 {
@@ -448,7 +493,6 @@ static void write_all(int fd, const uint8_t *p, size_t n)
         n -= (size_t)w;
     }
 }
-
 static double now_s() { return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // process_paired (FaQCs.cpp:153-538) / process_unpaired (:540-757): read -> GPU -> four ordered writers.
@@ -488,8 +532,9 @@ static void process(Run &R, bool paired)
         Worker readers[2], writers[4];
         auto post_fill = [&](int slot, int m, size_t have) {
             readers[m].post([&, slot, m, have] {
-                filled[m].n = src[m].fill(buf[slot][m], have, cap);
-                filled[m].lines = count_newlines(buf[slot][m], filled[m].n);
+                size_t lines = count_newlines(buf[slot][m], have);        // the carried tail
+                filled[m].n = src[m].fill(buf[slot][m], have, cap, &lines);
+                filled[m].lines = lines;
             });
         };
         for (int m = 0; m < n_mates; ++m) post_fill(0, m, 0);
