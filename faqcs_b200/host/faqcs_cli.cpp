@@ -8,6 +8,7 @@
 //   faqcs_b200 -1 r1.fq -2 r2.fq -d outdir [FaQCs flags]        extra: --device N, --batch_mb N
 #include <fcntl.h>
 #include <getopt.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -344,7 +345,13 @@ public:
     }
 };
 
-constexpr int kIoThreads = 4;      // pread threads per plain input file (writes to one file serialise on its inode lock)
+constexpr int kIoThreads = 4;      // threads per plain input file (pread slices) and per output file (mapped copies)
+// transfers below this size use plain read(2) / write(2); FAQCS_B200_IO_SLICE_MIN overrides it (the tests use a tiny value)
+static size_t io_slice_min()
+{
+    static const size_t v = [] { const char *e = getenv("FAQCS_B200_IO_SLICE_MIN"); return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(8u << 20); }();
+    return v;
+}
 
 static size_t count_newlines(const uint8_t *buf, size_t n)
 {
@@ -397,7 +404,7 @@ struct Source {
         size_t n = have;
         if (sliced) {
             const size_t want = (size_t)min<off_t>((off_t)(cap - have), size - pos);
-            const int nt = want >= (8u << 20) ? kIoThreads : 1;
+            const int nt = want >= io_slice_min() && want >= (size_t)kIoThreads ? kIoThreads : 1;
             const size_t per = (want + nt - 1) / nt;
             vector<thread> th;
             vector<size_t> lines(nt, 0);
@@ -477,7 +484,7 @@ struct Run {
 
 static int open_out(const string &fn, const char *what)
 {
-    const int fd = ::open(fn.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    const int fd = ::open(fn.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);      // O_RDWR: shared mappings need read access
     if (fd < 0) { cerr << "Unable to open " << fn << " for writing " << what << endl; throw "I/O error"; }
     return fd;
 }
@@ -493,6 +500,37 @@ static void write_all(int fd, const uint8_t *p, size_t n)
         n -= (size_t)w;
     }
 }
+// Large appends to a regular file: reserve the range (posix_fallocate reports a full disk as an error instead of a
+// SIGBUS later), map it and let kIoThreads threads copy disjoint slices -- write(2) calls on one file serialise on its
+// inode lock, page faults into a shared mapping do not.  Anything unusual falls back to write(2).
+static void write_mapped(int fd, const uint8_t *p, size_t n)
+{
+    struct stat st;
+    const off_t base = lseek(fd, 0, SEEK_CUR);
+    if (n < io_slice_min() || n < (size_t)kIoThreads || base < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size != base) { write_all(fd, p, n); return; }
+    if (posix_fallocate(fd, base, (off_t)n) != 0) { write_all(fd, p, n); return; }
+    const long page = sysconf(_SC_PAGESIZE);
+    const off_t map_off = base / page * page;
+    const size_t lead = (size_t)(base - map_off), map_len = lead + n;
+    void *m = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, map_off);
+    if (m == MAP_FAILED) {
+        if (ftruncate(fd, base) != 0) throw "I/O error while writing the trimmed reads";
+        write_all(fd, p, n);
+        return;
+    }
+    uint8_t *dst = (uint8_t *)m + lead;
+    const size_t per = (n + kIoThreads - 1) / kIoThreads;
+    vector<thread> th;
+    for (int t = 0; t < kIoThreads; ++t) {
+        const size_t lo = min(n, per * t), hi = min(n, per * (t + 1));
+        auto job = [dst, p, lo, hi] { memcpy(dst + lo, p + lo, hi - lo); };
+        if (t + 1 < kIoThreads) th.emplace_back(job); else job();
+    }
+    for (thread &x : th) x.join();
+    munmap(m, map_len);
+    lseek(fd, base + (off_t)n, SEEK_SET);
+}
+
 static double now_s() { return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // process_paired (FaQCs.cpp:153-538) / process_unpaired (:540-757): read -> GPU -> four ordered writers.
@@ -548,7 +586,7 @@ static void process(Run &R, bool paired)
                     const uint8_t *p = out.data[s];
                     const size_t n = out.bytes[s];
                     const int fd = fout[s];
-                    writers[s].post([fd, p, n] { write_all(fd, p, n); });
+                    writers[s].post([fd, p, n] { write_mapped(fd, p, n); });
                 }
         };
         for (int slot = 0;; slot ^= 1) {

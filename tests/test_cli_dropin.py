@@ -20,7 +20,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refcli.have_ref(), reason=
               pytest.mark.skipif(not os.path.exists(CLI), reason="CLI not built")]
 
 
-def run_both(inputs, flags, threads=2, extra_cli=()):
+def run_both(inputs, flags, threads=2, extra_cli=(), env=None):
     tmp = tempfile.mkdtemp(prefix="faqcs_cli_")
     try:
         args = []
@@ -36,7 +36,8 @@ def run_both(inputs, flags, threads=2, extra_cli=()):
         for tag, exe, more in (("ref", refcli.REF_BIN, []), ("gpu", CLI, list(extra_cli))):
             out = os.path.join(tmp, tag)
             p = subprocess.run([exe, "-d", out, "-t", str(threads), "--debug"] + args + list(flags) + more, stdout=subprocess.PIPE,
-                               stderr=subprocess.PIPE, preexec_fn=lambda: signal.signal(signal.SIGPIPE, signal.SIG_IGN))
+                               stderr=subprocess.PIPE, preexec_fn=lambda: signal.signal(signal.SIGPIPE, signal.SIG_IGN),
+                               env=dict(os.environ, **(env or {})))
             assert p.returncode == 0, (tag, p.stderr.decode(errors="replace")[-600:])
             outs[tag] = {n: open(os.path.join(out, n), "rb").read() for n in sorted(os.listdir(out)) if not n.endswith(".pdf")}
         return outs
@@ -71,6 +72,15 @@ def test_paired_mates_of_different_length_many_batches():
         short += rec[i] + b"\n" + rec[i + 1][:90] + b"\n+\n" + rec[i + 3][:90] + b"\n"
     outs = run_both({"-1": ("r1.fq.gz", w.r1), "-2": ("r2.fq", np.frombuffer(bytes(short), dtype=np.uint8))}, ["--discard"], threads=3,
                     extra_cli=["--batch_mb", "1"])
+    assert_same_files(outs)
+
+
+def test_parallel_io_paths_small_input():
+    """The multi-threaded pread reader and the mapped multi-threaded writer normally engage above 8 MiB per transfer;
+    here they are forced on for a small input (many batches, ragged slices) and must leave the same files."""
+    w = synth.c2(30000)
+    outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, ["--discard", "-q", "20"], threads=2,
+                    extra_cli=["--batch_mb", "2"], env={"FAQCS_B200_IO_SLICE_MIN": "1000"})
     assert_same_files(outs)
 
 
