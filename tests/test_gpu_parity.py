@@ -6,7 +6,7 @@ import pytest
 
 import refcli
 from faqcs_b200 import synth
-from faqcs_b200.api import (BUILTIN_ADAPTERS, MODE_BWA, MODE_HARD, OFFSET_AUTO, POLYA_ADAPTER, Engine, FaqcsError,
+from faqcs_b200.api import (BUILTIN_ADAPTERS, MODE_BWA, MODE_HARD, OFFSET_AUTO, POLYA_ADAPTER, Engine, FaqcsError, Stats,
                             Options)
 from faqcs_b200.synth import fastq_bytes
 from oracle_binding import OracleEngine
@@ -242,3 +242,44 @@ def test_randomized_options_and_reads(seed):
     # (thread-count emulation, SURVEY Q3, needs 32768-record batch boundaries: adapter runs stay single-batch)
     batch = None if kw.get("filter_adapter") else (int(rng.choice([0, 257])) or None)
     both(r1, r2, lambda: Options(**kw), batch_records=batch)
+
+
+def test_full_batch_size_properties():
+    """BASELINE-size batch (2 M pairs = 4 M reads in one call, the bench's step): properties that do not need the oracle.
+    Linearity: a batch made of 8 copies of a 250 k-pair block must give exactly 8 x the block's statistics and 8 x its
+    output bytes (checksum of checksums); conservation: every base is either kept or accounted to exactly one filter /
+    trimming counter, and the position matrices add up to the base counters."""
+    import hashlib
+    w = synth.c2(250_000)
+    reps = 8
+    with Engine(Options(discard_output=True)) as one, Engine(Options(discard_output=True)) as many:
+        one.autodetect(w.r1, w.r2)
+        many.autodetect(w.r1, w.r2)
+        a = one.process(w.r1, w.r2)
+        b = many.process(np.tile(w.r1, reps), np.tile(w.r2, reps))
+        sa, sb = one.stats(), many.stats()
+    assert b.n_records == reps * a.n_records
+    for s in range(4):
+        assert len(b.streams[s]) == reps * len(a.streams[s])
+        block = hashlib.sha256(a.streams[s]).digest()
+        n = len(a.streams[s])
+        for k in range(reps):            # every copy emits the same bytes at k x the block's offset
+            assert hashlib.sha256(b.streams[s][k * n:(k + 1) * n]).digest() == block, (s, k)
+    for f in Stats.FIELDS:
+        x, y = getattr(sa, f), getattr(sb, f)
+        assert x.shape == y.shape and np.array_equal(reps * x.astype(np.int64), y.astype(np.int64)), f
+    fs = sb.filter_stats.astype(np.int64)
+    T = {n: i for i, n in enumerate(["TOTAL_COUNT", "TOTAL_NUMBER", "TOTAL_LENGTH", "TRIMMED_NUMBER", "TRIMMED_LENGTH", "PAIRED_NUMBER",
+                                    "PAIRED_LENGTH", "READ_LENGTH", "BASE_LENGTH", "READ_NN", "BASE_NN", "READ_PHIX", "BASE_PHIX",
+                                    "READ_ADAPTER", "BASE_ADAPTER", "READ_AVG_Q", "BASE_AVG_Q", "READ_QUAL_TRIM", "BASE_QUAL_TRIM",
+                                    "READ_LC", "BASE_LC"])}
+    assert fs[T["TOTAL_NUMBER"]] == 2 * b.n_records and fs[T["TOTAL_LENGTH"]] == 150 * fs[T["TOTAL_NUMBER"]]
+    # reads: kept + one counter per discarded read; bases: kept + quality-trimmed + the bases of discarded reads
+    assert fs[T["TRIMMED_NUMBER"]] + fs[T["READ_LENGTH"]] + fs[T["READ_NN"]] + fs[T["READ_AVG_Q"]] + fs[T["READ_LC"]] == fs[T["TOTAL_NUMBER"]]
+    assert (fs[T["TRIMMED_LENGTH"]] + fs[T["BASE_QUAL_TRIM"]] + fs[T["BASE_LENGTH"]] + fs[T["BASE_NN"]] + fs[T["BASE_AVG_Q"]]
+            + fs[T["BASE_LC"]] == fs[T["TOTAL_LENGTH"]])
+    assert int(sb.pre_quality_matrix.sum()) == fs[T["TOTAL_LENGTH"]] == int(sb.pre_base_matrix.sum())
+    assert int(sb.post_quality_matrix.sum()) == fs[T["TRIMMED_LENGTH"]] == int(sb.post_base_matrix.sum())
+    assert int(sb.pre_length_hist.sum()) == fs[T["TOTAL_NUMBER"]] and int(sb.post_length_hist.sum()) == fs[T["TRIMMED_NUMBER"]]
+    assert int(sb.pre_read_quality_hist.sum()) == fs[T["TOTAL_NUMBER"]] and int(sb.post_base_quality_hist.sum()) == fs[T["TRIMMED_LENGTH"]]
+    assert sum(b.n_valid) == fs[T["TRIMMED_NUMBER"]] and b.paired_read_number == fs[T["PAIRED_NUMBER"]]
