@@ -224,8 +224,23 @@ __global__ void __launch_bounds__(256) k_build_records(const LineIndex li, uint3
     bool bad = false;
     if (r < n_rec) {
         uint32_t s = s_seg;
-        const uint32_t hdr = r ? (li.at(4 * r - 1, s) & kNlPosMask) + 1 : 0;
-        const uint32_t ex = li.at(4 * r, s), ey = li.at(4 * r + 1, s), ez = li.at(4 * r + 2, s), ew = li.at(4 * r + 3, s);
+        uint32_t hdr, ex, ey, ez, ew;
+        {
+            // the five line-index entries of a record (the end of the previous record's last line and its own four
+            // line ends) are consecutive inside one segment except at segment boundaries: locate the segment once,
+            // then five independent loads
+            const uint32_t g0 = r ? 4 * r - 1 : 0, g4 = 4 * r + 3;
+            while (g0 >= li.seg_base[s + 1]) ++s;
+            const uint32_t b0 = li.seg_base[s], b1 = li.seg_base[s + 1];
+            if (g4 < b1) {
+                const uint32_t *p = li.nl_seg + (size_t)s * li.seg_cap + (g0 - b0);
+                if (r) { hdr = (p[0] & kNlPosMask) + 1; ++p; } else hdr = 0;
+                ex = p[0]; ey = p[1]; ez = p[2]; ew = p[3];
+            } else {
+                hdr = r ? (li.at(4 * r - 1, s) & kNlPosMask) + 1 : 0;
+                ex = li.at(4 * r, s); ey = li.at(4 * r + 1, s); ez = li.at(4 * r + 2, s); ew = li.at(4 * r + 3, s);
+            }
+        }
         const uint32_t p0 = ex & kNlPosMask, p1 = ey & kNlPosMask, p2 = ez & kNlPosMask, p3 = ew & kNlPosMask;
         const uint32_t seq = p0 + 1, plus = p1 + 1, qual = p2 + 1;
         // a '\r' right before the '\n' belongs to the line end only if the line is not empty
