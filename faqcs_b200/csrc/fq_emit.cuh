@@ -1,12 +1,13 @@
 // fq_emit.cuh -- pair routing and in-order stream compaction
 // (FaQCs.cpp:296-361,431-496 paired; :634-659,696-720 unpaired; write_read, fastq.cpp:127-138).
 //
-// Three steps: k_route sums the emitted bytes of each 256-record tile for the
-// four streams, k_scan_tiles turns the tile sums into tile bases, k_emit
-// recomputes the per-record sizes, scans them inside the tile and has one warp
-// per record copy `def\nseq\n+\nqual\n` to its final position, applying the
-// mutations trim_read leaves in the read (terminal-N quality mask, G->N
-// replacement, quality re-encoding).  Discarded reads are copied raw.
+// Three steps: k_route sums the emitted bytes of each 256-record tile for the four streams, k_scan_tiles turns
+// the tile sums into tile bases, k_emit recomputes the per-record sizes and scans them inside the tile.  Each
+// k_emit warp owns 32 consecutive records: it stages their contiguous raw slab in shared memory (cp.async), then
+// copies runs of untouched records as block copies and writes the other records `def\nseq\n+\nqual\n` piecewise,
+// applying the mutations trim_read leaves in the read (terminal-N quality mask, G->N replacement, quality
+// re-encoding).  Discarded reads are copied raw.  The read-id comparison of the two mates (FaQCs.cpp:383-389)
+// rides along while both headers pass through the kernel.
 #pragma once
 #include "fq_common.cuh"
 #include "fq_frame.cuh"

@@ -1,9 +1,10 @@
 // fq_frame.cuh -- FASTQ record framing on the device.
 //
-// Replaces the line scanning half of next_read (fastq.cpp:32-122): the byte scan
-// for '\n' (gzgets) and '\r' (strpbrk), four lines per record, |seq| == |qual|.
-// HBM-bound byte work: 16-byte vector loads, one warp per 4 KiB chunk, SIMD byte
-// compares (__vcmpeq4), warp-shuffle scans.  No shared memory needed.
+// Replaces the line scanning half of next_read (fastq.cpp:32-122): the byte scan for '\n' (gzgets) and '\r'
+// (strpbrk), four lines per record, |seq| == |qual|.  Byte work: every resident warp streams its own contiguous
+// segment of the input 4 KiB at a time, each lane scanning 128 contiguous bytes with exact SWAR zero-byte masks;
+// one warp scan per chunk ranks the newlines, and the result is a segmented line index that k_build_records turns
+// into record descriptors without touching the raw bytes again.
 #pragma once
 #include "fq_common.cuh"
 

@@ -1,18 +1,18 @@
 // fq_trim.cuh -- the per-read trim / filter / statistics kernel (trim_read, trim.cpp:225-551).
 //
-// One warp per read, lanes striped over consecutive base positions (lane l holds
-// positions l, l+32, ...), persistent grid.  Reads of up to 320 bases take a
-// register-resident fast path (process_fast<K>: the whole read is loaded once,
-// byte-striped, and every later phase works from registers); longer reads take
-// process_generic, which re-reads global memory chunk by chunk.
+// Persistent grid, one 1024-thread CTA per SM.  A warp takes 32 reads at a time.  Phase 1 walks them one by one
+// with the lanes striped over consecutive base positions (lane l holds positions l, l+32, ...): reads of up to
+// 320 bases are register resident (phase1<K>, K chunks of 32 bases, branch-free: predicated byte loads, two
+// shared-memory LUT reads and two shared-memory reductions per base); longer reads take process_generic, which
+// re-reads global memory chunk by chunk.  The per-read scalar work (window, quality trimming, filters, bins,
+// verdict) then runs one lane per read, and the rare per-base follow-ups (bases trimmed away, discarded reads,
+// dinucleotide counts, exact N runs) are ballot-driven cooperative passes.
 //
-// Statistics go to shared-memory privatised histograms stored transposed
-// ([column][position], rows % 32 == 0) so that a warp's 32 consecutive positions
-// always fall into 32 distinct banks; they are merged into the global u64 block
-// once per CTA.  The post-trim matrices are accumulated as "pre minus removed"
-// (see StatsLayout), so an untrimmed surviving read costs one histogram update
-// per base.  Base letters are classified through a 256-entry shared-memory LUT,
-// per-read base counts are 5-bit packed per lane and reduced with REDUX.
+// Statistics go to shared-memory privatised histograms stored transposed ([column][position], rows % 32 == 0) so
+// that a warp's 32 consecutive positions always fall into 32 distinct banks; they are merged into the global u64
+// block once per CTA.  The post-trim matrices are accumulated as "pre minus removed" (see StatsLayout), so an
+// untrimmed surviving read costs one histogram update per base and matrix.  The kernel is instantiated per phase-1
+// width and for the default option set (k_trim<KSEL, PLAIN>): it is issue-bound and instruction-cache sensitive.
 #pragma once
 #include "fq_common.cuh"
 
