@@ -274,6 +274,7 @@ class Engine:
             L.fq_wait.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(CBatchOut)]
             L.fq_stats_reserve_rows.argtypes = [C.c_void_p, C.c_uint32]
             L.fq_set_check_pair_ids.argtypes = [C.c_void_p, C.c_int]
+            L.fq_set_quality.argtypes = [C.c_void_p, C.c_int32]
             L.fq_host_alloc.argtypes = [C.c_size_t]
             L.fq_host_alloc.restype = C.c_void_p
             L.fq_host_free.argtypes = [C.c_void_p]
@@ -306,6 +307,10 @@ class Engine:
     # ---- API -------------------------------------------------------------
     def set_debug_results(self, enable: bool = True):
         self._check(self._f("set_debug_results")(self.ctx, int(enable)))
+
+    def set_quality(self, quality: int):
+        """Options::quality for the following batches (the reference's NextSeq adjustment, FaQCs.cpp:272-277)."""
+        self._check(self.lib.fq_set_quality(self.ctx, int(quality)))
 
     @staticmethod
     def _buf(b):

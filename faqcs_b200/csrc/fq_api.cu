@@ -652,6 +652,14 @@ fq_status fq_set_check_pair_ids(fq_ctx *ctx, int enable)
     return FQ_OK;
 }
 
+fq_status fq_set_quality(fq_ctx *ctx, int32_t quality)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    ctx->opt.quality = quality;
+    refresh_dev_opts(ctx);
+    return FQ_OK;
+}
+
 void *fq_host_alloc(size_t bytes)
 {
     void *p = nullptr;

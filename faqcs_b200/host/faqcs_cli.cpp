@@ -600,7 +600,9 @@ static void process(Run &R, bool paired)
             if (!at_eof) {
                 const size_t r1 = filled[0].lines / 4, r2 = paired ? filled[1].lines / 4 : r1;
                 nrec = min(r1, r2);
-                if (emulate && nrec >= FQ_REF_BATCH) nrec -= nrec % FQ_REF_BATCH;
+                // whole reference batches where possible: Q3 emulation needs it, and the NextSeq re-check at the end of the
+                // input looks at the first read of the reference's final partial batch
+                if ((emulate || (int)o.quality < 20) && nrec >= FQ_REF_BATCH) nrec -= nrec % FQ_REF_BATCH;
                 if (nrec == 0) throw "record larger than the batch buffer: raise --batch_mb";
                 use1 = offset_after_line(buf[slot][0], n1, filled[0].lines, 4 * nrec);
                 if (paired) use2 = offset_after_line(buf[slot][1], n2, filled[1].lines, 4 * nrec);
@@ -624,20 +626,46 @@ static void process(Run &R, bool paired)
                 R.first_batch = false;
             }
             t_cut += now_s() - t0;
-            if (use1 || use2 || at_eof) {
+            // One piece per batch; the last batch may be cut in two at the start of the reference's final partial
+            // 32768-read batch, whose first header the reference tests for "@NS" once more (FaQCs.cpp:272-277, 613-618).
+            struct Piece { size_t o1, n1, o2, n2, nrec; bool final, recheck; };
+            Piece pieces[2] = {{0, use1, 0, use2, nrec, at_eof, false}, {}};
+            int n_pieces = 1;
+            if (at_eof && nrec && (int)o.quality < 20) {
+                const uint64_t total = first_index + nrec, rem = total % FQ_REF_BATCH;
+                if (rem && total - rem >= first_index) {            // else: that batch is empty, or began in a batch already run
+                    const size_t f_local = (size_t)(total - rem - first_index);
+                    if (f_local == 0) pieces[0].recheck = true;
+                    else {
+                        const size_t c1 = offset_of_record(buf[slot][0], use1, f_local), c2 = paired ? offset_of_record(buf[slot][1], use2, f_local) : 0;
+                        pieces[0] = Piece{0, c1, 0, c2, f_local, false, false};
+                        pieces[1] = Piece{c1, use1 - c1, c2, use2 - c2, nrec - f_local, true, true};
+                        n_pieces = 2;
+                    }
+                }
+            }
+            for (int k = 0; k < n_pieces; ++k) {
+                const Piece &pc = pieces[k];
+                if (!(pc.n1 || pc.n2 || pc.final)) continue;
+                const uint8_t *p1 = buf[slot][0] + pc.o1, *p2 = paired ? buf[slot][1] + pc.o2 : nullptr;
+                if (pc.recheck && (int)o.quality < 20 && pc.n1 >= 3 && p1[0] == '@' && p1[1] == 'N' && p1[2] == 'S') {
+                    cerr << "The input looks like NextSeq data and the quality level (-q) is adjusted to 20 for trimming." << endl;
+                    o.quality = 20;
+                    R.check(fq_set_quality(R.ctx, 20));
+                }
                 uint64_t ticket = 0;
                 // this batch's outputs reuse the host slot of the batch two tickets back: its writes must be done
                 t0 = now_s();
                 for (Worker &w : writers) w.wait_idle();
                 t_write_wait += now_s() - t0;
                 t0 = now_s();
-                R.check(fq_submit_host(R.ctx, buf[slot][0], use1, paired ? buf[slot][1] : nullptr, use2, first_index, at_eof ? 1 : 0, &ticket));
+                R.check(fq_submit_host(R.ctx, p1, pc.n1, p2, pc.n2, first_index, pc.final ? 1 : 0, &ticket));
                 R.check(fq_run(R.ctx, ticket));
                 if (have_pending) drain(pending_ticket);
                 t_gpu += now_s() - t0;
                 pending_ticket = ticket;
                 have_pending = true;
-                first_index += nrec;
+                first_index += pc.nrec;
             }
             if (at_eof) break;
         }

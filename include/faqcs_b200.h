@@ -201,6 +201,10 @@ const char *fq_last_error(const fq_ctx *ctx);   /* ctx may be NULL: last create 
 fq_status fq_set_debug_results(fq_ctx *ctx, int enable);
 /* parse_id(r1.def) == parse_id(r2.def) check of FaQCs.cpp:383-389 (on by default). */
 fq_status fq_set_check_pair_ids(fq_ctx *ctx, int enable);
+/* Change Options::quality (-q) between batches: the reference's drivers do this when a batch "looks like NextSeq data"
+ * (m_opt.quality = DEFAULT_NEXTSEQ_QUALITY_SCORE, FaQCs.cpp:272-277, 406-411, 613-618, 675-680); fq_autodetect covers the
+ * first batch, this call the re-check the reference makes on its final partial 32768-read batch. */
+fq_status fq_set_quality(fq_ctx *ctx, int32_t quality);
 
 /* Pinned host memory for the buffers handed to fq_process_host (pageable memory
  * works too, but the copies then cannot overlap and run at a fraction of PCIe speed). */

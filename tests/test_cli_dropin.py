@@ -84,6 +84,26 @@ def test_parallel_io_paths_small_input():
     assert_same_files(outs)
 
 
+def test_nextseq_recheck_on_the_final_partial_batch():
+    """FaQCs.cpp:272-277 / 613-618: at the end of the input the reference tests the first header of its final partial
+    32768-read batch for "@NS" again and, if it matches, trims that batch with -q 20.  Record 32768 of this input starts
+    with "@NS" while the file does not: only the last 432 pairs are trimmed at Q20."""
+    n = 33200
+    w = synth.c2(n)
+    def mark(buf):
+        b = bytearray(bytes(buf))
+        rec = len(b) // n                       # fixed-width synthetic records
+        assert b[32768 * rec:32768 * rec + 4] == b"@SYN"
+        b[32768 * rec + 1:32768 * rec + 3] = b"NS"
+        return np.frombuffer(bytes(b), dtype=np.uint8)
+    r1, r2 = mark(w.r1), mark(w.r2)
+    outs = run_both({"-1": ("r1.fq", r1), "-2": ("r2.fq", r2)}, ["--discard"], threads=2)
+    assert_same_files(outs)
+    assert b"-q 20" in outs["ref"]["QC.stats.txt"] or b"20" in outs["ref"]["QC.stats.txt"]
+    # the same through the single-end driver, small batches: the cut at record 32768 falls inside the last device batch
+    assert_same_files(run_both({"-u": ("u.fq", r1)}, [], threads=2, extra_cli=["--batch_mb", "8"]))
+
+
 def test_unpaired_gz_ascii64_hard():
     w = synth.c5(20000)
     outs = run_both({"-u": ("u.fq.gz", w.r1)}, ["--mode", "HARD", "-q", "20", "--avg_q", "25", "--replace_to_N_q", "10", "--discard"])
