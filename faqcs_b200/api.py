@@ -253,6 +253,7 @@ class Engine:
         getattr(L, p + "destroy").argtypes = [C.c_void_p]
         getattr(L, p + "destroy").restype = None
         getattr(L, p + "set_debug_results").argtypes = [C.c_void_p, C.c_int]
+        getattr(L, p + "set_quality").argtypes = [C.c_void_p, C.c_int32]
         getattr(L, p + "autodetect").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         getattr(L, p + "process_host").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
@@ -274,7 +275,6 @@ class Engine:
             L.fq_wait.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(CBatchOut)]
             L.fq_stats_reserve_rows.argtypes = [C.c_void_p, C.c_uint32]
             L.fq_set_check_pair_ids.argtypes = [C.c_void_p, C.c_int]
-            L.fq_set_quality.argtypes = [C.c_void_p, C.c_int32]
             L.fq_host_alloc.argtypes = [C.c_size_t]
             L.fq_host_alloc.restype = C.c_void_p
             L.fq_host_free.argtypes = [C.c_void_p]
@@ -310,7 +310,7 @@ class Engine:
 
     def set_quality(self, quality: int):
         """Options::quality for the following batches (the reference's NextSeq adjustment, FaQCs.cpp:272-277)."""
-        self._check(self.lib.fq_set_quality(self.ctx, int(quality)))
+        self._check(self._f("set_quality")(self.ctx, int(quality)))
 
     @staticmethod
     def _buf(b):

@@ -749,6 +749,14 @@ fq_status fqo_set_debug_results(fqo_ctx *ctx, int enable)
     return FQ_OK;
 }
 
+// the drivers' "looks like NextSeq data" adjustment between two trim() calls (FaQCs.cpp:272-277, 406-411, 613-618, 675-680)
+fq_status fqo_set_quality(fqo_ctx *ctx, int32_t quality)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    ctx->opt.quality = quality;
+    return FQ_OK;
+}
+
 // trim.cpp:599-617 + :619-626 and their call sites FaQCs.cpp:261-277,393-414,609-619,669-683
 fq_status fqo_autodetect(fqo_ctx *ctx, const uint8_t *r1, size_t n1, const uint8_t *r2, size_t n2,
                          int32_t *input_quality_offset, int32_t *quality)

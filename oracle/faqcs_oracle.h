@@ -22,6 +22,7 @@ fq_status   fqo_create(const fq_options *opt, fqo_ctx **out);
 void        fqo_destroy(fqo_ctx *ctx);
 const char *fqo_last_error(const fqo_ctx *ctx);
 fq_status   fqo_set_debug_results(fqo_ctx *ctx, int enable);
+fq_status   fqo_set_quality(fqo_ctx *ctx, int32_t quality);       /* m_opt.quality = ... between trim() calls, FaQCs.cpp:272-277 */
 fq_status   fqo_autodetect(fqo_ctx *ctx, const uint8_t *r1, size_t n1,
                            const uint8_t *r2, size_t n2,
                            int32_t *input_quality_offset, int32_t *quality);

@@ -283,3 +283,22 @@ def test_full_batch_size_properties():
     assert int(sb.pre_length_hist.sum()) == fs[T["TOTAL_NUMBER"]] and int(sb.post_length_hist.sum()) == fs[T["TRIMMED_NUMBER"]]
     assert int(sb.pre_read_quality_hist.sum()) == fs[T["TOTAL_NUMBER"]] and int(sb.post_base_quality_hist.sum()) == fs[T["TRIMMED_LENGTH"]]
     assert sum(b.n_valid) == fs[T["TRIMMED_NUMBER"]] and b.paired_read_number == fs[T["PAIRED_NUMBER"]]
+
+
+def test_quality_change_between_batches():
+    """fq_set_quality (the drivers' NextSeq adjustment, FaQCs.cpp:272-277): the second batch is trimmed at Q20."""
+    w1, w2 = synth.c2(3000), synth.c2(2000, start=50_000)
+    outs = []
+    for cls in (OracleEngine, Engine):
+        with cls(Options(input_quality_offset=33, discard_output=True)) as eng:
+            a = eng.process(w1.r1, w1.r2, 0, False)
+            eng.set_quality(20)
+            b = eng.process(w2.r1, w2.r2, a.n_records, True)
+            outs.append(([a.streams, b.streams], eng.stats()))
+    (so, sto), (sg, stg) = outs
+    assert so == sg
+    assert not stg.diff(sto), stg.diff(sto)
+    with Engine(Options(input_quality_offset=33, discard_output=True)) as eng:       # and it does change the outcome
+        eng.process(w1.r1, w1.r2, 0, False)
+        c = eng.process(w2.r1, w2.r2, 3000, True)
+    assert c.streams != sg[1]
