@@ -416,7 +416,7 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a 1-GPU-run item (rank 0, N = 1 only)
             if affinity0:
                 os.sched_setaffinity(0, affinity0)
             line["cpu_baseline"] = cpu_baseline(args.cpu_pairs)
