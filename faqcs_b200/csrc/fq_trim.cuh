@@ -1165,10 +1165,15 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
     __syncthreads();
     auto flush = [&](const uint32_t *src, size_t dst, size_t cols, bool plus1) {
         // src is [cols][R (+1)], dst is [cols][L.rows (+1)]
-        const size_t w = R + (plus1 ? 1 : 0), W = L.rows + (plus1 ? 1 : 0);
-        for (size_t i = threadIdx.x; i < cols * w; i += blockDim.x) {
+        // every CTA walks the table from its own starting cell, so the 148 CTAs' atomics on one global cell do not
+        // arrive together (32-bit index math: the tables hold at most 42 x 1024 cells)
+        const uint32_t w = R + (plus1 ? 1u : 0u), W = L.rows + (plus1 ? 1u : 0u), total = (uint32_t)cols * w;
+        const uint32_t rot = (uint32_t)(((unsigned long long)blockIdx.x * total) / gridDim.x);
+        for (uint32_t k = threadIdx.x; k < total; k += blockDim.x) {
+            uint32_t i = k + rot;
+            if (i >= total) i -= total;
             const uint32_t v = src[i];
-            if (v) gadd(&S[dst + (i / w) * W + (i % w)], v);
+            if (v) gadd(&S[dst + (size_t)(i / w) * W + (i % w)], v);
         }
     };
     flush(H.preq(), L.pre_q, kQualCols, false);
