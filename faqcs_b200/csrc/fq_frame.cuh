@@ -95,13 +95,23 @@ __global__ void __launch_bounds__(kFrameThreads, FQ_FRAME_MIN_CTAS) k_frame_line
     const uint64_t seg_hi = min((uint64_t)n, seg_lo + seg_bytes);
     uint32_t *out = nl_seg + (size_t)w * seg_cap;
     uint32_t rank0 = 0, any_cr = 0, cr_eol = 0;
+    const bool aligned32 = (reinterpret_cast<uintptr_t>(raw) & 31u) == 0;
     for (uint64_t chunk_base = seg_lo; chunk_base < seg_hi; chunk_base += kChunkBytes) {
         // lane l owns the 128 contiguous bytes chunk_base + l*128 ..: its eight 16-byte vectors are one cache line,
         // its newline mask is 128 contiguous bits, and ranks follow from ONE warp scan of the per-lane counts
         uint32_t m16[4] = {0, 0, 0, 0};                 // two 16-bit newline masks per register, memory order
         const uint32_t lane_base = (uint32_t)chunk_base + lane * 128;         // a batch is < 1 GiB per mate
         uint4 v[8];
-        if (chunk_base + kChunkBytes <= seg_hi) {       // whole chunk inside the segment (warp-uniform): plain vector loads
+        if (chunk_base + kChunkBytes <= seg_hi && aligned32) {
+            // whole chunk inside the segment (warp-uniform): four 256-bit loads per lane (sm_100 LDG.256): each touches one
+            // 32-byte sector once -- with 128-bit loads every sector is requested twice and the kernel is L1TEX-bound
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(v[2 * k].x), "=r"(v[2 * k].y), "=r"(v[2 * k].z), "=r"(v[2 * k].w), "=r"(v[2 * k + 1].x), "=r"(v[2 * k + 1].y),
+                               "=r"(v[2 * k + 1].z), "=r"(v[2 * k + 1].w)
+                             : "l"(raw + lane_base + 32 * k));
+        } else if (chunk_base + kChunkBytes <= seg_hi) {
             const uint4 *src = reinterpret_cast<const uint4 *>(raw + lane_base);
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = __ldg(src + k);
