@@ -96,10 +96,12 @@ __global__ void __launch_bounds__(kFrameThreads, FQ_FRAME_MIN_CTAS) k_frame_line
     uint32_t *out = nl_seg + (size_t)w * seg_cap;
     uint32_t rank0 = 0, any_cr = 0, cr_eol = 0;
     const bool aligned32 = (reinterpret_cast<uintptr_t>(raw) & 31u) == 0;
+    bool cr_before = true;        // the chunk in front of the segment belongs to another warp: assume it may end in CR
     for (uint64_t chunk_base = seg_lo; chunk_base < seg_hi; chunk_base += kChunkBytes) {
         // lane l owns the 128 contiguous bytes chunk_base + l*128 ..: its eight 16-byte vectors are one cache line,
         // its newline mask is 128 contiguous bits, and ranks follow from ONE warp scan of the per-lane counts
         uint32_t m16[4] = {0, 0, 0, 0};                 // two 16-bit newline masks per register, memory order
+        uint32_t cr_chunk = 0;                          // non-zero: this lane's bytes may hold a CR
         const uint32_t lane_base = (uint32_t)chunk_base + lane * 128;         // a batch is < 1 GiB per mate
         uint4 v[8];
         if (chunk_base + kChunkBytes <= seg_hi && aligned32) {
@@ -131,18 +133,29 @@ __global__ void __launch_bounds__(kFrameThreads, FQ_FRAME_MIN_CTAS) k_frame_line
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint32_t m = eq_mask16(v[k], 0x0a0a0a0au);
-            any_cr |= has_byte(v[k].x, 0x0d0d0d0du) | has_byte(v[k].y, 0x0d0d0d0du) | has_byte(v[k].z, 0x0d0d0d0du) | has_byte(v[k].w, 0x0d0d0d0du);
+            cr_chunk |= has_byte(v[k].x, 0x0d0d0d0du) | has_byte(v[k].y, 0x0d0d0d0du) | has_byte(v[k].z, 0x0d0d0d0du) | has_byte(v[k].w, 0x0d0d0d0du);
             m16[k >> 1] |= m << (16 * (k & 1));
         }
+        any_cr |= cr_chunk;
         const uint32_t cnt = __popc(m16[0]) + __popc(m16[1]) + __popc(m16[2]) + __popc(m16[3]);
         const uint32_t incl = warp_incl_scan(cnt, lane);
         uint32_t rank = rank0 + incl - cnt;
+        // The byte in front of a newline decides two flags: "preceded by CR" and "preceded by '+'".  Loading it for every
+        // newline costs a third of the kernel's L1 requests, so: CR is only looked for when this chunk or the one before
+        // holds a CR at all (warp-uniform), and '+' only where it can matter -- a one-character line, i.e. the byte two
+        // positions back is a newline as well (kNlPlus is consulted for "+" lines of length one only).
+        const bool cr_here = __any_sync(0xffffffffu, cr_chunk != 0);
+        const bool look_cr = cr_here || cr_before;
+        cr_before = cr_here;
 #pragma unroll
         for (int w4 = 0; w4 < 4; ++w4) {
             uint32_t m = m16[w4];
+            const uint32_t two_back = (m16[w4] << 2) | (w4 ? m16[w4 ? w4 - 1 : 0] >> 30 : 3u);   // bit b: newline at b-2 (unknown across lanes: assume yes)
             while (m) {
-                const uint32_t pos = lane_base + (uint32_t)(w4 * 32) + (uint32_t)(__ffs(m) - 1);
-                const uint32_t prev = pos ? raw[pos - 1] : 0;         // L1 resident: just loaded
+                const uint32_t b = (uint32_t)(__ffs(m) - 1);
+                const uint32_t pos = lane_base + (uint32_t)(w4 * 32) + b;
+                uint32_t prev = 0;
+                if (pos && (look_cr || ((two_back >> b) & 1u))) prev = raw[pos - 1];      // L1 resident: just loaded
                 const uint32_t e = pos | (prev == '\r' ? kNlCr : 0u) | (prev == '+' ? kNlPlus : 0u);
                 cr_eol += prev == '\r';
                 if (rank < seg_cap) out[rank] = e;
