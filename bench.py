@@ -251,7 +251,10 @@ def main():
     affinity0 = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version banner / warnings to stdout by default; the contract is ONE JSON line there
+        # NCCL writes to stdout; the contract is ONE JSON line there.  NCCL_DEBUG=VERSION (this image's default) prints
+        # the version banner straight to stdout, so that level is dropped; other levels are sent to stderr.
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
