@@ -484,8 +484,9 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         ea.canon[m] = ctx->d_canon[m].as<uint8_t>();
     }
     if (!o.qc_only) {
-        // a trimmed record is never longer than its raw record, so the inputs bound the outputs
-        const size_t cap[4] = {paired ? n1 : 0, paired ? n2 : 0, paired ? std::max(n1, n2) : n1, o.discard ? n1 + n2 : 0};
+        // a trimmed record is never longer than its raw record, so the inputs bound the outputs; the unpaired stream of a
+        // paired run takes mate 1 OR mate 2 of each pair, i.e. up to sum_i max(rec1_i, rec2_i) <= n1 + n2 bytes
+        const size_t cap[4] = {paired ? n1 : 0, paired ? n2 : 0, paired ? n1 + n2 : n1, o.discard ? n1 + n2 : 0};
         for (int s = 0; s < 4; ++s) {
             if (cap[s]) CK(ctx->d_out[ctx->out_slot][s].ensure(cap[s] + 16));
             ea.out[s] = ctx->d_out[ctx->out_slot][s].as<uint8_t>();
@@ -772,6 +773,8 @@ fq_status fq_run(fq_ctx *ctx, uint64_t ticket)
     fq_ctx::Submitted &p = ctx->sub[slot];
     if (!p.busy || p.ticket != ticket) return fail(ctx, FQ_ERR_STATE, "fq_run: unknown or already processed ticket");
     if (ctx->fin[slot].busy) return fail(ctx, FQ_ERR_STATE, "fq_run: the outputs of the ticket two submissions ago have not been collected with fq_wait");
+    // the per-read debug verdicts live in one buffer per mate, not one per output slot
+    if (ctx->debug_results) return fail(ctx, FQ_ERR_STATE, "fq_run: per-read debug results are only available through the synchronous entry points");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
     ctx->out_slot = slot;

@@ -298,13 +298,13 @@ static void parse_options(int argc, char *argv[], Cli &o)
 // ---- host pipeline: reader threads -> GPU -> writer threads --------------------
 // A worker thread that runs posted jobs in order; wait_idle() rethrows the first error a job raised.
 class Worker {
-    thread th;
     mutex mu;
     condition_variable cv, cv_idle;
     deque<function<void()>> jobs;
     size_t busy = 0;
     bool stop = false;
     const char *err = nullptr;
+    thread th;          // last member: the thread starts only after the state it uses is constructed
     void loop()
     {
         for (;;) {
@@ -316,7 +316,10 @@ class Worker {
                 job = move(jobs.front());
                 jobs.pop_front();
             }
-            try { job(); } catch (const char *e) { lock_guard<mutex> lk(mu); if (!err) err = e; }
+            try { job(); }
+            catch (const char *e) { lock_guard<mutex> lk(mu); if (!err) err = e; }
+            catch (const std::exception &) { lock_guard<mutex> lk(mu); if (!err) err = "I/O worker failed (std::exception)"; }
+            catch (...) { lock_guard<mutex> lk(mu); if (!err) err = "I/O worker failed"; }
             {
                 lock_guard<mutex> lk(mu);
                 --busy;
@@ -603,7 +606,14 @@ static void process(Run &R, bool paired)
                 // whole reference batches where possible: Q3 emulation needs it, and the NextSeq re-check at the end of the
                 // input looks at the first read of the reference's final partial batch
                 if ((emulate || (int)o.quality < 20) && nrec >= FQ_REF_BATCH) nrec -= nrec % FQ_REF_BATCH;
-                if (nrec == 0) throw "record larger than the batch buffer: raise --batch_mb";
+                if (nrec == 0) {
+                    // one file ran out of whole records while the other still has data: the reference's uneven-pair error (FaQCs.cpp:370-380)
+                    if (paired && ((src[0].eof && r1 == 0) || (src[1].eof && r2 == 0))) {
+                        cerr << "Did not find a match to read " << (r1 == 0 ? "two" : "one") << endl;
+                        throw "FaQCs.cppI/O error";
+                    }
+                    throw "record larger than the batch buffer: raise --batch_mb";
+                }
                 use1 = offset_after_line(buf[slot][0], n1, filled[0].lines, 4 * nrec);
                 if (paired) use2 = offset_after_line(buf[slot][1], n2, filled[1].lines, 4 * nrec);
                 // the tails open the next batch; its buffers are free (their batch has been run)

@@ -43,6 +43,20 @@ def micro_records():
     return recs
 
 
+def example_reads(*names):
+    """BASELINE configs[0] (C1): the reference tree ships only the OUTPUT of its example run
+    (example/output/QC.{1,2}.trimmed.fastq, 17 607 real HiSeq pairs, 50-100 bp; QC.unpaired.trimmed.fastq),
+    so those files are the inputs here."""
+    d = "/root/reference/example/output"
+    bufs = [np.fromfile(os.path.join(d, n), dtype=np.uint8) for n in names]
+    return synth.Workload("c1", bufs[0], bufs[1] if len(bufs) > 1 else None, [])
+
+
+# cases whose emitted streams are committed as (length, sha256) instead of bytes (fixture size)
+HASHED = {"c1_example_paired", "c1_example_unpaired", "c2_2m_pairs"}
+# cases whose INPUT is regenerated from the seeded generator at test time instead of being stored
+REGENERATED = {"c2_2m_pairs": "synth.c2(2_000_000)"}
+
 CASES = {
     # name: (workload factory, Options kwargs, reference extras)
     "c2_defaults": (lambda: synth.c2(1500), dict(discard_output=True), dict(threads=2)),
@@ -50,6 +64,14 @@ CASES = {
     "c5_hard_ascii64": (lambda: synth.c5(2500), dict(mode=MODE_HARD, quality=20, average_quality=25.0, replace_to_N_q=10,
                                                       discard_output=True), dict(threads=2)),
     "c3_adapters": (lambda: synth.c3(400), dict(filter_adapter=True, num_thread=1), dict(threads=1, polyA=True, artifacts=True)),
+    "c1_example_paired": (lambda: example_reads("QC.1.trimmed.fastq", "QC.2.trimmed.fastq"), dict(discard_output=True), dict(threads=2)),
+    "c1_example_unpaired": (lambda: example_reads("QC.unpaired.trimmed.fastq"), dict(), dict(threads=2)),
+    # BASELINE batch size: 2 M pairs = one bench step, compared through hashes of the four streams + every statistic
+    "c2_2m_pairs": (lambda: synth.c2(2_000_000), dict(discard_output=True), dict(threads=os.cpu_count() or 1)),
+    # composition-bin detector lengths: an all-one-base read lands in bin 10000 except for L = 549, 579, 587
+    "composition_detector_lengths": (lambda: synth.Workload("e16", np.frombuffer(synth.fastq_bytes(
+        [(f"@L{L}_{b}", b * L, "I" * (L - 1) + "5") for L in (3, 150, 548, 549, 550, 579, 587, 588, 1000) for b in "ACGTN"]), dtype=np.uint8), None, []),
+        dict(min_read_length=1, low_complexity_cutoff_ratio=1.0, max_num_poly_N=2000, input_quality_offset=33), dict(threads=1)),
     "micro_adapter_polya": (lambda: synth.Workload("micro", np.frombuffer(synth.fastq_bytes(micro_records()), dtype=np.uint8), None, []),
                             dict(filter_adapter=True, num_thread=1, min_read_length=1, low_complexity_cutoff_ratio=1.0, quality=10,
                                  input_quality_offset=33, discard_output=True), dict(threads=1, polyA=True)),
@@ -57,8 +79,12 @@ CASES = {
 
 
 def main():
+    import hashlib
     assert refcli.have_ref(), "build the reference first: make -C oracle ref"
+    only = set(sys.argv[1:])
     for name, (factory, okw, extra) in CASES.items():
+        if only and name not in only:
+            continue
         w = factory()
         opt = Options(**okw)
         polyA = extra.get("polyA", False)
@@ -70,13 +96,20 @@ def main():
             ref = refcli.run_reference(unpaired=w.r1, flags=flags, threads=extra["threads"], artifacts=artifacts)
         assert ref["returncode"] == 0, ref["stderr"]
         adapters = refcli.adapters_for(opt.filter_adapter, polyA, artifacts)
-        out = dict(r1=np.asarray(w.r1), r2=np.asarray(w.r2) if w.r2 is not None else np.zeros(0, np.uint8),
+        regen = name in REGENERATED
+        out = dict(r1=np.zeros(0, np.uint8) if regen else np.asarray(w.r1),
+                   r2=np.asarray(w.r2) if (w.r2 is not None and not regen) else np.zeros(0, np.uint8),
+                   generator=np.frombuffer(REGENERATED.get(name, "").encode(), dtype=np.uint8),
                    paired=np.array([w.r2 is not None]), stats_txt=np.frombuffer(ref["stats_txt"].encode(), dtype=np.uint8),
                    options=np.frombuffer(repr(okw).encode(), dtype=np.uint8),
                    adapters=np.frombuffer(repr(adapters).encode(), dtype=np.uint8),
                    cmd=np.frombuffer(" ".join(["FaQCs"] + flags + ["-t", str(extra["threads"])]).encode(), dtype=np.uint8))
         for i, s in enumerate(ref["streams"]):
-            out[f"stream{i}"] = np.frombuffer(s, dtype=np.uint8)
+            if name in HASHED:
+                out[f"stream{i}_sha256"] = np.frombuffer(hashlib.sha256(s).digest(), dtype=np.uint8)
+                out[f"stream{i}_len"] = np.array([len(s)], dtype=np.int64)
+            else:
+                out[f"stream{i}"] = np.frombuffer(s, dtype=np.uint8)
         for f in MATRIX_FIELDS:
             out[f] = ref[f]
         path = os.path.join(HERE, name + ".npz")

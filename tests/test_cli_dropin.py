@@ -194,3 +194,33 @@ def test_phix_filter_with_thread_emulation():
     data = synth.fastq_bytes(recs)
     for t in (1, 3):
         assert_same_files(run_both({"-u": ("u.fq", data)}, ["--phiX", "--discard", "--min_L", "30"], threads=t))
+
+
+def test_substitute_flag_is_a_noop_with_its_stats_line():
+    """--substitute is parsed, warned about and never applied; QC.stats.txt still prints the N_TO_* line."""
+    w = synth.c2(3000)
+    outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, ["--substitute", "--discard"])
+    assert_same_files(outs)
+    plain = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, ["--discard"])
+    assert outs["ref"]["QC.1.trimmed.fastq"] == plain["ref"]["QC.1.trimmed.fastq"]
+    assert outs["ref"]["QC.stats.txt"] != plain["ref"]["QC.stats.txt"]
+
+
+def test_polya_alone_does_nothing():
+    """--polyA without --adapter / --artifactFile / --phiX adds the poly-A target but the adapter pass never runs."""
+    w = synth.c3(1500)
+    alone = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, ["--polyA", "--min_L", "30"])
+    assert_same_files(alone)
+    both_flags = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, ["--polyA", "--adapter", "--min_L", "30"])
+    assert_same_files(both_flags)
+    assert alone["ref"]["QC.1.trimmed.fastq"] != both_flags["ref"]["QC.1.trimmed.fastq"]
+
+
+def test_c1_example_reads_through_the_cli():
+    """BASELINE configs[0]: the example reads (committed inside tests/golden/c1_example_*.npz), defaults, -t 2."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "c1_example_paired.npz"))
+    assert_same_files(run_both({"-1": ("r1.fq", z["r1"]), "-2": ("r2.fq", z["r2"])}, [], threads=2))
+    u = np.load(os.path.join(ROOT, "tests", "golden", "c1_example_unpaired.npz"))
+    assert_same_files(run_both({"-u": ("u.fq", u["r1"])}, ["--discard"], threads=2))
+    assert_same_files(run_both({"-1": ("r1.fq", z["r1"]), "-2": ("r2.fq", z["r2"]), "-u": ("u.fq", u["r1"])}, [], threads=2,
+                               extra_cli=["--batch_mb", "1"]))

@@ -134,6 +134,25 @@ def test_pairs_routing_with_discard():
     both(a, b, lambda: Options(discard_output=True, quality=12, input_quality_offset=33), batch_records=700)
 
 
+def test_anticorrelated_mates_fill_the_unpaired_stream():
+    """Pairs alternate between (long valid R1, short invalid R2) and the reverse: the unpaired stream receives the LONG mate of
+    every pair and the discard stream the short one, so the unpaired output approaches the larger input, not max(n1, n2) / 2
+    (the unpaired device buffer must be sized for sum_i max(rec1_i, rec2_i))."""
+    rng = np.random.default_rng(21)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), size=n))
+    r1, r2 = [], []
+    for i in range(4000):
+        long_s, short_s = rnd(int(rng.integers(200, 300))), rnd(int(rng.integers(5, 20)))
+        a, b = (long_s, short_s) if i % 2 == 0 else (short_s, long_s)
+        r1.append((f"@ac{i}/1", a, "I" * (len(a) - 1) + "5"))
+        r2.append((f"@ac{i}/2", b, "I" * (len(b) - 1) + "5"))
+    a = np.frombuffer(fastq_bytes(r1), dtype=np.uint8)
+    b = np.frombuffer(fastq_bytes(r2), dtype=np.uint8)
+    streams, _ = both(a, b, lambda: Options(discard_output=True, input_quality_offset=33))
+    assert len(streams[2]) > 0.9 * max(a.size, b.size) and len(streams[0]) == 0
+    both(a, b, lambda: Options(discard_output=True, input_quality_offset=33), batch_records=900)
+
+
 def test_pipelined_submit_run_wait_equals_synchronous():
     from faqcs_b200 import shard
     w = synth.c2(12000)
