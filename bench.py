@@ -149,39 +149,64 @@ def cpu_baseline(sample_pairs: int):
             "gbases_per_s": 2 * sample_pairs * 150 / dt / 1e9}
 
 
+def workload_config(args, world=1):
+    """The `config` object both arms print: BASELINE configs[1] as this bench runs it."""
+    reps = max(1, args.batch_pairs // args.block_pairs)
+    batch_pairs = reps * args.block_pairs
+    return {"workload": WORKLOAD, "pairs_per_step_per_gpu": batch_pairs * args.batches_per_step, "read_length": 150,
+            "device_batch_pairs": batch_pairs, "batches_per_step": args.batches_per_step}
+
+
 def run_reference_arm(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path on this box's cores."""
+    """--impl reference: the reference's own CPU implementation of the path (unmodified FaQCs v2.10 built from
+    /root/reference into oracle/_ref) on all of this box's cores.  Same metric / unit / config as the b200 arm; each step is
+    a bounded sample of that workload (args.ref_pairs pairs through the binary), so that W + K steps end within minutes."""
     if rank != 0:
         return
     from faqcs_b200 import synth
     cores = os.cpu_count() or 1
     pairs = args.ref_pairs
+    w = synth.c2(pairs, start=9_000_000)
+    d = tempfile.mkdtemp(prefix="faqcs_refarm_", dir=tmp_root())
     times = []
-    for i in range(args.warmup + args.steps):
-        w = synth.c2(pairs, start=9_000_000 + i * pairs)
-        if os.path.exists(REF_BIN):
-            dt = time_reference_binary(w, cores, tmp_root())
-            kind = "reference"
-        else:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            from faqcs_b200.api import Options
-            from oracle_binding import OracleEngine
-            with OracleEngine(Options(input_quality_offset=33)) as eng:
+    try:
+        p1, p2 = os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq")
+        w.r1.tofile(p1)
+        w.r2.tofile(p2)
+        kind = "reference" if os.path.exists(REF_BIN) else "port"
+        for i in range(args.warmup + args.steps):
+            if kind == "reference":
+                out = os.path.join(d, "out%d" % i)
                 t0 = time.perf_counter()
-                eng.process(w.r1, w.r2)
+                p = subprocess.run([REF_BIN, "-1", p1, "-2", p2, "-d", out, "-t", str(cores), "--trim_only"],
+                                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
                 dt = time.perf_counter() - t0
-            kind, cores = "port", 1
-        if i >= args.warmup:
-            times.append(dt)
+                if p.returncode != 0:
+                    raise RuntimeError("reference failed: " + p.stderr.decode(errors="replace")[-300:])
+                shutil.rmtree(out, ignore_errors=True)
+            else:                               # the reference binary did not travel: time the oracle port
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                from faqcs_b200.api import Options
+                from oracle_binding import OracleEngine
+                with OracleEngine(Options(input_quality_offset=33)) as eng:
+                    t0 = time.perf_counter()
+                    eng.process(w.r1, w.r2)
+                    dt = time.perf_counter() - t0
+                cores = 1
+            if i >= args.warmup:
+                times.append(dt)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
     total = sum(times)
     value = 2 * pairs * len(times) / total
+    cfg = workload_config(args)
+    cfg["gbases_per_s"] = value * 150 / 1e9
+    sample = (f"each step = {pairs} pairs (2x150) of the same workload through FaQCs v2.10 -t {cores} --trim_only "
+              f"(files on tmpfs, wall clock of the process); the reference streams at a size-independent rate")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step": pairs, "read_length": 150,
-                       "gbases_per_s": value * 150 / 1e9},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": f"{pairs} pairs per step, FaQCs v2.10 -t {cores} --trim_only, tmpfs, process wall clock"},
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -216,6 +241,11 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def stats_arrays(st):
+    from faqcs_b200.api import Stats
+    return {f: np.asarray(getattr(st, f)).astype(np.int64) for f in Stats.FIELDS}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,10 +253,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block-pairs", type=int, default=250_000, help="pairs generated on the host (numpy)")
-    ap.add_argument("--batch-pairs", type=int, default=2_000_000, help="pairs per step (block replicated in HBM)")
-    ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default: --steps; 0 disables)")
+    ap.add_argument("--batch-pairs", type=int, default=2_000_000, help="pairs per device batch (block replicated in HBM)")
+    ap.add_argument("--batches-per-step", type=int, default=50,
+                    help="device batches per step: 50 x 2 M pairs = the 100 M pairs of BASELINE configs[1] (the resident batch is replayed, SURVEY 8(d))")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default: min(steps, 4); 0 disables)")
     ap.add_argument("--cpu-pairs", type=int, default=500_000, help="sample size of the cpu_baseline leg")
-    ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs per step of --impl reference")
+    ap.add_argument("--ref-pairs", type=int, default=500_000, help="pairs per step of --impl reference (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 is the headline config (BASELINE configs[1]); the others are the parity configs, for profiling only")
@@ -261,6 +293,7 @@ def main():
     # ---- workload: each rank owns its own slice of the read stream (weak scaling, no data-path collective)
     reps = max(1, args.batch_pairs // args.block_pairs)
     batch_pairs = reps * args.block_pairs
+    nb = max(1, args.batches_per_step)
     from faqcs_b200.api import BUILTIN_ADAPTERS, MODE_HARD, POLYA_ADAPTER
     gen = {"c2": synth.c2, "c3": synth.c3, "c4": synth.c4, "c5": synth.c5}[args.workload]
     w = gen(args.block_pairs, start=rank * args.block_pairs)
@@ -268,7 +301,8 @@ def main():
     d_r1 = torch.from_numpy(w.r1).to(dev).repeat(reps)
     d_r2 = torch.from_numpy(w.r2).to(dev).repeat(reps) if paired else torch.zeros(16, dtype=torch.uint8, device=dev)
     n1, n2 = d_r1.numel(), (d_r2.numel() if paired else 0)
-    reads_per_step = (2 if paired else 1) * batch_pairs
+    reads_per_batch = (2 if paired else 1) * batch_pairs
+    reads_per_step = reads_per_batch * nb
     opts = {"c2": Options(),
             "c3": Options(filter_adapter=True, adapters=list(BUILTIN_ADAPTERS) + [POLYA_ADAPTER] + list(w.artifacts or [])),
             "c4": Options(qc_only=True),
@@ -277,11 +311,17 @@ def main():
     eng.autodetect(w.r1, w.r2)
     ext = torch.cuda.ExternalStream(eng.stream(), device=dev)
 
-    def step():
+    def batch():
         return eng.process_device(d_r1.data_ptr(), n1, d_r2.data_ptr() if paired else None, n2, 0, True, copy_out=False)
 
+    # one batch alone: its statistics are the unit the final check multiplies
+    res = batch()
+    one = stats_arrays(eng.stats())
+    n_batches_done = 1
     for _ in range(max(args.warmup, 3)):
-        res = step()
+        for _ in range(nb):
+            batch()
+            n_batches_done += 1
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -295,12 +335,14 @@ def main():
     torch.cuda.synchronize()
     e0.record(ext)
     for _ in range(args.steps):
-        step()
-        t = eng.last_timing()
-        for k in seg:
-            seg[k] += t[k]
+        for _ in range(nb):
+            batch()
+            t = eng.last_timing()
+            for k in seg:
+                seg[k] += t[k]
     e1.record(ext)
     torch.cuda.synchronize()
+    n_batches_done += args.steps * nb
     if world > 1:
         dist.barrier()
     sampler.stop_flag.set()
@@ -312,35 +354,36 @@ def main():
     total_ms = float(ms.item())
     value = world * reads_per_step * args.steps / (total_ms / 1e3)
 
-    # emitted bytes of one step (needed for the algorithmic byte count)
+    # ---- what the timed steps produced: every statistic must be exactly (batches run) x (one batch)
+    st_local = eng.stats()
+    got = stats_arrays(st_local)
+    for f, a in one.items():
+        if a.shape != got[f].shape or not np.array_equal(a * n_batches_done, got[f]):
+            raise SystemExit(f"bench: statistics after {n_batches_done} batches are not {n_batches_done} x one batch ({f})")
+    checked = f"statistics after {n_batches_done} identical batches == {n_batches_done} x one batch (all {len(one)} arrays)"
+
     import ctypes as C
     from faqcs_b200.api import CBatchOut
     out_bytes = list(res.stream_bytes)
-    alg_bytes = n1 + n2 + sum(out_bytes)
+    alg_batch = n1 + n2 + sum(out_bytes)          # B_in + B_out of one device batch
 
-    # ---- multi-GPU merge of the statistics: the path's only collective (NCCL all-reduce over NVLink)
+    # ---- multi-GPU merge of the statistics: the path's only collective (ncclAllReduce over NVLink inside the library)
     allreduce_ms = None
     if world > 1:
-        rows_needed = torch.tensor([320], device=dev, dtype=torch.int32)
-        dist.all_reduce(rows_needed, op=dist.ReduceOp.MAX)
-        eng.stats_reserve_rows(int(rows_needed.item()))
-        d, n, r = eng.stats_device_buffer()
-        t_stats = torch.as_tensor(_DevPtr(d, n, "<i8"), device=dev)
-        t_rows = torch.as_tensor(_DevPtr(r, 4, "<i4"), device=dev)
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        dist.all_reduce(t_stats, op=dist.ReduceOp.SUM)
-        dist.all_reduce(t_rows, op=dist.ReduceOp.MAX)
-        a1.record()
-        torch.cuda.synchronize()
-        allreduce_ms = a0.elapsed_time(a1)
+        from faqcs_b200 import dist_stats
+        allreduce_ms = dist_stats.allreduce_engine_stats(eng, dist, dev)
+        merged = stats_arrays(eng.stats())
+        fs = torch.tensor(got["filter_stats"], device=dev)
+        dist.all_reduce(fs, op=dist.ReduceOp.SUM)
+        if not np.array_equal(fs.cpu().numpy(), merged["filter_stats"]):
+            raise SystemExit("bench: merged filter counters differ from the sum of the ranks' counters")
+        checked += "; merged block == sum over ranks"
     st = eng.stats()
 
-    # ---- end-to-end: pinned host buffers in, host buffers out (fq_process_host)
+    # ---- end-to-end: pinned host buffers in, host buffers out
     e2e = None
     if args.e2e_steps is None:
-        args.e2e_steps = args.steps
+        args.e2e_steps = max(1, min(args.steps, 4))
     if args.e2e_steps > 0 and args.workload == "c2":
         h1, h2 = eng.host_alloc(n1), eng.host_alloc(n2)
         for k in range(reps):
@@ -348,37 +391,38 @@ def main():
             h2[k * w.r2.size:(k + 1) * w.r2.size] = w.r2
         cb2 = CBatchOut()
 
-        def pipeline(n_steps):
+        def pipeline(n_b):
             """submit(i+1); run(i); wait(i-1): upload, kernels and download of three consecutive batches overlap."""
-            tk = [None] * n_steps
+            tk = [None] * n_b
             t = C.c_uint64()
             eng._check(eng.lib.fq_submit_host(eng.ctx, C.c_void_p(h1.ctypes.data), n1, C.c_void_p(h2.ctypes.data), n2, 0, 1, C.byref(t)))
             tk[0] = t.value
-            for i in range(n_steps):
-                if i + 1 < n_steps:
+            for i in range(n_b):
+                if i + 1 < n_b:
                     eng._check(eng.lib.fq_submit_host(eng.ctx, C.c_void_p(h1.ctypes.data), n1, C.c_void_p(h2.ctypes.data), n2, 0, 1, C.byref(t)))
                     tk[i + 1] = t.value
                 eng._check(eng.lib.fq_run(eng.ctx, tk[i]))
                 if i > 0:
                     eng._check(eng.lib.fq_wait(eng.ctx, tk[i - 1], C.byref(cb2)))
-            eng._check(eng.lib.fq_wait(eng.ctx, tk[n_steps - 1], C.byref(cb2)))
+            eng._check(eng.lib.fq_wait(eng.ctx, tk[n_b - 1], C.byref(cb2)))
 
-        pipeline(2)                                  # warm-up: allocates the pinned output slots
+        pipeline(3)                                  # warm-up: allocates the pinned output slots
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(ext)
-        pipeline(args.e2e_steps)
+        pipeline(args.e2e_steps * nb)
         f1.record(ext)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ems = torch.tensor([max(f0.elapsed_time(f1), wall * 1e3)], device=dev)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        d2h = int(sum(int(cb2.bytes[i]) for i in range(4)))
         e2e = {"value": world * reads_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": n1 + n2, "d2h_bytes_per_step": int(sum(int(cb2.bytes[i]) for i in range(4))),
+               "h2d_bytes_per_step": (n1 + n2) * nb, "d2h_bytes_per_step": d2h * nb, "steps": args.e2e_steps,
                "ms_per_step": float(ems.item()) / args.e2e_steps,
                "api": "fq_submit_host / fq_run / fq_wait (pinned host buffers; H2D, kernels and D2H of consecutive batches overlap)"}
         eng.host_free(h1)
@@ -386,34 +430,51 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        dom = max(("frame", "trim", "emit"), key=lambda k: seg[k])
-        dom_ms = seg[dom] / args.steps
-        # algorithmic bytes of each segment: framing reads B_in, trim reads the seq+qual lines,
-        # emit reads B_in and writes B_out; the headline figure charges the whole B_in + B_out to the dominant kernel
-        achieved = alg_bytes / (dom_ms / 1e3) / 1e9
-        traffic = None
-        try:        # measured DRAM bytes of the dominant kernel (ncu --set full capture, profiles/r1_traffic.json), scaled to this batch
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            key = {"frame": "k_frame_lines", "trim": "k_trim", "emit": "k_emit"}[dom]
-            traffic = tj[key]["dram_bytes_per_input_byte"] * (n1 + n2)
+        steps_batches = args.steps * nb
+        ms_batch = total_ms / steps_batches
+        # fraction = sum over reads of (B_in + B_out) / device time / peak -- the WHOLE path
+        achieved = alg_batch / (ms_batch / 1e3) / 1e9
+        # per-segment figures, each against ITS OWN algorithmic bytes: framing reads B_in; the trim/filter/stats kernel reads
+        # the sequence and quality lines (2L per read) -- or, when emission is fused into it, B_in's share + B_out --;
+        # a separate emit kernel reads B_in and writes B_out
+        total_len = float(one["filter_stats"][2])
+        seg_ms = {k: v / steps_batches for k, v in seg.items()}
+        fused = seg_ms["emit"] <= 0.0 and sum(out_bytes) > 0
+        seg_bytes = {"frame": n1 + n2, "trim": (n1 + n2 + sum(out_bytes)) if fused else 2 * total_len + 8 * reads_per_batch,
+                     "emit": 0 if fused else n1 + n2 + sum(out_bytes), "adapter": total_len}
+        traffic = {}
+        try:        # measured DRAM bytes per input byte of each kernel (ncu capture of this code, profiles/r2_traffic.json)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            traffic = {k: v["dram_bytes_per_input_byte"] * (n1 + n2) for k, v in tj.items() if isinstance(v, dict)}
+        except Exception:
+            pass
+        kernels = {}
+        for k in ("frame", "adapter", "trim", "emit"):
+            if seg_ms[k] > 0:
+                a = seg_bytes[k] / (seg_ms[k] / 1e3) / 1e9
+                kernels[k] = {"ms": seg_ms[k], "algorithmic_bytes": seg_bytes[k], "achieved": a, "frac": a / peak,
+                              "dram_bytes": traffic.get(k), "traffic_ratio": (traffic[k] / seg_bytes[k]) if k in traffic and seg_bytes[k] else None}
+        dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+        cfg = workload_config(args, world)
+        rl = float(one["filter_stats"][2]) / max(float(one["filter_stats"][1]), 1.0)
+        if args.workload != "c2":
+            cfg["workload"] = args.workload + " (parity config, not the headline)"
+        cfg.update({"read_length": rl, "bytes_in_per_batch": n1 + n2, "bytes_out_per_batch": sum(out_bytes),
+                    "gbases_per_s": rl * value / 1e9, "l2": "inputs (%.0f MB per device batch) exceed the 126 MB L2" % ((n1 + n2) / 1e6),
+                    "reads_total": int(st.filter_stats[1]), "reads_kept": int(st.filter_stats[3]),
+                    "stats_allreduce_ms": allreduce_ms, "result_check": checked})
+        try:        # un-profiled bench lines of the other BASELINE configs, measured with this code (profiles/)
+            cfg["other_workloads"] = json.load(open(os.path.join(ROOT, "profiles", "r2_other_workloads.json")))
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.workload == "c2" else args.workload + " (parity config, not the headline)",
-                       "pairs_per_step_per_gpu": batch_pairs, "read_length": 150,
-                       "bytes_in_per_step_per_gpu": n1 + n2, "bytes_out_per_step_per_gpu": sum(out_bytes),
-                       "gbases_per_s": float(st.filter_stats[2]) / max(float(st.filter_stats[1]), 1.0) * value / 1e9, "l2": "inputs (%.0f MB per step) exceed the 126 MB L2" % ((n1 + n2) / 1e6),
-                       "reads_total": int(st.filter_stats[1]), "reads_kept": int(st.filter_stats[3]),
-                       "stats_allreduce_ms": allreduce_ms,
-                       "whole_job_hbm_frac": (alg_bytes / (total_ms / args.steps / 1e3) / 1e9) / peak},
+            "dtype": "u8", "data": "synthetic", "config": cfg,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": {"frame": "k_count_lines+k_scatter_lines+k_build_records", "trim": "k_trim",
-                                                     "emit": "k_route+k_scan_tiles+k_emit"}[dom],
-                         "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                         "segments_ms": {k: v / args.steps for k, v in seg.items()}},
+                         "traffic": sum(traffic.get(k, 0) for k in kernels) or None,
+                         "kernel": "whole path (frame -> trim/filter/stats -> emit), per device batch", "ms_per_batch": ms_batch,
+                         "algorithmic_bytes": alg_batch, "peak_source": peak_src, "dominant_kernel": dom, "kernels": kernels},
             "clocks": sampler.result(),
             "gpu_launches": int(launches),
         }

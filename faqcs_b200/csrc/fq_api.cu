@@ -455,7 +455,8 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         int per_sm = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         per_sm = std::max(per_sm, 1);
-        const int grid = std::max(1, std::min<int>((n * n_mates + 15) / 16, ctx->sm_count * per_sm));
+        const uint32_t groups = ((n + 31) / 32) * n_mates;
+        const int grid = std::max(1, std::min<int>((groups + threads / 32 - 1) / (threads / 32), ctx->sm_count * per_sm));
         kern<<<grid, threads, smem, ctx->stream>>>(ta, o);
         ctx->launches++;
     }

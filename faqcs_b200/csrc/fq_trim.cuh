@@ -143,33 +143,39 @@ extern __shared__ uint32_t g_smem[];
 constexpr uint32_t kTrashWords = 320;      // phase 1 handles reads of up to 320 bases; every position needs a dump slot
 struct SmemHist {
     uint32_t rows, key;
-    // [42][rows] pre / removed quality, [5][rows] pre / removed base, [rows] g2n, [rows+1] x2 length,
-    // [4][42] avg-Q hists, [32] filter counters, [256] LUT, [256] x2 phase-1 LUTs (uint2), [320] trash row,
-    // [12] composition bin 0, [2][7][key+1] composition by count
+    // Tables at fixed offsets first (their addresses are compile-time constants in the hot loop), then the histograms:
+    //   [256] class LUT, [256] + [258] phase-1 LUTs (uint2; the quality table has a pad entry 256 for lanes past the end of a
+    //   read), [320] trash row, [12] composition bin 0, [4][42] avg-Q hists, [32] filter counters,
+    //   [42][rows] pre / removed quality, [5][rows] pre / removed base, [rows] g2n, [rows+1] x2 length,
+    //   [2][7][key+1] composition by count
+    static constexpr uint32_t kLut = 0, kLutBase = 256, kLutQual = kLutBase + 2 * 256, kTrash = kLutQual + 2 * 258, kZero = kTrash + kTrashWords,
+                              kQh = kZero + 12, kFilt = kQh + 4 * kQualCols, kHist = kFilt + 32;
     __host__ __device__ static size_t words(uint32_t rows, uint32_t key)
     {
-        return (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + 4 * kQualCols + 32 + 256 + 1024 + kTrashWords + 12 +
-               (key == 0xffffffffu ? 0 : 14 * ((size_t)key + 1));
+        return kHist + (size_t)rows * (2 * kQualCols + 2 * kBaseCols + 1) + 2 * ((size_t)rows + 1) + (key == 0xffffffffu ? 0 : 14 * ((size_t)key + 1));
     }
-    __device__ __forceinline__ uint32_t *preq() const { return g_smem; }
-    __device__ __forceinline__ uint32_t *remq() const { return g_smem + kQualCols * rows; }
-    __device__ __forceinline__ uint32_t *preb() const { return g_smem + 2 * kQualCols * rows; }
-    __device__ __forceinline__ uint32_t *remb() const { return g_smem + (2 * kQualCols + kBaseCols) * rows; }
-    __device__ __forceinline__ uint32_t *g2n() const { return g_smem + (2 * kQualCols + 2 * kBaseCols) * rows; }
-    __device__ __forceinline__ uint32_t *prelen() const { return g_smem + (2 * kQualCols + 2 * kBaseCols + 1) * rows; }
+    __device__ __forceinline__ uint32_t *preq() const { return g_smem + kHist; }
+    __device__ __forceinline__ uint32_t *remq() const { return preq() + kQualCols * rows; }
+    __device__ __forceinline__ uint32_t *preb() const { return preq() + 2 * kQualCols * rows; }
+    __device__ __forceinline__ uint32_t *remb() const { return preq() + (2 * kQualCols + kBaseCols) * rows; }
+    __device__ __forceinline__ uint32_t *g2n() const { return preq() + (2 * kQualCols + 2 * kBaseCols) * rows; }
+    __device__ __forceinline__ uint32_t *prelen() const { return preq() + (2 * kQualCols + 2 * kBaseCols + 1) * rows; }
     __device__ __forceinline__ uint32_t *postlen() const { return prelen() + rows + 1; }
-    __device__ __forceinline__ uint32_t *qh() const { return postlen() + rows + 1; }
-    __device__ __forceinline__ uint32_t *filt() const { return qh() + 4 * kQualCols; }
-    __device__ __forceinline__ uint32_t *lut() const { return filt() + 32; }
-    // phase-1 tables: per byte value {byte offset of the histogram row to bump, payload}
-    //   base:    row = pre_b[class] (trash row for non-ACGTN), payload = 1 << (5 * class) (packed per-lane counters)
-    //   quality: row = pre_q[max(0, (signed char)ch - in_off)] (trash row above 41), payload = (int)(signed char)ch
-    __device__ __forceinline__ uint2 *lut_base() const { return reinterpret_cast<uint2 *>(lut() + 256); }
-    __device__ __forceinline__ uint2 *lut_qual() const { return lut_base() + 256; }
-    __device__ __forceinline__ uint32_t *trash() const { return lut() + 256 + 1024; }
-    __device__ __forceinline__ uint32_t trash_bytes() const { return (uint32_t)((2 * kQualCols + 2 * kBaseCols + 1) * rows + 2 * (rows + 1) + 4 * kQualCols + 32 + 256 + 1024) * 4u; }
-    __device__ __forceinline__ uint32_t *zero() const { return trash() + kTrashWords; }
-    __device__ __forceinline__ uint32_t *compk() const { return zero() + 12; }
+    __device__ __forceinline__ uint32_t *compk() const { return postlen() + rows + 1; }
+    __device__ __forceinline__ uint32_t *qh() const { return g_smem + kQh; }
+    __device__ __forceinline__ uint32_t *filt() const { return g_smem + kFilt; }
+    __device__ __forceinline__ uint32_t *lut() const { return g_smem + kLut; }
+    // phase-1 tables: per byte value {byte offset (from the start of the block) of the histogram row to bump, payload}
+    //   base:    row = pre_b[class] (trash row for non-ACGTN), payload = 1 << (8 * class) for A, T, C, G (packed per-lane
+    //            counters, one byte each), 0 for N and everything else
+    //   quality: row = pre_q[max(0, (signed char)ch - in_off)], payload = (int)(signed char)ch; a score above 41 goes to the
+    //            trash row with kBadQual added to the payload (the read's quality sum then exposes it); entry 256 is the pad
+    //            of lanes past the end of the read: trash row, payload 0
+    __device__ __forceinline__ uint2 *lut_base() const { return reinterpret_cast<uint2 *>(g_smem + kLutBase); }
+    __device__ __forceinline__ uint2 *lut_qual() const { return reinterpret_cast<uint2 *>(g_smem + kLutQual); }
+    __device__ __forceinline__ uint32_t *trash() const { return g_smem + kTrash; }
+    __device__ __forceinline__ uint32_t trash_bytes() const { return kTrash * 4u; }
+    __device__ __forceinline__ uint32_t *zero() const { return g_smem + kZero; }
 };
 
 __device__ __forceinline__ void gadd(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
@@ -180,6 +186,8 @@ struct KernelCtx {
     const SmemHist &H;
     unsigned long long *S;
     uint32_t lane;
+    uint32_t col;       // shared-memory byte address of this lane's position column (phase 1)
+    uint32_t one;       // a run-time 1 (see red_shared_add)
 };
 
 // One increment in each of the six composition histograms (trim.cpp:860-874).  `cnt` holds the
@@ -383,29 +391,16 @@ __device__ __forceinline__ uint32_t unpack5(uint32_t packed, int field) { return
 struct LaneRead {
     Rec rc;
     int sum_q;              // sum of (masked) raw quality chars of the whole read
-    uint32_t cnt_atc;       // 10-bit fields A,T,C
-    uint32_t cnt_gn;        // 10-bit fields G,N
+    uint32_t cnt_ac;        // 16-bit fields A,C  (phase 1), then 10-bit fields A,T,C
+    uint32_t cnt_tg;        // 16-bit fields T,G  (phase 1), then 10-bit fields G,N
+    uint32_t cnt_n;         // N / n
     uint32_t lead, trail;   // terminal-N mask bounds
     uint32_t run_whole;     // longest 'N' run of the whole read (0 if fewer than -n 'N's)
     bool done;              // already fully processed (generic path) or out of range
 };
 
-// One chunk of phase-1 input for this lane: base and quality byte of position p (if p < len, else the given
-// defaults) and the histogram increment (one / 0), as one compare, two predicated loads and a select.
-__device__ __forceinline__ void load_chunk(const uint8_t *sp, const uint8_t *qp, uint32_t p, uint32_t len, uint32_t one, uint32_t &c,
-                                           uint32_t &q, uint32_t &inc)
-{
-    asm("{ .reg .pred p;\n\t"
-        "setp.lt.u32 p, %3, %4;\n\t"
-        "@p ld.global.nc.u8 %0, [%5];\n\t"
-        "@p ld.global.nc.u8 %1, [%6];\n\t"
-        "selp.u32 %2, %7, 0, p; }"
-        : "+r"(c), "+r"(q), "=r"(inc)
-        : "r"(p), "r"(len), "l"(sp), "l"(qp), "r"(one));
-}
 // `one` must be a run-time 1: with an immediate the assembler picks the warp-aggregating form, which needs a
 // convergence region (three more instructions) around every single increment.
-// (A predicated shared atomic is turned into a branch as well, so lanes past the end of the read add 0 instead.)
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
 {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -413,112 +408,162 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
 
 __device__ __forceinline__ uint32_t f10(uint32_t packed, int field) { return (packed >> (10 * field)) & 1023u; }
 
-// Phase 1 for the read owned by lane j: PRE matrices + per-read summaries.
-// Loads of one read for phase 1: raw bytes per chunk; lanes past the end hold a non-base and the zero-quality character.
+constexpr uint32_t kQualPad = 256;          // index of the pad entry of the quality table
+constexpr int kBadQual = 1 << 20;           // added to the quality sum by every score above 41 (fastq.h:31-33)
+
+// Loads of one read for phase 1: raw bytes per chunk of 32 bases, lanes striped over positions.  A lane past the end of the
+// read holds a non-base and the quality table's pad index, whose table entries point at the trash row and add nothing to
+// the per-read sums -- so the histogram increment is the same run-time 1 for every lane.  Reads that fill all but the last
+// chunk (the fixed-length case) load those chunks without a predicate.
 template <int K>
 __device__ __forceinline__ void phase1_load(const KernelCtx &kc, const uint8_t *raw, uint32_t seq, uint32_t qual, uint32_t len,
-                                            uint32_t (&c)[K], uint32_t (&q)[K], uint32_t (&inc)[K])
+                                            uint32_t (&c)[K], uint32_t (&q)[K])
 {
     const uint32_t lane = kc.lane;
     const uint8_t *const spl = raw + (seq + lane), *const qpl = raw + (qual + lane);
-    const uint32_t one = min(kc.a.n_mates, 1u);
+    if (K <= 5 && len > (uint32_t)(32 * (K - 1))) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        c[k] = 0;
-        q[k] = (uint32_t)kc.o.in_off;
-        load_chunk(spl + k * 32, qpl + k * 32, (uint32_t)(k * 32) + lane, len, one, c[k], q[k], inc[k]);
+        for (int k = 0; k < K - 1; ++k) {
+            c[k] = __ldg(spl + k * 32);
+            q[k] = __ldg(qpl + k * 32);
+        }
+        const bool in = (uint32_t)(32 * (K - 1)) + lane < len;
+        c[K - 1] = in ? (uint32_t)__ldg(in ? spl + 32 * (K - 1) : spl) : 0u;
+        q[K - 1] = in ? (uint32_t)__ldg(in ? qpl + 32 * (K - 1) : qpl) : kQualPad;
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool in = (uint32_t)(k * 32) + lane < len;
+            c[k] = 0;
+            q[k] = kQualPad;
+            if (in) {
+                c[k] = __ldg(spl + k * 32);
+                q[k] = __ldg(qpl + k * 32);
+            }
+        }
     }
 }
+
+// Bounds of the terminal 'N' runs of a read given its per-chunk 'N' ballots (mask_quality_terminal_N, trim.cpp:1191-1216):
+// returns {lead, trail}.  Rare (first or last base is 'N'), kept out of line and out of the hot loop's registers.
 template <int K>
-__device__ __forceinline__ void phase1_body(const KernelCtx &kc, uint32_t (&c)[K], uint32_t (&q)[K], uint32_t (&inc)[K], uint32_t len,
-                                            int &out_sum, uint32_t &out_atc, uint32_t &out_gn, uint32_t &out_lead, uint32_t &out_trail,
-                                            uint32_t &out_run, uint32_t &max_row);
+struct NBallots {
+    uint32_t w[K];
+};
 template <int K>
-__device__ __forceinline__ void phase1(const KernelCtx &kc, const uint8_t *raw, uint32_t seq, uint32_t qual, uint32_t len,
-                                       int &out_sum, uint32_t &out_atc, uint32_t &out_gn, uint32_t &out_lead, uint32_t &out_trail,
-                                       uint32_t &out_run, uint32_t &max_row)
+__device__ __noinline__ uint2 terminal_n_bounds(const NBallots<K> nm, uint32_t len)
 {
-    uint32_t c[K], q[K], inc[K];
-    phase1_load<K>(kc, raw, seq, qual, len, c, q, inc);
-    phase1_body<K>(kc, c, q, inc, len, out_sum, out_atc, out_gn, out_lead, out_trail, out_run, max_row);
+    uint32_t lead = 0, trail = len;
+    bool open = true;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (open && (uint32_t)(k * 32) < len) {
+            const uint32_t nb = min(32u, len - k * 32);
+            const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            const uint32_t inv = ~nm.w[k] & valid;
+            if (inv) { lead += __ffs(inv) - 1; open = false; }
+            else lead += nb;
+        }
+    }
+    open = true;
+#pragma unroll
+    for (int k = K - 1; k >= 0; --k) {
+        if (open && (uint32_t)(k * 32) < len) {
+            const uint32_t nb = min(32u, len - k * 32);
+            const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            const uint32_t inv = ~nm.w[k] & valid;
+            if (inv) { trail = k * 32 + (31 - __clz(inv)) + 1; open = false; }
+            else trail = k * 32;
+        }
+    }
+    if (lead >= len) trail = 0;
+    return make_uint2(lead, trail);
 }
+
+// Phase 1 for one read: PRE matrices + per-read summaries.  Branch-free in the common case: every lane looks both bytes up
+// (two LDS.64 from tables at constant addresses), bumps two histogram cells (two RED.shared) and accumulates the payloads;
+// the A/T/C/G counts of the read are ONE warp reduction of byte-packed counters.  Only a read that holds something else
+// than A, C, G, T takes the ballot path ('N' counts, terminal-N mask, longest run); a quality above 41 shows up in the sum.
+struct ReadSummary {
+    int sum_q;
+    uint32_t ac, tg;        // 16-bit fields: A | C << 16, T | G << 16
+    uint32_t n;             // N / n
+    uint32_t lead, trail, run;
+};
+
 template <int K>
-__device__ __forceinline__ void phase1_body(const KernelCtx &kc, uint32_t (&c)[K], uint32_t (&q)[K], uint32_t (&inc)[K], uint32_t len,
-                                            int &out_sum, uint32_t &out_atc, uint32_t &out_gn, uint32_t &out_lead, uint32_t &out_trail,
-                                            uint32_t &out_run, uint32_t &max_row)
+__device__ __forceinline__ void phase1_body(const KernelCtx &kc, uint32_t (&c)[K], uint32_t (&q)[K], uint32_t len, ReadSummary &out)
 {
     const DevOpts &o = kc.o;
-    const SmemHist &H = kc.H;
     const uint32_t lane = kc.lane;
-    // Branch-free from here: every lane looks both bytes up; a lane past the end holds (non-base, zero quality),
-    // whose payloads add nothing to the class counters and `in_off` to the quality sum (taken out again below),
-    // and its histogram increments are 0.
-    const uint2 *const lb = H.lut_base(), *const lq = H.lut_qual();
-    const uint32_t col = (uint32_t)__cvta_generic_to_shared(g_smem) + 4 * lane;      // this lane's position column; chunk k adds 128 bytes
-    uint32_t packed = 0, n_chunks = 0;
+    const uint2 *const lb = reinterpret_cast<const uint2 *>(g_smem + SmemHist::kLutBase);
+    const uint2 *const lq = reinterpret_cast<const uint2 *>(g_smem + SmemHist::kLutQual);
+    const uint32_t col = kc.col;                    // shared address of this lane's position column; chunk k adds 128 bytes
+#ifdef FQ_EXP_ONE_RUNTIME
+    const uint32_t one = kc.one;                    // a run-time 1 keeps the plain ATOMS.ADD
+#else
+    const uint32_t one = 1u;                        // ptxas picks ATOMS.POPC.INC; every lane takes part, so no convergence region
+#endif
+    constexpr int KH = K <= 5 ? K : 5;              // byte-packed counters hold at most 5 chunks per lane
+    uint32_t packed = 0, packed_hi = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if (K <= 5 || (uint32_t)(k * 32) < len) {
             const uint2 eb = lb[c[k]];
-            packed += eb.y;
-            ++n_chunks;
+            if (k < KH) packed += eb.y; else packed_hi += eb.y;
 #ifndef FQ_EXP_NOATOM
-            red_shared_add(col + eb.x + k * 128, inc[k]);
+            red_shared_add(col + eb.x + k * 128, one);
 #endif
         }
     }
-    out_atc = warp_sum(unpack5(packed, 0) | (unpack5(packed, 1) << 10) | (unpack5(packed, 2) << 20));
-    out_gn = warp_sum(unpack5(packed, 3) | (unpack5(packed, 4) << 10));
-    const bool any_n = (out_gn >> 10) != 0;          // some 'N' or 'n' in the read
-    uint32_t lead = 0, trail = len, run = 0;
-    if (any_n) {
-        uint32_t nm[K];
+    uint32_t atcg = warp_sum(packed);               // A | T << 8 | C << 16 | G << 24: at most 160 each
+    out.ac = atcg & 0x00ff00ffu;
+    out.tg = (atcg >> 8) & 0x00ff00ffu;
+    uint32_t acgt = __dp4a(atcg, 0x01010101u, 0u);
+    if (K > 5) {
+        atcg = warp_sum(packed_hi);
+        out.ac += atcg & 0x00ff00ffu;
+        out.tg += (atcg >> 8) & 0x00ff00ffu;
+        acgt = __dp4a(atcg, 0x01010101u, acgt);
+    }
+    out.n = 0;
+    out.lead = 0;
+    out.trail = len;
+    out.run = 0;
+    if (acgt != len) {                              // something else than A, C, G, T (any case) in the read (warp-uniform)
+        uint32_t n_any = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) nm[k] = __ballot_sync(0xffffffffu, c[k] == 'N');
-        bool last_n = false;
-        uint32_t n_count = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if ((uint32_t)k == ((len - 1) >> 5)) last_n = (nm[k] >> ((len - 1) & 31)) & 1u;
-            n_count += __popc(nm[k]);
-        }
-        if ((nm[0] & 1u) || last_n) {                            // terminal 'N' runs (trim.cpp:1191-1216)
-            bool open = true;
-            lead = 0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if (open && (uint32_t)(k * 32) < len) {
-                    const uint32_t nb = min(32u, len - k * 32);
-                    const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-                    const uint32_t inv = ~nm[k] & valid;
-                    if (inv) { lead += __ffs(inv) - 1; open = false; }
-                    else lead += nb;
-                }
-            }
-            open = true;
-#pragma unroll
-            for (int k = K - 1; k >= 0; --k) {
-                if (open && (uint32_t)(k * 32) < len) {
-                    const uint32_t nb = min(32u, len - k * 32);
-                    const uint32_t valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-                    const uint32_t inv = ~nm[k] & valid;
-                    if (inv) { trail = k * 32 + (31 - __clz(inv)) + 1; open = false; }
-                    else trail = k * 32;
-                }
-            }
-            if (lead >= len) trail = 0;
+        for (int k = 0; k < K; ++k) n_any += __popc(__ballot_sync(0xffffffffu, (c[k] | 0x20u) == 'n'));
+        out.n = n_any;
+        if (n_any) {
+            NBallots<K> nm;
+            uint32_t n_count = 0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const uint32_t p = k * 32 + lane;
-                if (p < lead || p >= trail) q[k] = (uint32_t)o.in_off;
+                nm.w[k] = __ballot_sync(0xffffffffu, c[k] == 'N');
+                n_count += __popc(nm.w[k]);
             }
-        }
-        if (n_count >= o.max_poly_n) {                           // candidate for the N filter: longest run of the whole read
-            RunTracker rt;
+            uint32_t nm_last = nm.w[0];             // ballot of the chunk that holds the last base (no dynamic indexing)
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                if ((uint32_t)(k * 32) < len) rt.feed(nm[k]);
-            run = rt.best;
+            for (int k = 1; k < K; ++k)
+                if (((len - 1) >> 5) == (uint32_t)k) nm_last = nm.w[k];
+            if (len && ((nm.w[0] & 1u) | ((nm_last >> ((len - 1) & 31)) & 1u))) {   // terminal 'N' runs (trim.cpp:1191-1216)
+                const uint2 lt = terminal_n_bounds<K>(nm, len);
+                out.lead = lt.x;
+                out.trail = lt.y;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t p = k * 32 + lane;
+                    if (p < len && (p < lt.x || p >= lt.y)) q[k] = (uint32_t)o.in_off & 0xffu;
+                }
+            }
+            if (n_count >= o.max_poly_n) {          // candidate for the N filter: longest run of the whole read
+                RunTracker rt;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if ((uint32_t)(k * 32) < len) rt.feed(nm.w[k]);
+                out.run = rt.best;
+            }
         }
     }
     int sum_q = 0;
@@ -527,16 +572,12 @@ __device__ __forceinline__ void phase1_body(const KernelCtx &kc, uint32_t (&c)[K
         if (K <= 5 || (uint32_t)(k * 32) < len) {
             const uint2 eq = lq[q[k]];
             sum_q += (int)eq.y;
-            max_row = max(max_row, eq.x);       // the trash row lies above every quality row: reaching it means a score above 41
 #ifndef FQ_EXP_NOATOM
-            red_shared_add(col + eq.x + k * 128, inc[k]);
+            red_shared_add(col + eq.x + k * 128, one);
 #endif
         }
     }
-    out_sum = warp_sum_i(sum_q) - o.in_off * (int)(n_chunks * 32 - len);
-    out_lead = lead;
-    out_trail = trail;
-    out_run = run;
+    out.sum_q = warp_sum_i(sum_q);
 }
 
 // Cooperative pass over one read for the "removed" histograms.
@@ -713,7 +754,7 @@ __device__ __forceinline__ Window lane_window(const KernelCtx &kc, uint32_t mate
 // ---------------------------------------------------------------------------------------------
 // Generic path: any length, chunk loops over global memory (L1 resident after the first pass).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t mate, uint32_t r, const Rec &rc)
+__device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t mate, uint32_t r, const Rec &rc, uint32_t &v_off5, uint32_t &v_lenflags)
 {
     const DevOpts &o = kc.o;
     const SmemHist &H = kc.H;
@@ -852,8 +893,9 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
             }
         }
     }
+    v_off5 = w.off5;
+    v_lenflags = pack_len_flags(w.ret ? w.wl : 0, w.flags | ((lead > 0 || trail < len) ? kFlagMasked : 0u));
     if (lane == 0) {
-        kc.a.res[mate][r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags | ((lead > 0 || trail < len) ? kFlagMasked : 0u)));
         if (kc.a.dbg[mate]) {
             fq_read_result d;
             d.offset_5 = w.off5;
@@ -866,320 +908,313 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// trim_group: trim_read (trim.cpp:225-551) for the 32 reads r0 .. r0+31 of one mate, by one warp.
+// Returns, in the lane that owns read r0 + lane, the verdict {offset_5, length | flags << 24}
+// (length 0 = invalid).  KSEL / PLAIN: see k_trim_emit (fq_fused.cuh).
+// ---------------------------------------------------------------------------------------------
 #ifndef FQ_TRIM_THREADS
 #define FQ_TRIM_THREADS 1024
 #endif
-#ifndef FQ_TRIM_MIN_CTAS
-#define FQ_TRIM_MIN_CTAS 1
-#endif
-constexpr int kTrimThreads = FQ_TRIM_THREADS;
-// width-specialised instances request the bytes of read j+1 before they process read j (1.28 -> 1.26 ms on C2)
+// width-specialised instances request the bytes of read j+1 before they process read j (C2: 1.27 -> 1.15 ms per 4 M reads)
 #ifndef FQ_TRIM_PIPE
 #define FQ_TRIM_PIPE 1
 #endif
+struct GroupErr {
+    uint32_t bits = 0, rec = 0xffffffffu;
+};
 
-// KSEL: which register-resident phase-1 widths this instance carries (the host picks it from the batch's longest read):
-//   4: reads <= 128 bases, 5: reads <= 160 bases, 0: all widths (4, 5 and 10 chunks of 32 bases).  Longer reads always
-//   take the chunked generic path.  Specialised instances keep the hot loop small: the kernel is issue-bound and its
-//   instruction-cache misses are measurable (C2: 1.50 -> 1.46 ms without the unused widths).
-// PLAIN: the option set of a default run (BWA_plus, no 5'/3' clip, no adapters, no G->N replacement, no re-encoding,
-//   not --qc_only) is baked in, so every branch on those options disappears from the instance.
 template <int KSEL, bool PLAIN>
-__global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const TrimArgs a, const DevOpts o_in)
+__device__ __forceinline__ void trim_group(const KernelCtx &kc, uint32_t mate, uint32_t r0, const Rec &my_rc, LaneAcc &acc, GroupErr &ge,
+                                           uint32_t &v_off5, uint32_t &v_lenflags)
 {
-    DevOpts o = o_in;
-    if (PLAIN) {
-        o.mode = FQ_MODE_BWA_PLUS;
-        o.trim_5 = 0;
-        o.trim_3 = 0;
-        o.replace_q = 0;
-        o.qc_only = 0;
-        o.filter_adapter = 0;
-        o.out_off = o.in_off;
+    const TrimArgs &a = kc.a;
+    const DevOpts &o = kc.o;
+    const SmemHist &H = kc.H;
+    const uint32_t lane = kc.lane, R = H.rows;
+    const uint8_t *const raw = mate ? a.raw[1] : a.raw[0];
+    const bool need_max = o.in_off != o.out_off && o.out_off + FQ_MAX_QUALITY_SCORE > 127;   // re-encode can overflow
+
+    const uint32_t r = r0 + lane;
+    const uint32_t n_here = r0 < a.n_rec ? min(32u, a.n_rec - r0) : 0u;
+    LaneRead me;
+    me.done = lane >= n_here;
+    me.rc = my_rc;
+    me.sum_q = 0; me.cnt_ac = 0; me.cnt_tg = 0; me.cnt_n = 0; me.lead = 0; me.trail = me.rc.len; me.run_whole = 0;
+    uint32_t g_off5 = 0, g_lenflags = 0;          // verdict of a read that took the generic path
+
+    // ---- phase 1: cooperative per-base pass, read by read
+    int max_sum = 0;
+#if FQ_TRIM_PIPE
+    // width-specialised instances request the bytes of read j+1 before they process read j
+    constexpr int KP = KSEL == 4 ? 4 : 5;
+    uint32_t nc[KP], nq[KP], nlen = 0;
+    if (KSEL != 0 && n_here) {
+        nlen = __shfl_sync(0xffffffffu, me.rc.len, 0);
+        phase1_load<KP>(kc, raw, __shfl_sync(0xffffffffu, me.rc.seq, 0), __shfl_sync(0xffffffffu, me.rc.qual, 0), nlen, nc, nq);
     }
-    SmemHist H{a.smem_rows, a.comp_key_len};
+#endif
+    for (uint32_t j = 0; j < n_here; ++j) {
+#if FQ_TRIM_PIPE
+        if (KSEL != 0) {
+            uint32_t c[KP], q[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) { c[k] = nc[k]; q[k] = nq[k]; }
+            const uint32_t len = nlen;
+            if (j + 1 < n_here) {
+                nlen = __shfl_sync(0xffffffffu, me.rc.len, j + 1);
+                phase1_load<KP>(kc, raw, __shfl_sync(0xffffffffu, me.rc.seq, j + 1), __shfl_sync(0xffffffffu, me.rc.qual, j + 1), nlen, nc, nq);
+            }
+            ReadSummary rs;
+            phase1_body<KP>(kc, c, q, len, rs);
+            max_sum = max(max_sum, rs.sum_q);
+            if (lane == j) { me.sum_q = rs.sum_q; me.cnt_ac = rs.ac; me.cnt_tg = rs.tg; }
+            if (rs.n && lane == j) { me.cnt_n = rs.n; me.lead = rs.lead; me.trail = rs.trail; me.run_whole = rs.run; }
+            continue;
+        }
+#endif
+        const uint32_t len = __shfl_sync(0xffffffffu, me.rc.len, j);
+        const uint32_t seq = __shfl_sync(0xffffffffu, me.rc.seq, j);
+        const uint32_t qual = __shfl_sync(0xffffffffu, me.rc.qual, j);
+        ReadSummary rs;
+        // KSEL 4 / 5: the host launches these instances only for batches whose longest read fits the width, so
+        // the generic path (and its code) is not part of them
+        if (KSEL == 4) {
+            uint32_t c[4], q[4];
+            phase1_load<4>(kc, raw, seq, qual, len, c, q);
+            phase1_body<4>(kc, c, q, len, rs);
+        } else if (KSEL == 5 || (len <= 160 && len <= R)) {
+            uint32_t c[5], q[5];
+            phase1_load<5>(kc, raw, seq, qual, len, c, q);
+            phase1_body<5>(kc, c, q, len, rs);
+        } else if (len <= 320 && len <= R) {
+            uint32_t c[10], q[10];
+            phase1_load<10>(kc, raw, seq, qual, len, c, q);
+            phase1_body<10>(kc, c, q, len, rs);
+        } else {
+            const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
+            uint32_t go = 0, gl = 0;
+            process_generic(kc, mate, r0 + j, rcj, go, gl);
+            if (lane == j) { g_off5 = go; g_lenflags = gl; me.done = true; }
+            continue;
+        }
+        max_sum = max(max_sum, rs.sum_q);
+        if (lane == j) { me.sum_q = rs.sum_q; me.cnt_ac = rs.ac; me.cnt_tg = rs.tg; }
+        if (rs.n && lane == j) { me.cnt_n = rs.n; me.lead = rs.lead; me.trail = rs.trail; me.run_whole = rs.run; }
+    }
+    const bool bad_sum = max_sum >= kBadQual / 2;
+    {   // counts in the layout the scalar phases use: 10-bit fields A,T,C and G,N
+        const uint32_t A = me.cnt_ac & 0xffffu, C = me.cnt_ac >> 16, T = me.cnt_tg & 0xffffu, G = me.cnt_tg >> 16;
+        me.cnt_ac = A | (T << 10) | (C << 20);
+        me.cnt_tg = G | (me.cnt_n << 10);
+    }
+
+    if (bad_sum) {
+        // a quality score above 41 (fastq.h:31-33): find the first offending read of the group
+        for (uint32_t j = 0; j < n_here; ++j) {
+            const uint32_t lenj = __shfl_sync(0xffffffffu, me.rc.len, j), qual = __shfl_sync(0xffffffffu, me.rc.qual, j);
+            const uint32_t lead = __shfl_sync(0xffffffffu, me.lead, j), trail = __shfl_sync(0xffffffffu, me.trail, j);
+            const bool skip = __shfl_sync(0xffffffffu, (int)me.done, j) != 0;      // generic path reports its own errors
+            const signed char *qp = reinterpret_cast<const signed char *>(raw + qual);
+            bool bad = false;
+            for (uint32_t p = lane; p < lenj && !skip; p += 32)
+                bad |= p >= lead && p < trail && (int)qp[p] - o.in_off > FQ_MAX_QUALITY_SCORE;
+            if (__any_sync(0xffffffffu, bad)) {
+                ge.bits |= kErrQualGt41;
+                ge.rec = min(ge.rec, r0 + j);
+                break;
+            }
+        }
+    }
+
+    // ---- phase 2a: one lane per read: PRE scalar statistics and the window
+    const signed char *qp_mine = reinterpret_cast<const signed char *>(raw + me.rc.qual);
+    const uint32_t len = me.rc.len;
+    const QualAt qa{qp_mine, me.lead, me.trail, o.in_off};
+    Window w{0, len, 0, 0, false, -1};
+    if (!me.done) {
+        lane_scalar_stats(kc, 0, len, me.cnt_ac, me.cnt_tg, (int)average_quality(me.sum_q, len, o.in_off));
+        acc.reads += 1;
+        acc.len += len;
+        acc.max_pre_rows = max(acc.max_pre_rows, len);
+        w = lane_window(kc, mate, r, len, qa);
+    }
+
+    // ---- phase 3a: cooperative pass over the bases outside the window (and G->N candidates / max quality inside)
+    uint32_t w_atc = me.cnt_ac, w_gn = me.cnt_tg, n_lowg = 0;
+    int sum_w = me.sum_q, max_qv = 0;
+    {
+        const bool partial = !me.done && (w.lo > 0 || w.lo + w.wl < len);
+        const bool want = !me.done && (partial || ((o.replace_q > 0 || need_max) && w.ret));
+        uint32_t todo = __ballot_sync(0xffffffffu, want);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t lenj = __shfl_sync(0xffffffffu, len, j);
+            const uint8_t *sp = raw + __shfl_sync(0xffffffffu, me.rc.seq, j);
+            const signed char *qp = reinterpret_cast<const signed char *>(raw + __shfl_sync(0xffffffffu, me.rc.qual, j));
+            const uint32_t lo = __shfl_sync(0xffffffffu, w.lo, j), wl = __shfl_sync(0xffffffffu, w.wl, j);
+            const uint32_t lead = __shfl_sync(0xffffffffu, me.lead, j), trail = __shfl_sync(0xffffffffu, me.trail, j);
+            uint32_t r_atc = 0, r_gn = 0, nl = 0;
+            int r_sum = 0, mq = need_max ? 0 : -1;
+            removed_pass(kc, 0, sp, qp, lenj, lo, wl, lead, trail, r_atc, r_gn, r_sum, nl, mq);
+            if ((int)lane == j) {
+                w_atc -= r_atc;            // fields never borrow: removed counts <= totals per class
+                w_gn -= r_gn;
+                sum_w -= r_sum;
+                n_lowg = nl;
+                max_qv = mq;
+            }
+        }
+    }
+
+    // ---- phase 2b: one lane per read: filters (trim.cpp:363-513)
+    float ave_q = 0.0f;
+    bool want_dinuc = false, want_run = false;
+    float norm2 = 0.0f;
+    uint32_t wA = f10(w_atc, 0), wT = f10(w_atc, 1), wC = f10(w_atc, 2), wG = f10(w_gn, 0), wN = f10(w_gn, 1);
+    if (!me.done && w.ret) {
+        wG -= n_lowg;                                       // G -> N replacement happens before the complexity filter
+        wN += n_lowg;
+        if (me.run_whole >= o.max_poly_n) want_run = true;  // exact run inside the window needed
+    }
+    {   // exact 'N' run of the window (rare: the whole read has a long enough run)
+        uint32_t todo = __ballot_sync(0xffffffffu, want_run);
+        uint32_t run_w = 0;
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint8_t *sp = raw + __shfl_sync(0xffffffffu, me.rc.seq, j);
+            const uint32_t rw = window_n_run(kc, sp, __shfl_sync(0xffffffffu, w.lo, j), __shfl_sync(0xffffffffu, w.wl, j));
+            if ((int)lane == j) run_w = rw;
+        }
+        if (want_run && run_w >= o.max_poly_n) {            // trim.cpp:363-371
+            atomicAdd(&H.filt()[FQ_READ_NN], 1u);
+            atomicAdd(&H.filt()[FQ_BASE_NN], w.wl);
+            w.flags |= FQ_RR_F_NN;
+            if (!o.qc_only) w.ret = false;
+        }
+    }
+    if (!me.done && w.ret) {
+        ave_q = average_quality(sum_w, w.wl, o.in_off);
+        if (ave_q < o.avg_q) {                              // trim.cpp:374-382
+            atomicAdd(&H.filt()[FQ_READ_AVG_Q], 1u);
+            atomicAdd(&H.filt()[FQ_BASE_AVG_Q], w.wl);
+            w.flags |= FQ_RR_F_AVGQ;
+            w.ret = false;
+        }
+    }
+    bool lowc = false;
+    if (!me.done && w.ret) {                                // low complexity, trim.cpp:405-513
+        const float norm = (float)(1.0 / (double)w.wl);     // trim.cpp:483
+        lowc = __fmul_rn((float)wA, norm) > o.lc || __fmul_rn((float)wT, norm) > o.lc ||
+               __fmul_rn((float)wG, norm) > o.lc || __fmul_rn((float)wC, norm) > o.lc;
+        if (!lowc) {
+            norm2 = norm * 2.0f;                            // trim.cpp:499
+            const uint32_t second = max(max(min(wA, wT), min(wC, wG)), min(max(wA, wT), max(wC, wG)));
+            want_dinuc = __fmul_rn((float)second, norm2) > o.lc;   // a dinucleotide count <= second largest base count
+        }
+    }
+    {   // dinucleotide counts (rare), cooperative
+        uint32_t todo = __ballot_sync(0xffffffffu, want_dinuc);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint8_t *sp = raw + __shfl_sync(0xffffffffu, me.rc.seq, j);
+            const QualAt qaj{reinterpret_cast<const signed char *>(raw + __shfl_sync(0xffffffffu, me.rc.qual, j)),
+                             __shfl_sync(0xffffffffu, me.lead, j), __shfl_sync(0xffffffffu, me.trail, j), o.in_off};
+            const bool res = dinucleotide_low_complexity(kc, sp, qaj, __shfl_sync(0xffffffffu, w.lo, j), __shfl_sync(0xffffffffu, w.wl, j),
+                                                         __shfl_sync(0xffffffffu, norm2, j));
+            if ((int)lane == j) lowc = res;
+        }
+    }
+    if (!me.done && w.ret) {
+        if (lowc) {
+            atomicAdd(&H.filt()[FQ_READ_LOW_COMPLEXITY], 1u);
+            atomicAdd(&H.filt()[FQ_BASE_LOW_COMPLEXITY], w.wl);
+            w.flags |= FQ_RR_F_LOWCOMP;
+            w.ret = false;
+        } else if (need_max && max_qv + o.out_off > 127) {  // trim.cpp:516-525
+            ge.bits |= kErrReencode;
+            ge.rec = min(ge.rec, r);
+        }
+    }
+
+    // ---- phase 2c: one lane per read: POST scalar statistics and the verdict (trim.cpp:527-548)
+    v_off5 = g_off5;
+    v_lenflags = g_lenflags;
+    if (!me.done) {
+        if (w.ret) {
+            w.flags |= FQ_RR_VALID;
+            acc.trimmed += 1;
+            acc.trimmed_len += w.wl;
+            acc.max_post_rows = max(acc.max_post_rows, w.off5 + w.wl);
+            acc.max_post_len1 = max(acc.max_post_len1, w.wl + 1);
+            const uint32_t p_atc = wA | (wT << 10) | (wC << 20), p_gn = wG | (wN << 10);
+            lane_scalar_stats(kc, 1, w.wl, p_atc, p_gn, (int)ave_q);
+        }
+        const uint32_t masked = (me.lead > 0 || me.trail < len) ? kFlagMasked : 0u;
+        v_off5 = w.off5;
+        v_lenflags = pack_len_flags(w.ret ? w.wl : 0, w.flags | masked);
+        fq_read_result *dbg = mate ? a.dbg[1] : a.dbg[0];
+        if (dbg) {
+            fq_read_result d;
+            d.offset_5 = w.off5;
+            d.length = w.ret ? w.wl : 0;
+            d.flags = (uint16_t)w.flags;
+            d.adapter = (int16_t)w.best_adapter;
+            d.avg_q = ave_q;
+            dbg[r] = d;
+        }
+    }
+
+    // ---- phase 3c: cooperative: the window of reads that turned out invalid (mode 1), surviving G->N (mode 2)
+    {
+        const bool inv = !me.done && !w.ret && w.wl > 0;
+        const bool g2n = !me.done && w.ret && n_lowg > 0;
+        uint32_t todo = __ballot_sync(0xffffffffu, inv || g2n);
+        const uint32_t inv_mask = __ballot_sync(0xffffffffu, inv);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint8_t *sp = raw + __shfl_sync(0xffffffffu, me.rc.seq, j);
+            const signed char *qp = reinterpret_cast<const signed char *>(raw + __shfl_sync(0xffffffffu, me.rc.qual, j));
+            uint32_t d0 = 0, d1 = 0, d3 = 0;
+            int d2 = 0, d4 = -1;
+            removed_pass(kc, ((inv_mask >> j) & 1u) ? 1 : 2, sp, qp, __shfl_sync(0xffffffffu, len, j), __shfl_sync(0xffffffffu, w.lo, j),
+                         __shfl_sync(0xffffffffu, w.wl, j), __shfl_sync(0xffffffffu, me.lead, j), __shfl_sync(0xffffffffu, me.trail, j),
+                         d0, d1, d2, d3, d4);
+        }
+    }
+}
+
+// Fill the CTA's shared tables (call with all threads, then __syncthreads()).
+__device__ __forceinline__ void init_shared_tables(const SmemHist &H, const TrimArgs &a, const DevOpts &o)
+{
     const size_t n_words = SmemHist::words(a.smem_rows, a.comp_key_len);
     for (size_t i = threadIdx.x; i < n_words; i += blockDim.x) g_smem[i] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
-        H.lut()[i] = lut_entry(i);
-        const int code = base_code_slow(i);
-        H.lut_base()[i] = code < 5 ? make_uint2((uint32_t)((2 * kQualCols + code) * a.smem_rows) * 4u, 1u << (5 * code)) : make_uint2(H.trash_bytes(), 0u);
-        const int ch = (int)(signed char)i, qv = max(0, ch - o.in_off);
-        H.lut_qual()[i] = make_uint2(qv <= FQ_MAX_QUALITY_SCORE ? (uint32_t)(qv * a.smem_rows) * 4u : H.trash_bytes(), (uint32_t)ch);
+    for (uint32_t i = threadIdx.x; i < 258; i += blockDim.x) {
+        if (i < 256) {
+            H.lut()[i] = lut_entry(i);
+            const int code = base_code_slow(i);
+            H.lut_base()[i] = code < 5 ? make_uint2((SmemHist::kHist + (uint32_t)((2 * kQualCols + code) * a.smem_rows)) * 4u, code < 4 ? 1u << (8 * code) : 0u)
+                                       : make_uint2(H.trash_bytes(), 0u);
+            const int ch = (int)(signed char)i, qv = max(0, ch - o.in_off);
+            H.lut_qual()[i] = qv <= FQ_MAX_QUALITY_SCORE ? make_uint2((SmemHist::kHist + (uint32_t)(qv * a.smem_rows)) * 4u, (uint32_t)ch)
+                                                         : make_uint2(H.trash_bytes(), (uint32_t)(ch + kBadQual));
+        } else H.lut_qual()[i] = make_uint2(H.trash_bytes(), 0u);       // pad entry (kQualPad) and its alignment filler
     }
-    __syncthreads();
+}
 
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t total = a.n_rec * a.n_mates;
+// Merge at the end of the kernel: lane accumulators -> warp -> global; shared -> global (matrix.h:111-142 / trim.cpp:120-154).
+__device__ __forceinline__ void flush_accumulators(const KernelCtx &kc, const LaneAcc &acc, const GroupErr &ge)
+{
+    const TrimArgs &a = kc.a;
+    const SmemHist &H = kc.H;
     const StatsLayout &L = a.L;
-    unsigned long long *const S = a.stats;
-    const uint32_t R = H.rows;
-    const KernelCtx kc{a, o, H, S, lane};
-    LaneAcc acc;
-    uint32_t err = 0, err_rec = 0xffffffffu;
-    const bool need_max = o.in_off != o.out_off && o.out_off + FQ_MAX_QUALITY_SCORE > 127;   // re-encode can overflow
-
-    for (uint32_t base = warp_global * 32; base < total; base += n_warps * 32) {
-        // ---- each lane owns one read of this group
-        const uint32_t g = base + lane;
-        LaneRead me;
-        me.done = g >= total;
-        const uint32_t mate = (!me.done && g >= a.n_rec) ? 1 : 0;
-        const uint32_t r = me.done ? 0 : g - mate * a.n_rec;
-        me.rc = Rec{0, 0, 0, 0};
-        if (!me.done) me.rc = (mate ? a.rec[1] : a.rec[0])[r];
-        me.sum_q = 0; me.cnt_atc = 0; me.cnt_gn = 0; me.lead = 0; me.trail = me.rc.len; me.run_whole = 0;
-        const uint8_t *raw_mine = mate ? a.raw[1] : a.raw[0];
-
-        // ---- phase 1: cooperative per-base pass, read by read
-        const uint32_t n_here = min(32u, total - base);
-        uint32_t max_row = 0;           // highest quality row any base of this group was counted in
-        const uint32_t split = base < a.n_rec ? min(32u, a.n_rec - base) : 0u;     // reads j >= split belong to mate 2
-#if FQ_TRIM_PIPE
-        constexpr int KP = KSEL == 4 ? 4 : 5;
-        uint32_t nc[KP], nq[KP], ninc[KP], nlen = 0;        // the next read's bytes: requested one read ahead
-        if (KSEL != 0) {
-            nlen = __shfl_sync(0xffffffffu, me.rc.len, 0);
-            phase1_load<KP>(kc, split ? a.raw[0] : a.raw[1], __shfl_sync(0xffffffffu, me.rc.seq, 0), __shfl_sync(0xffffffffu, me.rc.qual, 0), nlen, nc, nq, ninc);
-        }
-#endif
-        for (uint32_t j = 0; j < n_here; ++j) {
-#if FQ_TRIM_PIPE
-            if (KSEL != 0) {
-                uint32_t c[KP], q[KP], inc[KP];
-#pragma unroll
-                for (int k = 0; k < KP; ++k) { c[k] = nc[k]; q[k] = nq[k]; inc[k] = ninc[k]; }
-                const uint32_t len = nlen;
-                if (j + 1 < n_here) {
-                    nlen = __shfl_sync(0xffffffffu, me.rc.len, j + 1);
-                    phase1_load<KP>(kc, (j + 1 >= split) ? a.raw[1] : a.raw[0], __shfl_sync(0xffffffffu, me.rc.seq, j + 1),
-                                    __shfl_sync(0xffffffffu, me.rc.qual, j + 1), nlen, nc, nq, ninc);
-                }
-                int s_sum = 0;
-                uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
-                phase1_body<KP>(kc, c, q, inc, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-                if (lane == j) {
-                    me.sum_q = s_sum; me.cnt_atc = s_atc; me.cnt_gn = s_gn; me.lead = s_lead; me.trail = s_trail; me.run_whole = s_run;
-                }
-                continue;
-            }
-#endif
-            const uint32_t len = __shfl_sync(0xffffffffu, me.rc.len, j);
-            const uint32_t seq = __shfl_sync(0xffffffffu, me.rc.seq, j);
-            const uint32_t qual = __shfl_sync(0xffffffffu, me.rc.qual, j);
-            const uint32_t mj = j >= split ? 1 : 0;
-            const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
-            int s_sum = 0;
-            uint32_t s_atc = 0, s_gn = 0, s_lead = 0, s_trail = len, s_run = 0;
-            bool generic = false;
-            // KSEL 4 / 5: the host launches these instances only for batches whose longest read fits the width, so
-            // the generic path (and its code) is not part of them
-            if (KSEL == 4) phase1<4>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else if (KSEL == 5) phase1<5>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else if (len <= 128 && len <= R) phase1<4>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else if (len <= 160 && len <= R) phase1<5>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else if (len <= 320 && len <= R) phase1<10>(kc, rawj, seq, qual, len, s_sum, s_atc, s_gn, s_lead, s_trail, s_run, max_row);
-            else {
-                const Rec rcj{__shfl_sync(0xffffffffu, me.rc.hdr, j), seq, qual, len};
-                process_generic(kc, mj, base + j - mj * a.n_rec, rcj);
-                generic = true;
-            }
-            if (lane == j) {
-                me.sum_q = s_sum; me.cnt_atc = s_atc; me.cnt_gn = s_gn; me.lead = s_lead; me.trail = s_trail; me.run_whole = s_run;
-                me.done = generic;
-            }
-        }
-
-        if (__any_sync(0xffffffffu, max_row == H.trash_bytes())) {
-            // a quality score above 41 (fastq.h:31-33): find the first offending read of the group
-            for (uint32_t j = 0; j < n_here; ++j) {
-                const uint32_t lenj = __shfl_sync(0xffffffffu, me.rc.len, j), qual = __shfl_sync(0xffffffffu, me.rc.qual, j);
-                const uint32_t lead = __shfl_sync(0xffffffffu, me.lead, j), trail = __shfl_sync(0xffffffffu, me.trail, j);
-                const bool skip = __shfl_sync(0xffffffffu, (int)me.done, j) != 0;      // generic path reports its own errors
-                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
-                const signed char *qp = reinterpret_cast<const signed char *>((mj ? a.raw[1] : a.raw[0]) + qual);
-                bool bad = false;
-                for (uint32_t p = lane; p < lenj && !skip; p += 32)
-                    bad |= p >= lead && p < trail && (int)qp[p] - o.in_off > FQ_MAX_QUALITY_SCORE;
-                if (__any_sync(0xffffffffu, bad)) {
-                    err |= kErrQualGt41;
-                    err_rec = min(err_rec, base + j - mj * a.n_rec);
-                    break;
-                }
-            }
-        }
-#ifdef FQ_EXP_PHASE1_ONLY
-        continue;
-#endif
-        // ---- phase 2a: one lane per read: PRE scalar statistics and the window
-        const signed char *qp_mine = reinterpret_cast<const signed char *>(raw_mine + me.rc.qual);
-        const uint32_t len = me.rc.len;
-        const QualAt qa{qp_mine, me.lead, me.trail, o.in_off};
-        Window w{0, len, 0, 0, false, -1};
-        if (!me.done) {
-            lane_scalar_stats(kc, 0, len, me.cnt_atc, me.cnt_gn, (int)average_quality(me.sum_q, len, o.in_off));
-            acc.reads += 1;
-            acc.len += len;
-            acc.max_pre_rows = max(acc.max_pre_rows, len);
-            w = lane_window(kc, mate, r, len, qa);
-        }
-
-        // ---- phase 3a: cooperative pass over the bases outside the window (and G->N candidates / max quality inside)
-        uint32_t w_atc = me.cnt_atc, w_gn = me.cnt_gn, n_lowg = 0;
-        int sum_w = me.sum_q, max_qv = 0;
-        {
-            const bool partial = !me.done && (w.lo > 0 || w.lo + w.wl < len);
-            const bool want = !me.done && (partial || ((o.replace_q > 0 || need_max) && w.ret));
-            uint32_t todo = __ballot_sync(0xffffffffu, want);
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
-                const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
-                const uint32_t lenj = __shfl_sync(0xffffffffu, len, j);
-                const uint8_t *sp = rawj + __shfl_sync(0xffffffffu, me.rc.seq, j);
-                const signed char *qp = reinterpret_cast<const signed char *>(rawj + __shfl_sync(0xffffffffu, me.rc.qual, j));
-                const uint32_t lo = __shfl_sync(0xffffffffu, w.lo, j), wl = __shfl_sync(0xffffffffu, w.wl, j);
-                const uint32_t lead = __shfl_sync(0xffffffffu, me.lead, j), trail = __shfl_sync(0xffffffffu, me.trail, j);
-                uint32_t r_atc = 0, r_gn = 0, nl = 0;
-                int r_sum = 0, mq = need_max ? 0 : -1;
-                removed_pass(kc, 0, sp, qp, lenj, lo, wl, lead, trail, r_atc, r_gn, r_sum, nl, mq);
-                if ((int)lane == j) {
-                    w_atc -= r_atc;            // fields never borrow: removed counts <= totals per class
-                    w_gn -= r_gn;
-                    sum_w -= r_sum;
-                    n_lowg = nl;
-                    max_qv = mq;
-                }
-            }
-        }
-
-        // ---- phase 2b: one lane per read: filters (trim.cpp:363-513)
-        float ave_q = 0.0f;
-        bool want_dinuc = false, want_run = false;
-        float norm2 = 0.0f;
-        uint32_t wA = f10(w_atc, 0), wT = f10(w_atc, 1), wC = f10(w_atc, 2), wG = f10(w_gn, 0), wN = f10(w_gn, 1);
-        if (!me.done && w.ret) {
-            wG -= n_lowg;                                       // G -> N replacement happens before the complexity filter
-            wN += n_lowg;
-            if (me.run_whole >= o.max_poly_n) want_run = true;  // exact run inside the window needed
-        }
-        {   // exact 'N' run of the window (rare: the whole read has a long enough run)
-            uint32_t todo = __ballot_sync(0xffffffffu, want_run);
-            uint32_t run_w = 0;
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
-                const uint8_t *sp = (mj ? a.raw[1] : a.raw[0]) + __shfl_sync(0xffffffffu, me.rc.seq, j);
-                const uint32_t rw = window_n_run(kc, sp, __shfl_sync(0xffffffffu, w.lo, j), __shfl_sync(0xffffffffu, w.wl, j));
-                if ((int)lane == j) run_w = rw;
-            }
-            if (want_run && run_w >= o.max_poly_n) {            // trim.cpp:363-371
-                atomicAdd(&H.filt()[FQ_READ_NN], 1u);
-                atomicAdd(&H.filt()[FQ_BASE_NN], w.wl);
-                w.flags |= FQ_RR_F_NN;
-                if (!o.qc_only) w.ret = false;
-            }
-        }
-        if (!me.done && w.ret) {
-            ave_q = average_quality(sum_w, w.wl, o.in_off);
-            if (ave_q < o.avg_q) {                              // trim.cpp:374-382
-                atomicAdd(&H.filt()[FQ_READ_AVG_Q], 1u);
-                atomicAdd(&H.filt()[FQ_BASE_AVG_Q], w.wl);
-                w.flags |= FQ_RR_F_AVGQ;
-                w.ret = false;
-            }
-        }
-        bool lowc = false;
-        if (!me.done && w.ret) {                                // low complexity, trim.cpp:405-513
-            const float norm = (float)(1.0 / (double)w.wl);     // trim.cpp:483
-            lowc = __fmul_rn((float)wA, norm) > o.lc || __fmul_rn((float)wT, norm) > o.lc ||
-                   __fmul_rn((float)wG, norm) > o.lc || __fmul_rn((float)wC, norm) > o.lc;
-            if (!lowc) {
-                norm2 = norm * 2.0f;                            // trim.cpp:499
-                const uint32_t second = max(max(min(wA, wT), min(wC, wG)), min(max(wA, wT), max(wC, wG)));
-                want_dinuc = __fmul_rn((float)second, norm2) > o.lc;   // a dinucleotide count <= second largest base count
-            }
-        }
-        {   // dinucleotide counts (rare), cooperative
-            uint32_t todo = __ballot_sync(0xffffffffu, want_dinuc);
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
-                const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
-                const uint8_t *sp = rawj + __shfl_sync(0xffffffffu, me.rc.seq, j);
-                const QualAt qaj{reinterpret_cast<const signed char *>(rawj + __shfl_sync(0xffffffffu, me.rc.qual, j)),
-                                 __shfl_sync(0xffffffffu, me.lead, j), __shfl_sync(0xffffffffu, me.trail, j), o.in_off};
-                const bool res = dinucleotide_low_complexity(kc, sp, qaj, __shfl_sync(0xffffffffu, w.lo, j), __shfl_sync(0xffffffffu, w.wl, j),
-                                                             __shfl_sync(0xffffffffu, norm2, j));
-                if ((int)lane == j) lowc = res;
-            }
-        }
-        if (!me.done && w.ret) {
-            if (lowc) {
-                atomicAdd(&H.filt()[FQ_READ_LOW_COMPLEXITY], 1u);
-                atomicAdd(&H.filt()[FQ_BASE_LOW_COMPLEXITY], w.wl);
-                w.flags |= FQ_RR_F_LOWCOMP;
-                w.ret = false;
-            } else if (need_max && max_qv + o.out_off > 127) {  // trim.cpp:516-525
-                err |= kErrReencode;
-                err_rec = min(err_rec, r);
-            }
-        }
-
-        // ---- phase 2c: one lane per read: POST scalar statistics and the verdict (trim.cpp:527-548)
-        if (!me.done) {
-            if (w.ret) {
-                w.flags |= FQ_RR_VALID;
-                acc.trimmed += 1;
-                acc.trimmed_len += w.wl;
-                acc.max_post_rows = max(acc.max_post_rows, w.off5 + w.wl);
-                acc.max_post_len1 = max(acc.max_post_len1, w.wl + 1);
-                const uint32_t p_atc = wA | (wT << 10) | (wC << 20), p_gn = wG | (wN << 10);
-                lane_scalar_stats(kc, 1, w.wl, p_atc, p_gn, (int)ave_q);
-            }
-            const uint32_t masked = (me.lead > 0 || me.trail < len) ? kFlagMasked : 0u;
-            (mate ? a.res[1] : a.res[0])[r] = make_uint2(w.off5, pack_len_flags(w.ret ? w.wl : 0, w.flags | masked));
-            fq_read_result *dbg = mate ? a.dbg[1] : a.dbg[0];
-            if (dbg) {
-                fq_read_result d;
-                d.offset_5 = w.off5;
-                d.length = w.ret ? w.wl : 0;
-                d.flags = (uint16_t)w.flags;
-                d.adapter = (int16_t)w.best_adapter;
-                d.avg_q = ave_q;
-                dbg[r] = d;
-            }
-        }
-
-        // ---- phase 3c: cooperative: the window of reads that turned out invalid (mode 1), surviving G->N (mode 2)
-        {
-            const bool inv = !me.done && !w.ret && w.wl > 0;
-            const bool g2n = !me.done && w.ret && n_lowg > 0;
-            uint32_t todo = __ballot_sync(0xffffffffu, inv || g2n);
-            const uint32_t inv_mask = __ballot_sync(0xffffffffu, inv);
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t mj = (base + j >= a.n_rec) ? 1 : 0;
-                const uint8_t *rawj = mj ? a.raw[1] : a.raw[0];
-                const uint8_t *sp = rawj + __shfl_sync(0xffffffffu, me.rc.seq, j);
-                const signed char *qp = reinterpret_cast<const signed char *>(rawj + __shfl_sync(0xffffffffu, me.rc.qual, j));
-                uint32_t d0 = 0, d1 = 0, d3 = 0;
-                int d2 = 0, d4 = -1;
-                removed_pass(kc, ((inv_mask >> j) & 1u) ? 1 : 2, sp, qp, __shfl_sync(0xffffffffu, len, j), __shfl_sync(0xffffffffu, w.lo, j),
-                             __shfl_sync(0xffffffffu, w.wl, j), __shfl_sync(0xffffffffu, me.lead, j), __shfl_sync(0xffffffffu, me.trail, j),
-                             d0, d1, d2, d3, d4);
-            }
-        }
-    }
-
-    // ---- merge: lane accumulators -> warp -> global; shared -> global (matrix.h:111-142 / trim.cpp:120-154)
+    unsigned long long *const S = kc.S;
+    const uint32_t lane = kc.lane, R = H.rows;
     {
         const uint32_t reads = warp_sum(acc.reads), trimmed = warp_sum(acc.trimmed);
         unsigned long long len_sum = acc.len, tlen_sum = acc.trimmed_len;
@@ -1191,8 +1226,8 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
         const uint32_t pre_rows = __reduce_max_sync(0xffffffffu, acc.max_pre_rows);
         const uint32_t post_rows = __reduce_max_sync(0xffffffffu, acc.max_post_rows);
         const uint32_t post_len1 = __reduce_max_sync(0xffffffffu, acc.max_post_len1);
-        const uint32_t err_all = __reduce_or_sync(0xffffffffu, err);
-        const uint32_t err_min = __reduce_min_sync(0xffffffffu, err_rec);
+        const uint32_t err_all = __reduce_or_sync(0xffffffffu, ge.bits);
+        const uint32_t err_min = __reduce_min_sync(0xffffffffu, ge.rec);
         if (lane == 0) {
             if (reads) {
                 gadd(&S[L.filter + FQ_TOTAL_COUNT], reads);
@@ -1258,6 +1293,50 @@ __global__ void __launch_bounds__(kTrimThreads, FQ_TRIM_MIN_CTAS) k_trim(const T
             gadd(&S[(which ? L.post_comp : L.pre_comp) + (size_t)hist * kCompBins + bin], v);
         }
     }
+}
+
+constexpr int kTrimThreads = FQ_TRIM_THREADS;
+
+// KSEL: which register-resident phase-1 widths this instance carries (the host picks it from the batch's longest read):
+//   4: reads <= 128 bases, 5: reads <= 160 bases, 0: all widths (5 and 10 chunks of 32 bases) + the chunked generic path for
+//   longer reads.  Specialised instances keep the hot loop small: the kernel is issue-bound and instruction-cache sensitive.
+// PLAIN: the option set of a default run (BWA_plus, no 5'/3' clip, no adapters, no G->N replacement, no re-encoding,
+//   not --qc_only) is baked in, so every branch on those options disappears from the instance.
+// Persistent grid, one CTA per SM; a warp takes groups of 32 consecutive reads of one mate (mate 1's groups first).
+template <int KSEL, bool PLAIN>
+__global__ void __launch_bounds__(kTrimThreads, 1) k_trim(const TrimArgs a, const DevOpts o_in)
+{
+    DevOpts o = o_in;
+    if (PLAIN) {
+        o.mode = FQ_MODE_BWA_PLUS;
+        o.trim_5 = 0;
+        o.trim_3 = 0;
+        o.replace_q = 0;
+        o.qc_only = 0;
+        o.filter_adapter = 0;
+        o.out_off = o.in_off;
+    }
+    SmemHist H{a.smem_rows, a.comp_key_len};
+    init_shared_tables(H, a, o);
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const KernelCtx kc{a, o, H, a.stats, lane, (uint32_t)__cvta_generic_to_shared(g_smem) + 4 * lane, min(a.n_mates, 1u)};
+    const uint32_t groups_per_mate = (a.n_rec + 31) / 32, n_groups = groups_per_mate * a.n_mates;
+    LaneAcc acc;
+    GroupErr ge;
+    for (uint32_t g = warp_global; g < n_groups; g += n_warps) {
+        const uint32_t mate = g >= groups_per_mate ? 1u : 0u;
+        const uint32_t r0 = (g - mate * groups_per_mate) * 32, r = r0 + lane;
+        Rec rc{0, 0, 0, 0};
+        if (r < a.n_rec) rc = (mate ? a.rec[1] : a.rec[0])[r];
+        uint32_t off5 = 0, lenflags = 0;
+        trim_group<KSEL, PLAIN>(kc, mate, r0, rc, acc, ge, off5, lenflags);
+        if (r < a.n_rec) (mate ? a.res[1] : a.res[0])[r] = make_uint2(off5, lenflags);
+    }
+    flush_accumulators(kc, acc, ge);
 }
 
 }  // namespace fq
