@@ -104,6 +104,7 @@ struct fq_ctx {
     uint64_t next_ticket = 0;
     bool debug_results = false;
     bool check_pair_ids = true;
+    bool frame_exact[2] = {false, false};      // this mate's input is not plain LF text: skip the fast framing instance
 
     // host-side stats views handed out by fq_stats
     std::vector<uint64_t> v_adapter_reads, v_adapter_bases, v_pre_q, v_post_q, v_pre_b, v_post_b, v_hist[4], v_pre_comp,
@@ -238,7 +239,7 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
     BatchInfo *info = ctx->d_info.as<BatchInfo>();
     // single-pass segmented line index: one contiguous segment per resident warp, no cross-warp dependency
     int frame_ctas = 4;                                     // resident CTAs per SM -> exactly one wave of segments
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&frame_ctas, k_frame_lines, kFrameThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&frame_ctas, k_frame_lines<false>, kFrameThreads, 0));
     const uint32_t want_warps = (uint32_t)ctx->sm_count * (uint32_t)std::max(frame_ctas, 1) * (kFrameThreads / 32);
     uint32_t seg_bytes = (uint32_t)((n + want_warps - 1) / want_warps);
     seg_bytes = std::max<uint32_t>(kChunkBytes, (seg_bytes + kChunkBytes - 1) / kChunkBytes * kChunkBytes);
@@ -256,12 +257,20 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
             CK(cudaMemsetAsync(&info->n_cr_eol[m], 0, 4, ctx->stream));
             CK(cudaMemsetAsync(&info->seg_overflow, 0, 4, ctx->stream));
         }
-        k_frame_lines<<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, seg_bytes, n_seg, ctx->d_nl[m].as<uint32_t>(), seg_cap, seg_count, info, m);
+        // the fast instance first (plain LF text); the exact instance right behind it does the work only if the fast one met
+        // a control character other than '\n' (CRLF input: remembered, later batches go straight to the exact instance)
+        if (!ctx->frame_exact[m]) {
+            k_frame_lines<true><<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, seg_bytes, n_seg, ctx->d_nl[m].as<uint32_t>(), seg_cap, seg_count, info, m, 0);
+            ctx->launches++;
+        }
+        k_frame_lines<false><<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, seg_bytes, n_seg, ctx->d_nl[m].as<uint32_t>(), seg_cap, seg_count, info, m,
+                                                                     ctx->frame_exact[m] ? 0 : 1);
         k_scan_segments<<<1, 1024, 0, ctx->stream>>>(seg_count, n_seg, seg_base, info, m);
         ctx->launches += 2;
         CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         n_lines = ctx->h_info->n_lines[m];
+        if (ctx->h_info->frame_exact[m]) ctx->frame_exact[m] = true;
         if (ctx->h_info->seg_overflow == 0) break;
         seg_cap = ctx->h_info->seg_overflow + 64;           // very short lines: repeat once with the exact need
     }

@@ -64,6 +64,8 @@ struct BatchInfo {
     uint32_t err;              // kErr* bits
     uint32_t err_record;       // smallest record index that raised an error
     uint32_t seg_overflow;     // largest per-segment line count that did not fit its index region (0 = none)
+    uint32_t frame_exact[2];   // the fast framing kernel met a control character that is not '\n': the exact kernel must run
+    uint32_t seg_overflow_fast;
     uint32_t pad0;
     unsigned long long detect_key;   // autodetect: (record << 8 | offset), min over decisive reads
     unsigned long long out_bytes[4];
@@ -128,7 +130,9 @@ struct StatsRows {
 // internal verdict flag (not part of the public FQ_RR_* set): terminal-N quality masking touched this read
 constexpr uint32_t kFlagMasked = 0x80u;
 
-// trim verdict packing
+// trim verdict packing: res.x = offset_5 | kResPlusBad (the one-character third line of the record is not "+": the record
+// must not be block-copied), res.y = length | flags << 24
+constexpr uint32_t kResPlusBad = 1u << 31;
 constexpr uint32_t kResLenBits = 24;            // reads < 16 Mi bases
 constexpr uint32_t kResLenMask = (1u << kResLenBits) - 1;
 

@@ -293,8 +293,9 @@ __device__ __forceinline__ LaneRec lane_record(const EmitArgs &a, const DevOpts 
     const bool requal = o.in_off != o.out_off;
     for (int m = 0; m < n_mates; ++m) {
         L.rc[m] = a.rec[m][r];
-        L.res[m] = a.res[m][r];
-        L.canon[m] = a.canon[m][r] != 0;
+        const uint2 rv = a.res[m][r];
+        L.res[m] = make_uint2(rv.x & ~kResPlusBad, rv.y);
+        L.canon[m] = a.canon[m][r] != 0 && !(rv.x & kResPlusBad);
         const uint32_t fl = L.res[m].y >> kResLenBits, wl = L.res[m].y & kResLenMask;
         L.valid[m] = (fl & FQ_RR_VALID) != 0;
         L.tsize[m] = header_len(a.raw[m], L.rc[m], L.canon[m]) + 2 * wl + 5;

@@ -40,7 +40,6 @@ constexpr uint32_t kFrameTile = (kFrameThreads / 32) * kChunkBytes;   // 32 KiB
 // A line-index entry is the byte offset of a '\n' plus two facts about the byte before it, so
 // that record building never has to touch the raw bytes again (a batch is < 1 GiB per mate).
 constexpr uint32_t kNlCr = 1u << 31;      // preceded by '\r'  (CRLF line end)
-constexpr uint32_t kNlPlus = 1u << 30;    // preceded by '+'
 constexpr uint32_t kNlPosMask = (1u << 30) - 1;
 
 // Exact zero-byte mask: 0x80 in every byte of x that is zero (no cross-byte borrows).
@@ -66,6 +65,23 @@ __device__ __forceinline__ uint32_t has_byte(uint32_t w, uint32_t c4)      // no
     return (x - 0x01010101u) & ~x & 0x80808080u;
 }
 
+// 16-bit mask (bit i = byte i), shifted left by 7, of the bytes of a 16-byte vector whose value lies in 0x08..0x0f ('\n' and
+// its class): per word one exact zero-byte test on the value with the low three bits cleared (three instructions: the two
+// constants sit in registers so that (w & c1) ^ c2 is one LOP3) and one dot product that drops the four 0x80 flags into
+// consecutive bits.
+__device__ __forceinline__ uint32_t class_flags(uint32_t w, uint32_t c_f8, uint32_t c_08)     // 0x80 in every byte of w that lies in 0x08..0x0f
+{
+    uint32_t x;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(x) : "r"(w), "r"(c_f8), "r"(c_08));           // (w & c_f8) ^ c_08
+    return (x - 0x01010101u) & ~x & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t class_mask16_shl7(const uint4 &v, uint32_t c_f8, uint32_t c_08)
+{
+    const uint32_t lo = __dp4a(class_flags(v.y, c_f8, c_08), 0x80402010u, __dp4a(class_flags(v.x, c_f8, c_08), 0x08040201u, 0u));
+    const uint32_t hi = __dp4a(class_flags(v.w, c_f8, c_08), 0x80402010u, __dp4a(class_flags(v.z, c_f8, c_08), 0x08040201u, 0u));
+    return lo + (hi << 8);
+}
+
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane)
 {
 #pragma unroll
@@ -81,20 +97,30 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane)
 // it writes the offsets of its '\n' bytes, in order, to its own region nl_seg[w * seg_cap ...]
 // and its line count to seg_count[w].  A tiny scan (k_scan_segments) then turns the counts into
 // global line bases and k_build_records maps global line numbers to (segment, local index).
+//
+// Two instances.  FAST (the first one launched): one exact 3-instruction SWAR test per 32-bit word for the byte class
+// 0x08..0x0f -- with the low three bits masked off, a byte of the word is zero exactly for that class and the classic
+// (x - 0x01..) & ~x & 0x80.. test has no false positives because a masked byte is never 0x01 -- then one dot-product
+// instruction per word turns the four flags into address-ordered mask bits.  Plain FASTQ text holds no other member of that
+// class than '\n', so every flagged byte is checked to BE '\n' when its index entry is written; the first one that is not
+// (a '\r' of a CRLF file, a tab) raises info->frame_exact[mate] and the EXACT instance, launched right behind, redoes the
+// mate with separate masks for '\n' and '\r' (it returns at once when the flag is not set).
 #ifndef FQ_FRAME_MIN_CTAS
 #define FQ_FRAME_MIN_CTAS 4
 #endif
+template <bool FAST>
 __global__ void __launch_bounds__(kFrameThreads, FQ_FRAME_MIN_CTAS) k_frame_lines(const uint8_t *__restrict__ raw, uint64_t n, uint32_t seg_bytes, uint32_t n_seg,
                                                                uint32_t *__restrict__ nl_seg, uint32_t seg_cap, uint32_t *__restrict__ seg_count,
-                                                               BatchInfo *info, int mate)
+                                                               BatchInfo *info, int mate, int only_if_flagged)
 {
+    if (!FAST && only_if_flagged && *reinterpret_cast<volatile uint32_t *>(&info->frame_exact[mate]) == 0) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_seg) return;
     const uint64_t seg_lo = (uint64_t)w * seg_bytes;
     const uint64_t seg_hi = min((uint64_t)n, seg_lo + seg_bytes);
     uint32_t *out = nl_seg + (size_t)w * seg_cap;
-    uint32_t rank0 = 0, any_cr = 0, cr_eol = 0;
+    uint32_t rank0 = 0, any_cr = 0, cr_eol = 0, not_nl = 0;
     const bool aligned32 = (reinterpret_cast<uintptr_t>(raw) & 31u) == 0;
     bool cr_before = true;        // the chunk in front of the segment belongs to another warp: assume it may end in CR
     for (uint64_t chunk_base = seg_lo; chunk_base < seg_hi; chunk_base += kChunkBytes) {
@@ -118,52 +144,85 @@ __global__ void __launch_bounds__(kFrameThreads, FQ_FRAME_MIN_CTAS) k_frame_line
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = __ldg(src + k);
         } else {
+            // bytes past the end of the segment read as 0xff: no member of any class the masks look for
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint64_t off = (uint64_t)lane_base + (uint64_t)k * 16;
-                v[k] = make_uint4(0, 0, 0, 0);
+                v[k] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
                 if (off + 16 <= seg_hi) v[k] = __ldg(reinterpret_cast<const uint4 *>(raw + off));
                 else if (off < seg_hi) {
-                    uint32_t x[4] = {0, 0, 0, 0};
-                    for (uint32_t b = 0; b < 16 && off + b < seg_hi; ++b) x[b >> 2] |= (uint32_t)raw[off + b] << (8 * (b & 3));
+                    uint32_t x[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                    for (uint32_t b = 0; b < 16 && off + b < seg_hi; ++b) x[b >> 2] = (x[b >> 2] & ~(0xffu << (8 * (b & 3)))) | ((uint32_t)raw[off + b] << (8 * (b & 3)));
                     v[k] = make_uint4(x[0], x[1], x[2], x[3]);
                 }
             }
         }
+        if (FAST) {
+            uint32_t c_f8 = 0xf8f8f8f8u, c_08 = 0x08080808u;
+            asm volatile("" : "+r"(c_f8), "+r"(c_08));                      // keep the two constants in registers
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t m = eq_mask16(v[k], 0x0a0a0a0au);
-            cr_chunk |= has_byte(v[k].x, 0x0d0d0d0du) | has_byte(v[k].y, 0x0d0d0d0du) | has_byte(v[k].z, 0x0d0d0d0du) | has_byte(v[k].w, 0x0d0d0d0du);
-            m16[k >> 1] |= m << (16 * (k & 1));
+            for (int k = 0; k < 4; ++k)
+                m16[k] = (class_mask16_shl7(v[2 * k], c_f8, c_08) >> 7) | (class_mask16_shl7(v[2 * k + 1], c_f8, c_08) << 9);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t m = eq_mask16(v[k], 0x0a0a0a0au);
+                cr_chunk |= has_byte(v[k].x, 0x0d0d0d0du) | has_byte(v[k].y, 0x0d0d0d0du) | has_byte(v[k].z, 0x0d0d0d0du) | has_byte(v[k].w, 0x0d0d0d0du);
+                m16[k >> 1] |= m << (16 * (k & 1));
+            }
         }
         any_cr |= cr_chunk;
         const uint32_t cnt = __popc(m16[0]) + __popc(m16[1]) + __popc(m16[2]) + __popc(m16[3]);
         const uint32_t incl = warp_incl_scan(cnt, lane);
         uint32_t rank = rank0 + incl - cnt;
-        // The byte in front of a newline decides two flags: "preceded by CR" and "preceded by '+'".  Loading it for every
-        // newline costs a third of the kernel's L1 requests, so: CR is only looked for when this chunk or the one before
-        // holds a CR at all (warp-uniform), and '+' only where it can matter -- a one-character line, i.e. the byte two
-        // positions back is a newline as well (kNlPlus is consulted for "+" lines of length one only).
+        if (FAST) {
+            // one entry per flagged byte, lowest address first; the flagged byte must BE '\n' (it sits in the cache line this
+            // lane has just loaded).  Which byte precedes it is not recorded here: LF text has no CR line ends, and the '+' of
+            // a bare "+" line is looked at by the kernel that decides whether a record can be block-copied (k_emit).
+            uint32_t m0 = m16[0], m1 = m16[1], m2 = m16[2], m3 = m16[3];
+            const uint8_t *mine = raw + lane_base;
+            for (;;) {
+                const uint32_t mw = m0 ? m0 : m1 ? m1 : m2 ? m2 : m3;
+                if (!mw) break;
+                const uint32_t off = (m0 ? 0u : m1 ? 32u : m2 ? 64u : 96u) + (uint32_t)(__ffs(mw) - 1);
+                not_nl |= (uint32_t)mine[off] ^ 0x0au;
+                if (rank < seg_cap) out[rank] = lane_base + off;
+                ++rank;
+                const uint32_t cleared = mw & (mw - 1);
+                if (m0) m0 = cleared; else if (m1) m1 = cleared; else if (m2) m2 = cleared; else m3 = cleared;
+            }
+        } else {
+        // The byte in front of a newline decides the flag "preceded by CR".  Loading it for every newline costs a third of the
+        // kernel's L1 requests, so it is only looked at when this chunk or the one before holds a CR at all (warp-uniform).
         const bool cr_here = __any_sync(0xffffffffu, cr_chunk != 0);
         const bool look_cr = cr_here || cr_before;
         cr_before = cr_here;
 #pragma unroll
         for (int w4 = 0; w4 < 4; ++w4) {
             uint32_t m = m16[w4];
-            const uint32_t two_back = (m16[w4] << 2) | (w4 ? m16[w4 ? w4 - 1 : 0] >> 30 : 3u);   // bit b: newline at b-2 (unknown across lanes: assume yes)
             while (m) {
                 const uint32_t b = (uint32_t)(__ffs(m) - 1);
                 const uint32_t pos = lane_base + (uint32_t)(w4 * 32) + b;
                 uint32_t prev = 0;
-                if (pos && (look_cr || ((two_back >> b) & 1u))) prev = raw[pos - 1];      // L1 resident: just loaded
-                const uint32_t e = pos | (prev == '\r' ? kNlCr : 0u) | (prev == '+' ? kNlPlus : 0u);
+                if (pos && look_cr) prev = raw[pos - 1];                                   // L1 resident: just loaded
+                const uint32_t e = pos | (prev == '\r' ? kNlCr : 0u);
                 cr_eol += prev == '\r';
                 if (rank < seg_cap) out[rank] = e;
                 ++rank;
                 m &= m - 1;
             }
         }
+        }
         rank0 += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (FAST) {
+        not_nl = __reduce_or_sync(0xffffffffu, not_nl);
+        if (lane == 0) {
+            seg_count[w] = rank0;
+            if (rank0 > seg_cap) atomicMax(&info->seg_overflow_fast, rank0);
+            if (not_nl) atomicOr(&info->frame_exact[mate], 1u);
+        }
+        return;
     }
     any_cr = __reduce_or_sync(0xffffffffu, any_cr);
     cr_eol = __reduce_add_sync(0xffffffffu, cr_eol);
@@ -198,7 +257,13 @@ __global__ void __launch_bounds__(1024) k_scan_segments(const uint32_t *__restri
         if (threadIdx.x == 1023) carry = before + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { seg_base[n_seg] = carry; info->n_lines[mate] = carry; }
+    if (threadIdx.x == 0) {
+        seg_base[n_seg] = carry;
+        info->n_lines[mate] = carry;
+        // the index was written by the fast framing instance unless it asked for the exact one
+        if (info->frame_exact[mate] == 0 && info->seg_overflow_fast > info->seg_overflow) info->seg_overflow = info->seg_overflow_fast;
+        info->seg_overflow_fast = 0;
+    }
 }
 
 // Exact count of one byte value (only launched when k_frame_lines saw a '\r': CRLF input).
@@ -274,9 +339,10 @@ __global__ void __launch_bounds__(256) k_build_records(const LineIndex li, uint3
         const uint32_t qlen = p3 - qual - c3;
         bad = (len != qlen);
         rec[r] = Rec{hdr, seq, qual, len};
-        // canonical record: LF line ends and a bare "+" line, i.e. the raw bytes ARE what write_read
-        // (fastq.cpp:127-138) prints for an untouched read, so emission can be a block copy
-        canon[r] = (uint8_t)(!(c0 | c1 | c2 | c3) && p2 == plus + 1 && (ez & kNlPlus));
+        // canonical record: LF line ends and a one-character third line; when that character is '+' (k_trim looks at it
+        // and clears the claim in its verdict otherwise) the raw bytes ARE what write_read (fastq.cpp:127-138) prints for an
+        // untouched read, so emission can be a block copy
+        canon[r] = (uint8_t)(!(c0 | c1 | c2 | c3) && p2 == plus + 1);
     }
     uint32_t m = len;
 #pragma unroll

@@ -1141,7 +1141,11 @@ __device__ __forceinline__ void trim_group(const KernelCtx &kc, uint32_t mate, u
     }
 
     // ---- phase 2c: one lane per read: POST scalar statistics and the verdict (trim.cpp:527-548)
-    v_off5 = g_off5;
+    // third line of the record: with LF line ends and a one-character line it sits two bytes behind the bases (same sector
+    // as the end of the bases or the start of the qualities); anything but '+' bars the record from being block-copied
+    uint32_t plus_bad = 0;
+    if (lane < n_here && me.rc.qual == me.rc.seq + me.rc.len + 3 && raw[me.rc.seq + me.rc.len + 1] != '+') plus_bad = kResPlusBad;
+    v_off5 = g_off5 | plus_bad;
     v_lenflags = g_lenflags;
     if (!me.done) {
         if (w.ret) {
@@ -1154,7 +1158,7 @@ __device__ __forceinline__ void trim_group(const KernelCtx &kc, uint32_t mate, u
             lane_scalar_stats(kc, 1, w.wl, p_atc, p_gn, (int)ave_q);
         }
         const uint32_t masked = (me.lead > 0 || me.trail < len) ? kFlagMasked : 0u;
-        v_off5 = w.off5;
+        v_off5 = w.off5 | plus_bad;
         v_lenflags = pack_len_flags(w.ret ? w.wl : 0, w.flags | masked);
         fq_read_result *dbg = mate ? a.dbg[1] : a.dbg[0];
         if (dbg) {

@@ -116,6 +116,23 @@ def test_crlf_and_ragged_headers():
     both(r1, None, lambda: Options(replace_to_N_q=10, min_read_length=10, discard_output=True))
 
 
+def test_third_line_variants():
+    """fastq.cpp:79-91: the content of the '+' line is never looked at and never written back; the output line is always a bare
+    '+'.  One-character third lines that are not '+', named '+' lines and empty third lines must all be re-emitted as "+"."""
+    rng = np.random.default_rng(5)
+    rnd = lambda n: "".join(rng.choice(list("ACGT"), size=n))
+    thirds = ["+", "x", "-", "+name 1", "", "+", "@", "+"]
+    buf = b""
+    for i in range(400):
+        L = int(rng.integers(60, 150))
+        q = "".join(chr(int(x)) for x in rng.integers(40, 74, size=L - 1)) + "5"
+        buf += f"@t{i}\n{rnd(L)}\n{thirds[i % len(thirds)]}\n{q}\n".encode()
+    r1 = np.frombuffer(buf, dtype=np.uint8)
+    streams, _ = both(r1, None, lambda: Options(discard_output=True, input_quality_offset=33))
+    assert b"\nx\n" not in bytes(streams[2]) and b"+name" not in bytes(streams[2])
+    both(r1, None, lambda: Options(discard_output=True, input_quality_offset=33, min_read_length=100))      # raw copies to discard
+
+
 def test_pairs_routing_with_discard():
     rng = np.random.default_rng(7)
     rnd = lambda n, al="ACGT": "".join(rng.choice(list(al), size=n))
