@@ -280,6 +280,14 @@ class Engine:
             L.fq_host_free.argtypes = [C.c_void_p]
             L.fq_host_free.restype = None
             L.fq_reset_stats.argtypes = [C.c_void_p]
+            L.fq_comm_unique_id.argtypes = [C.c_void_p]
+            L.fq_comm_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+            L.fq_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+            L.fq_comm_destroy.argtypes = [C.c_void_p]
+            L.fq_comm_destroy.restype = None
+            L.fq_allreduce_stats.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+            L.fq_last_allreduce_ms.argtypes = [C.c_void_p]
+            L.fq_last_allreduce_ms.restype = C.c_float
             L.fq_device_outputs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p * NUM_STREAM)]
             L.fq_build_info.restype = C.c_char_p
 

@@ -7,5 +7,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -Xcompiler -fPIC,-Wall,-Wno-unused-function -shared ${FQ_NVCC_EXTRA:-} \
     -ccbin /usr/bin/g++ \
-    "$HERE/fq_api.cu" -o "$OUT" -lcudart
+    "$HERE/fq_api.cu" -o "$OUT" -lcudart -ldl
 echo "built $OUT"

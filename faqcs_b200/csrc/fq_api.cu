@@ -6,6 +6,8 @@
 // route -> scan -> emit.  There is no CPU implementation of any of these steps
 // in this library: without a CUDA device fq_create fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>          // types and enums only: the library is loaded with dlopen, not linked
 
 #include <algorithm>
 #include <cstdio>
@@ -116,6 +118,7 @@ struct fq_ctx {
     float t_seg[5] = {0, 0, 0, 0, 0};
     int sm_count = 0;
     size_t smem_optin = 0;
+    float allreduce_ms = 0.0f;
     const void *last_dev_out[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -936,5 +939,164 @@ fq_status fq_stats(fq_ctx *ctx, fq_stats_view *v)
     v->post_length_hist = ctx->v_post_len.data();
     return FQ_OK;
 }
+
+
+// ---- multi-GPU merge: NCCL, loaded at run time --------------------------------------------------------
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl()
+{
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) return a;
+        auto sym = [&](const char *n) { return dlsym(a.handle, n); };
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+        a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(sym("ncclCommInitAll"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+        a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+        a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.AllReduce && a.GroupStart && a.GroupEnd && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+
+struct fq_comm {
+    ncclComm_t comm = nullptr;
+    int device = 0;
+};
+
+#define NK(ctx_, call)                                                                                          \
+    do {                                                                                                        \
+        ncclResult_t r__ = (call);                                                                              \
+        if (r__ != ncclSuccess) return fail(ctx_, FQ_ERR_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r__)); \
+    } while (0)
+
+fq_status fq_comm_unique_id(uint8_t id[FQ_COMM_ID_BYTES])
+{
+    static_assert(sizeof(ncclUniqueId) == FQ_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    if (!id) return FQ_ERR_ARG;
+    if (!nccl().ok) return fail(nullptr, FQ_ERR_STATE, "NCCL (libnccl.so.2) could not be loaded");
+    ncclUniqueId u;
+    NK(nullptr, nccl().GetUniqueId(&u));
+    memcpy(id, &u, FQ_COMM_ID_BYTES);
+    return FQ_OK;
+}
+
+fq_status fq_comm_init_rank(fq_ctx *ctx, int n_ranks, int rank, const uint8_t id[FQ_COMM_ID_BYTES], fq_comm **out)
+{
+    if (!ctx || !id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return FQ_ERR_ARG;
+    if (!nccl().ok) return fail(ctx, FQ_ERR_STATE, "NCCL (libnccl.so.2) could not be loaded");
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    memcpy(&u, id, FQ_COMM_ID_BYTES);
+    fq_comm *c = new fq_comm();
+    c->device = ctx->device;
+    ncclResult_t r = nccl().CommInitRank(&c->comm, n_ranks, u, rank);
+    if (r != ncclSuccess) { delete c; return fail(ctx, FQ_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r)); }
+    *out = c;
+    return FQ_OK;
+}
+
+fq_status fq_comm_init_all(fq_ctx *const *ctxs, int n, fq_comm **out)
+{
+    if (!ctxs || !out || n < 1) return FQ_ERR_ARG;
+    fq_ctx *ctx = ctxs[0];
+    if (!nccl().ok) return fail(ctx, FQ_ERR_STATE, "NCCL (libnccl.so.2) could not be loaded");
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+    NK(ctx, nccl().CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) {
+        out[i] = new fq_comm();
+        out[i]->comm = comms[i];
+        out[i]->device = devs[i];
+    }
+    return FQ_OK;
+}
+
+void fq_comm_destroy(fq_comm *c)
+{
+    if (!c) return;
+    if (c->comm && nccl().ok) {
+        cudaSetDevice(c->device);
+        nccl().CommDestroy(c->comm);
+    }
+    delete c;
+}
+
+fq_status fq_allreduce_stats(fq_ctx *const *ctxs, int n, fq_comm *const *comms)
+{
+    if (!ctxs || !comms || n < 1) return FQ_ERR_ARG;
+    fq_ctx *ctx = ctxs[0];
+    if (!nccl().ok) return fail(ctx, FQ_ERR_STATE, "NCCL (libnccl.so.2) could not be loaded");
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i] || !comms[i] || comms[i]->device != ctxs[i]->device) return fail(ctx, FQ_ERR_ARG, "fq_allreduce_stats: communicator and context are on different devices");
+        CK(cudaSetDevice(ctxs[i]->device));
+        CK(cudaStreamSynchronize(ctxs[i]->stream));
+    }
+    // 1. every rank must use the same layout: agree on the row capacity (MAX), grow where needed
+    std::vector<DevBuf> d_cap(n);
+    std::vector<uint32_t> cap(n);
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(ctxs[i]->device));
+        CK(d_cap[i].ensure(4));
+        cap[i] = ctxs[i]->L.rows;
+        CK(cudaMemcpyAsync(d_cap[i].p, &cap[i], 4, cudaMemcpyHostToDevice, ctxs[i]->stream));
+    }
+    NK(ctx, nccl().GroupStart());
+    for (int i = 0; i < n; ++i) NK(ctx, nccl().AllReduce(d_cap[i].p, d_cap[i].p, 1, ncclUint32, ncclMax, comms[i]->comm, ctxs[i]->stream));
+    NK(ctx, nccl().GroupEnd());
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(ctxs[i]->device));
+        CK(cudaMemcpyAsync(&cap[i], d_cap[i].p, 4, cudaMemcpyDeviceToHost, ctxs[i]->stream));
+        CK(cudaStreamSynchronize(ctxs[i]->stream));
+        fq_status st = ensure_stats_rows(ctxs[i], cap[i]);
+        if (st != FQ_OK) return st;
+        if (ctxs[i]->L.rows != cap[i] && ctxs[i]->L.rows != std::max(64u, round_up(cap[i], 64)))
+            return fail(ctx, FQ_ERR_STATE, "fq_allreduce_stats: row capacities disagree");
+    }
+    // 2. the merge: SUM of the flat u64 block, MAX of the four row counters (timed: the first collective above also carries
+    //    NCCL's one-off connection set-up)
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(ctxs[i]->device));
+        CK(cudaEventRecord(ctxs[i]->ev[0], ctxs[i]->stream));
+    }
+    NK(ctx, nccl().GroupStart());
+    for (int i = 0; i < n; ++i) {
+        NK(ctx, nccl().AllReduce(ctxs[i]->d_stats.p, ctxs[i]->d_stats.p, ctxs[i]->L.total, ncclUint64, ncclSum, comms[i]->comm, ctxs[i]->stream));
+        NK(ctx, nccl().AllReduce(ctxs[i]->d_rows.p, ctxs[i]->d_rows.p, 4, ncclUint32, ncclMax, comms[i]->comm, ctxs[i]->stream));
+    }
+    NK(ctx, nccl().GroupEnd());
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(ctxs[i]->device));
+        CK(cudaEventRecord(ctxs[i]->ev[1], ctxs[i]->stream));
+        CK(cudaStreamSynchronize(ctxs[i]->stream));
+        cudaEventElapsedTime(&ctxs[i]->allreduce_ms, ctxs[i]->ev[0], ctxs[i]->ev[1]);
+        d_cap[i].release();
+    }
+    return FQ_OK;
+}
+
+float fq_last_allreduce_ms(const fq_ctx *ctx) { return ctx ? ctx->allreduce_ms : 0.0f; }
 
 }  // extern "C"

@@ -5,7 +5,7 @@
 // the --debug data files of plot() (plot.cpp:540-681).  The R/PDF report and k-mer rarefaction
 // are out of scope.
 //
-//   faqcs_b200 -1 r1.fq -2 r2.fq -d outdir [FaQCs flags]        extra: --device N, --batch_mb N
+//   faqcs_b200 -1 r1.fq -2 r2.fq -d outdir [FaQCs flags]        extra: --device N | --devices 0,1,.., --batch_mb N
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
@@ -56,6 +56,7 @@ struct Cli {
     vector<pair<string, string>> adapter;
     int device = 0;
     size_t batch_mb = 64;
+    vector<int> devices;            // --devices 0,1,...: consecutive batches go to consecutive GPUs, one NCCL all-reduce at the end
     bool has_paired() const { return !input_read1_file.empty(); }       // has_paired() tests read1 twice, FaQCs.h:135-138
     bool has_unpaired() const { return !input_unpaired_file.empty(); }
 };
@@ -136,7 +137,8 @@ static void usage()
     cerr << "\t--split_size\t\t<INT> (kept for compatibility)\n\t--qc_only\t\t<bool> no Filters, no Trimming, report numbers.\n\t--discard\t\t<bool> Output discarded reads\n";
     cerr << "\t--substitute\t\t<bool> (not implemented, as in FaQCs)\n\t--trim_only\t\t<bool> No quality report. Output trimmed reads only.\n\t--replace_to_N_q\t<INT> Replace base G to N when below this quality score (default:0, off)\n";
     cerr << "\t--5trim_off\t\t<bool> Turn off trimming from 5'end.\n\t--debug\t\t\t<bool> Keep intermediate files\n\t--version\t\t<bool> Print the version and exit\n";
-    cerr << "GPU:\n\t--device\t\t<INT> CUDA device (default 0)\n\t--batch_mb\t\t<INT> MiB of FASTQ per mate per batch (default 64)\n";
+    cerr << "GPU:\n\t--device\t\t<INT> CUDA device (default 0)\n\t--devices\t\t<INT,INT,..> several CUDA devices: batches are dealt out in order, statistics merged with one NCCL all-reduce\n"
+            "\t--batch_mb\t\t<INT> MiB of FASTQ per mate per batch (default 64)\n";
 }
 
 static void parse_options(int argc, char *argv[], Cli &o)
@@ -161,7 +163,7 @@ static void parse_options(int argc, char *argv[], Cli &o)
         {"qc_only", false, &config_opt, 17}, {"kmer_rarefaction", false, &config_opt, 18}, {"subset", true, &config_opt, 19},
         {"discard", false, &config_opt, 20}, {"substitute", false, &config_opt, 21}, {"trim_only", false, &config_opt, 22},
         {"5trim_off", false, &config_opt, 23}, {"debug", false, &config_opt, 24}, {"version", false, &config_opt, 25}, {"R1", true, &config_opt, 26},
-        {"R2", true, &config_opt, 27}, {"replace_to_N_q", true, &config_opt, 31}, {"device", true, &config_opt, 40}, {"batch_mb", true, &config_opt, 41},
+        {"R2", true, &config_opt, 27}, {"replace_to_N_q", true, &config_opt, 31}, {"device", true, &config_opt, 40}, {"batch_mb", true, &config_opt, 41}, {"devices", true, &config_opt, 42},
         {0, 0, 0, 0}};
     int opt_code;
     opterr = 0;
@@ -214,6 +216,17 @@ static void parse_options(int argc, char *argv[], Cli &o)
                     case 31: o.replace_to_N_q = strtou(optarg); break;
                     case 40: o.device = atoi(optarg); break;
                     case 41: o.batch_mb = (size_t)max(1, atoi(optarg)); break;
+                    case 42: {
+                        o.devices.clear();
+                        for (const char *p = optarg; *p;) {
+                            char *end = nullptr;
+                            const long d = strtol(p, &end, 10);
+                            if (end == p || d < 0) { cerr << "--devices expects a comma separated list of CUDA device indices" << endl; o.print_usage = true; break; }
+                            o.devices.push_back((int)d);
+                            p = *end == ',' ? end + 1 : end;
+                        }
+                        break;
+                    }
                     default: cerr << "Unknown flag!" << endl; break;
                 }
                 break;
@@ -478,11 +491,26 @@ static size_t offset_of_record(const uint8_t *buf, size_t n, size_t k)
 
 struct Run {
     Cli &o;
-    fq_ctx *ctx = nullptr;
-    uint64_t records_done = 0;
+    fq_ctx *ctx = nullptr;          // context of the first device: autodetection, statistics after the merge
+    vector<fq_ctx *> ctxs;          // one per device; batch k runs on ctxs[k % n] (created after autodetection, with its result)
+    fq_options fopt{};
+    uint64_t records_done = 0, batches_done = 0;
     bool first_batch = true;
     explicit Run(Cli &opt) : o(opt) {}
-    void check(fq_status st) { if (st != FQ_OK) throw string(fq_last_error(ctx)); }
+    void check(fq_status st, fq_ctx *c = nullptr) { if (st != FQ_OK) throw string(fq_last_error(c ? c : ctx)); }
+    // the other devices' contexts, once the quality offset is known (A1 runs once, before sharding: SURVEY 8(e))
+    void create_peers()
+    {
+        while (ctxs.size() < o.devices.size()) {
+            fq_options f = fopt;
+            f.input_quality_offset = o.input_quality_offset;
+            f.quality = o.quality;
+            fq_ctx *c = nullptr;
+            if (fq_create(&f, o.devices[ctxs.size()], &c) != FQ_OK) throw string(fq_last_error(nullptr));
+            ctxs.push_back(c);
+        }
+    }
+    void set_quality_everywhere(int q) { for (fq_ctx *c : ctxs) check(fq_set_quality(c, q), c); }
 };
 
 static int open_out(const string &fn, const char *what)
@@ -580,10 +608,11 @@ static void process(Run &R, bool paired)
         };
         for (int m = 0; m < n_mates; ++m) post_fill(0, m, 0);
         uint64_t first_index = 0, pending_ticket = 0;
+        fq_ctx *pending_ctx = nullptr;
         bool have_pending = false;
-        auto drain = [&](uint64_t ticket) {
+        auto drain = [&](fq_ctx *c, uint64_t ticket) {
             fq_batch_out out;
-            R.check(fq_wait(R.ctx, ticket, &out));
+            R.check(fq_wait(c, ticket, &out), c);
             for (int s = 0; s < 4; ++s)
                 if (fout[s] >= 0 && out.bytes[s]) {
                     const uint8_t *p = out.data[s];
@@ -634,6 +663,8 @@ static void process(Run &R, bool paired)
                 o.quality = (char)q;
                 if (q != q_before) cerr << "The input looks like NextSeq data and the quality level (-q) is adjusted to 20 for trimming." << endl;
                 R.first_batch = false;
+                R.create_peers();
+                R.set_quality_everywhere(o.quality);
             }
             t_cut += now_s() - t0;
             // One piece per batch; the last batch may be cut in two at the start of the reference's final partial
@@ -661,7 +692,7 @@ static void process(Run &R, bool paired)
                 if (pc.recheck && (int)o.quality < 20 && pc.n1 >= 3 && p1[0] == '@' && p1[1] == 'N' && p1[2] == 'S') {
                     cerr << "The input looks like NextSeq data and the quality level (-q) is adjusted to 20 for trimming." << endl;
                     o.quality = 20;
-                    R.check(fq_set_quality(R.ctx, 20));
+                    R.set_quality_everywhere(20);
                 }
                 uint64_t ticket = 0;
                 // this batch's outputs reuse the host slot of the batch two tickets back: its writes must be done
@@ -669,11 +700,13 @@ static void process(Run &R, bool paired)
                 for (Worker &w : writers) w.wait_idle();
                 t_write_wait += now_s() - t0;
                 t0 = now_s();
-                R.check(fq_submit_host(R.ctx, p1, pc.n1, p2, pc.n2, first_index, pc.final ? 1 : 0, &ticket));
-                R.check(fq_run(R.ctx, ticket));
-                if (have_pending) drain(pending_ticket);
+                fq_ctx *c = R.ctxs[R.batches_done++ % R.ctxs.size()];          // consecutive batches on consecutive devices
+                R.check(fq_submit_host(c, p1, pc.n1, p2, pc.n2, first_index, pc.final ? 1 : 0, &ticket), c);
+                R.check(fq_run(c, ticket), c);
+                if (have_pending) drain(pending_ctx, pending_ticket);
                 t_gpu += now_s() - t0;
                 pending_ticket = ticket;
+                pending_ctx = c;
                 have_pending = true;
                 first_index += pc.nrec;
             }
@@ -681,7 +714,7 @@ static void process(Run &R, bool paired)
         }
         if (have_pending) {
             for (Worker &w : writers) w.wait_idle();
-            drain(pending_ticket);
+            drain(pending_ctx, pending_ticket);
         }
         const double t0 = now_s();
         for (Worker &w : writers) w.wait_idle();
@@ -869,21 +902,33 @@ int main(int argc, char *argv[])
         f.n_adapters = (uint32_t)adapters.size(); f.adapters = adapters.data();
         const bool timing = getenv("FAQCS_B200_TIMING") != nullptr;
         const double t_start = now_s();
-        if (fq_create(&f, o.device, &ctx) != FQ_OK) throw string(fq_last_error(nullptr));
+        if (o.devices.empty()) o.devices.push_back(o.device);
+        if (fq_create(&f, o.devices[0], &ctx) != FQ_OK) throw string(fq_last_error(nullptr));
         const double t_created = now_s();
         Run R(o);
         R.ctx = ctx;
+        R.ctxs.push_back(ctx);
+        R.fopt = f;
         if (o.has_paired()) process(R, true);
         if (o.has_unpaired()) {
             R.first_batch = true;      // offset detection only if still unknown; the NextSeq check runs per input (FaQCs.cpp:586,673-683)
             process(R, false);
         }
         const double t_processed = now_s();
+        if (R.ctxs.size() > 1) {
+            // the path's only collective: one ncclAllReduce of the integer statistics over NVLink
+            vector<fq_comm *> comms(R.ctxs.size(), nullptr);
+            R.check(fq_comm_init_all(R.ctxs.data(), (int)R.ctxs.size(), comms.data()));
+            const fq_status st = fq_allreduce_stats(R.ctxs.data(), (int)R.ctxs.size(), comms.data());
+            for (fq_comm *c : comms) fq_comm_destroy(c);
+            R.check(st);
+        }
         fq_stats_view v;
         if (fq_stats(ctx, &v) != FQ_OK) throw string(fq_last_error(ctx));
         write_stats(v, o);
         if (!o.trim_only && o.debug) write_debug_files(v, o);    // the reference deletes these unless --debug (plot.cpp:517-537)
         const double t_stats = now_s();
+        for (size_t k = 1; k < R.ctxs.size(); ++k) fq_destroy(R.ctxs[k]);
         fq_destroy(ctx);
         if (timing)
             cerr << "[timing] fq_create " << t_created - t_start << " s, process " << t_processed - t_created << " s, stats files "

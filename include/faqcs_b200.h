@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FQ_ABI_VERSION 1
+#define FQ_ABI_VERSION 2
 
 /* ---- FilterStat (FaQCs.h:46-75), same order, same meaning ---------------- */
 enum fq_filter_stat {
@@ -284,6 +284,29 @@ fq_status fq_stats(fq_ctx *ctx, fq_stats_view *view);
 fq_status fq_stats_reserve_rows(fq_ctx *ctx, uint32_t rows);
 fq_status fq_stats_device_buffer(fq_ctx *ctx, void **d_u64, size_t *n_u64,
                                  void **d_rows_u32x4);
+
+/*
+ * The collective itself, inside the library (SURVEY 8(b) fq_allreduce_stats, 8(e)): merges the accumulators of n contexts
+ * -- all n ranks of a single-process run, or this process's one context of an n-rank job -- with ONE ncclAllReduce
+ * (ncclUint64, ncclSum) over the flat statistics block, preceded by an agreement on the row capacity and followed by an
+ * ncclAllReduce(ncclMax) of the four row counters.  Replaces the `omp critical` merge of trim() (trim.cpp:120-154) and the
+ * matrix / vector operator+= it uses (matrix.h:111-142, trim.cpp:47-65) across devices.  Afterwards fq_stats returns the
+ * merged statistics on every context.  NCCL is loaded at run time (libnccl.so.2); FQ_ERR_STATE if it is not available.
+ *
+ * fq_comm wraps one ncclComm_t bound to one context's device.
+ *   single process, n devices:  fq_comm_init_all(ctx, n, comms);           fq_allreduce_stats(ctx, n, comms);
+ *   one process per device:     rank 0: fq_comm_unique_id(id); broadcast id with the job's launcher;
+ *                               fq_comm_init_rank(ctx, n_ranks, rank, id, &comm);   fq_allreduce_stats(&ctx, 1, &comm);
+ */
+typedef struct fq_comm fq_comm;
+#define FQ_COMM_ID_BYTES 128
+fq_status fq_comm_unique_id(uint8_t id[FQ_COMM_ID_BYTES]);
+fq_status fq_comm_init_rank(fq_ctx *ctx, int n_ranks, int rank, const uint8_t id[FQ_COMM_ID_BYTES], fq_comm **out);
+fq_status fq_comm_init_all(fq_ctx *const *ctx, int n, fq_comm **out);
+void      fq_comm_destroy(fq_comm *comm);
+fq_status fq_allreduce_stats(fq_ctx *const *ctx, int n, fq_comm *const *comm);
+/* Device milliseconds of the last fq_allreduce_stats on this context (CUDA events around the three collectives). */
+float     fq_last_allreduce_ms(const fq_ctx *ctx);
 
 /* Zero the accumulators (new run on the same context). */
 fq_status fq_reset_stats(fq_ctx *ctx);
