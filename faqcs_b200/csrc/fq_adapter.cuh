@@ -40,6 +40,29 @@ struct AdapterArgs {
     uint32_t plane_words;             // total words of the adapter bit planes (incl. padding)
     uint32_t has_gap;                 // some adapter contains '-'
     uint32_t rpad;                    // zero words on both sides of every read bit plane (longest adapter in words + 1)
+    uint32_t sweep;                   // segment sweep enabled (needs use_planes)
+    uint32_t n_seg;                   // number of 32-base segments of the adapters of up to kSweepMaxLen bases
+    uint32_t sweep_pure;              // every swept adapter is plain A/C/G/T
+};
+
+// ---- segment sweep ------------------------------------------------------------------------------------
+// Every adapter of up to 96 bases is cut into segments of (up to) 32 bases.  A segment is four position masks: x: the base
+// can be a purine (A, G), y: a pyrimidine (C, T), u: strong (C, G), v: weak (A, T); IUPAC unions, N and '-' set all that
+// apply.  Two bases match iff they agree in the purine/pyrimidine AND in the strong/weak split, so for 32 read positions
+// with masks (wx, wy, wu, wv) the match mask of the segment is ((x & wx) | (y & wy)) & ((u & wu) | (v & wv)) -- exact for
+// A, C, G, T, N and never missing a match for the other codes.
+// If an adapter of T bases has `threshold` matching positions on some diagonal, one of its segments (len_k bases) has at
+// least threshold * len_k / T of them against the 32 read positions it faces there (pigeonhole).  The sweep checks that
+// necessary condition for ALL segments at once: one lane owns one segment (masks and bound in registers), the warp walks
+// the windows of 32 read positions one position at a time (four funnel shifts of warp-uniform words), and each step
+// costs every lane five logic operations, a popcount and a max.  Only the adapters it flags are looked at any further:
+// one-segment adapters go straight to the exact alignment (their count was exact), longer ones through the exact
+// per-diagonal plane count first.
+constexpr uint32_t kSweepMaxLen = 96;
+struct SegInfo {
+    uint16_t owner;     // adapter index
+    uint8_t len;        // bases in this segment
+    uint8_t total;      // bases in the adapter
 };
 
 // seq_overlap.cpp:372-411; 0xff = unknown base (the reference throws)
@@ -94,7 +117,8 @@ __device__ __forceinline__ int exact_align(const uint8_t *s_read, uint32_t L, co
     return (int)(kmax >> 48);
 }
 
-// Shared memory: [offsets n+1][plane offsets n+1][adapter codes][adapter bit planes][per warp: read codes, mask words, read planes]
+// Shared memory: [offsets n+1][plane offsets n+1][adapter codes][adapter bit planes][segment masks][segment infos]
+//                [per warp: read codes, mask words, read planes (5 + 4 sweep masks), candidate bits]
 //
 // Prefilter (exact-safe): an adapter can only pass the threshold test num_match >= threshold (trim.cpp:1024-1027)
 // if SOME diagonal holds at least `threshold` matching positions, because num_match counts the matches inside
@@ -114,11 +138,17 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
     const uint32_t rstride = mask_words + 2 * a.rpad;          // words of one (zero padded) read bit plane
     uint32_t *s_planes = reinterpret_cast<uint32_t *>(s_codes + codes_pad);
     const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t per_warp_words = read_pad / 4 + mask_words + (a.use_planes ? 5 * rstride : 0);
-    uint32_t *warp_base = s_planes + a.plane_words + (size_t)warp_in_cta * per_warp_words;
+    const uint32_t cand_words = (A.n + 31) >> 5;
+    const uint32_t per_warp_words = read_pad / 4 + mask_words + (a.use_planes ? 5 * rstride : 0) + (a.sweep ? 4 * rstride + cand_words : 0);
+    uint4 *s_seg = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(s_planes + a.plane_words) + 15) & ~(uintptr_t)15);   // [n_seg] masks {x, y, u, v}
+    SegInfo *s_seginfo = reinterpret_cast<SegInfo *>(s_seg + a.n_seg);                                                         // [n_seg]
+    uint32_t *s_unswept = reinterpret_cast<uint32_t *>(s_seginfo + a.n_seg);          // [cand_words] adapters the sweep does not cover (longer than its limit)
+    uint32_t *warp_base = (a.sweep ? s_unswept + cand_words : s_planes + a.plane_words) + (size_t)warp_in_cta * per_warp_words;
     uint8_t *s_read = reinterpret_cast<uint8_t *>(warp_base);
     uint32_t *s_mask = warp_base + read_pad / 4;
     uint32_t *s_rp = s_mask + mask_words;                      // read planes [5][rstride], data at word offset rpad
+    uint32_t *s_rxy = s_rp + 5 * rstride;                      // sweep masks of the read x, y, u, v: [4][rstride]
+    uint32_t *s_cand = s_rxy + 4 * rstride;                    // adapters flagged by the sweep
 
     for (uint32_t i = threadIdx.x; i <= A.n; i += blockDim.x) s_off[i] = A.offset[i];
     for (uint32_t i = threadIdx.x; i < A.total; i += blockDim.x) s_codes[i] = A.codes[i];
@@ -135,6 +165,37 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
         }
         for (uint32_t i = threadIdx.x; i < a.plane_words; i += blockDim.x) s_planes[i] = 0;
         for (uint32_t i = lane; i < 5 * rstride; i += 32) s_rp[i] = 0;       // the padding stays zero for the whole kernel
+        if (a.sweep) {
+            for (uint32_t i = lane; i < 4 * rstride; i += 32) s_rxy[i] = 0;
+            if (threadIdx.x == 0) {                // segment -> (adapter, part): serial walk, the set is small
+                uint32_t k = 0;
+                for (uint32_t w = 0; w < cand_words; ++w) s_unswept[w] = 0;
+                for (uint32_t j = 0; j < A.n; ++j) {
+                    const uint32_t T = s_off[j + 1] - s_off[j];
+                    if (T > kSweepMaxLen) s_unswept[j >> 5] |= 1u << (j & 31);
+                    if (T == 0 || T > kSweepMaxLen) continue;
+                    for (uint32_t p = 0; p < T; p += 32) s_seginfo[k++] = SegInfo{(uint16_t)j, (uint8_t)min(32u, T - p), (uint8_t)T};
+                }
+            }
+        }
+        __syncthreads();
+        if (a.sweep) {
+            for (uint32_t k = threadIdx.x; k < a.n_seg; k += blockDim.x) {
+                const SegInfo si = s_seginfo[k];
+                uint32_t first = k;                // segments of one adapter are consecutive: its first one
+                while (first > 0 && s_seginfo[first - 1].owner == si.owner) --first;
+                const uint8_t *codes = s_codes + s_off[si.owner] + 32 * (k - first);
+                uint32_t m[4] = {0, 0, 0, 0};
+                for (uint32_t p = 0; p < si.len; ++p) {
+                    const uint32_t code = codes[p], bit = 1u << p;
+                    if (code & (1u | 4u | 16u)) m[0] |= bit;
+                    if (code & (2u | 8u | 16u)) m[1] |= bit;
+                    if (code & (2u | 4u | 16u)) m[2] |= bit;
+                    if (code & (1u | 8u | 16u)) m[3] |= bit;
+                }
+                s_seg[k] = make_uint4(m[0], m[1], m[2], m[3]);
+            }
+        }
         __syncthreads();
         for (uint32_t j = 0; j < A.n; ++j) {
             const uint32_t T = s_off[j + 1] - s_off[j], stride = (T + 31) / 32;
@@ -179,13 +240,27 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
                     const uint32_t m = __ballot_sync(0xffffffffu, (code >> b) & 1u);
                     if (lane == 0) s_rp[b * rstride + a.rpad + (b0 >> 5)] = m;
                 }
+                if (a.sweep) {
+                    const uint32_t mx = __ballot_sync(0xffffffffu, (code & (1u | 4u | 16u)) != 0), my = __ballot_sync(0xffffffffu, (code & (2u | 8u | 16u)) != 0);
+                    const uint32_t mu = __ballot_sync(0xffffffffu, (code & (2u | 4u | 16u)) != 0), mv = __ballot_sync(0xffffffffu, (code & (1u | 8u | 16u)) != 0);
+                    if (lane == 0) {
+                        uint32_t *w = s_rxy + a.rpad + (b0 >> 5);
+                        w[0] = mx; w[rstride] = my; w[2 * rstride] = mu; w[3 * rstride] = mv;
+                    }
+                }
             }
         }
-        if (a.use_planes)       // a shorter read after a longer one: clear the plane words it does not own
+        if (a.use_planes) {     // a shorter read after a longer one: clear the plane words it does not own
             for (uint32_t i = lane; i < 5 * (mask_words - read_words); i += 32) {
                 const uint32_t b = i / (mask_words - read_words), w = read_words + i % (mask_words - read_words);
                 s_rp[b * rstride + a.rpad + w] = 0;
             }
+            if (a.sweep)
+                for (uint32_t i = lane; i < 4 * (mask_words - read_words); i += 32) {
+                    const uint32_t b = i / (mask_words - read_words), w = read_words + i % (mask_words - read_words);
+                    s_rxy[b * rstride + a.rpad + w] = 0;
+                }
+        }
         for (uint32_t w = lane; w < mask_words; w += 32) s_mask[w] = 0;     // 1 = masked
         if (__any_sync(0xffffffffu, unknown)) {
             if (lane == 0) { atomicOr(&a.info->err, kErrUnknownBase); atomicMin(&a.info->err_record, r); }
@@ -211,11 +286,80 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
             else thr_min = false;
         }
 
+        bool all_shared = false;                  // every adapter shares a base with the read (the usual case): see below
+        if (a.sweep && L) {
+            for (uint32_t w = lane; w < cand_words; w += 32) s_cand[w] = 0;
+            bool sh_ok = true;
+            for (uint32_t j = lane; j < A.n; j += 32) sh_ok = sh_ok && (read_or & A.or_bits[j]) && (s_off[j + 1] > s_off[j]);
+            all_shared = __all_sync(0xffffffffu, sh_ok);
+            __syncwarp();
+            const uint32_t *rx = s_rxy + a.rpad;
+            const int last_word = (int)((L - 1) >> 5);
+            for (uint32_t c0 = 0; c0 < a.n_seg; c0 += 96) {          // three segments per lane: the windows are extracted once for all three
+                uint4 sm[3];
+                uint32_t va[3], bound[3], owner[3], best[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const uint32_t k = c0 + 32 * q + lane;
+                    sm[q] = make_uint4(0, 0, 0, 0);
+                    bound[q] = 0xffffffffu;
+                    owner[q] = 0;
+                    best[q] = 0;
+                    if (k < a.n_seg) {
+                        sm[q] = s_seg[k];
+                        const SegInfo si = s_seginfo[k];
+                        owner[q] = si.owner;
+                        const uint32_t T = si.total;
+                        const uint32_t tl = thr_min ? min(thr_len, T) : T;
+                        const int threshold = __float2int_rz(__fmul_rn(o.match_rate, (float)tl));
+                        bound[q] = threshold <= 0 ? 0u : ((uint32_t)threshold * si.len + T - 1) / T;      // ceil(threshold * len / T)
+                    }
+                    va[q] = sm[q].x | sm[q].y;
+                }
+                // windows of 32 read positions starting at p0 = 32 * idx + sh, from -31 (only the last base of a segment on the
+                // first base of the read) to the last base of the read; the planes are zero outside the read
+                for (int idx = -1; idx <= last_word; ++idx) {
+                    const uint32_t *p = rx + idx;
+                    const uint32_t x0 = p[0], x1 = p[1], y0 = p[rstride], y1 = p[rstride + 1];
+                    const uint32_t u0 = p[2 * rstride], u1 = p[2 * rstride + 1], v0 = p[3 * rstride], v1 = p[3 * rstride + 1];
+#pragma unroll 4
+                    for (uint32_t sh = 0; sh < 32; ++sh) {
+                        const uint32_t wx = __funnelshift_r(x0, x1, sh), wy = __funnelshift_r(y0, y1, sh);
+                        const uint32_t wu = __funnelshift_r(u0, u1, sh), wv = __funnelshift_r(v0, v1, sh);
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            uint32_t m;
+                            if (a.sweep_pure)       // plain A/C/G/T segments: y = ~x and v = ~u inside the segment, so each pair is a bit select
+                                m = ((sm[q].x & wx) | (~sm[q].x & wy)) & ((sm[q].z & wu) | (~sm[q].z & wv)) & va[q];
+                            else
+                                m = ((sm[q].x & wx) | (sm[q].y & wy)) & ((sm[q].z & wu) | (sm[q].w & wv));
+                            best[q] = max(best[q], (uint32_t)__popc(m));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (c0 + 32 * q + lane < a.n_seg && best[q] >= bound[q]) atomicOr(&s_cand[owner[q] >> 5], 1u << (owner[q] & 31));
+            }
+            __syncwarp();
+        }
+
         int best_score = 0, best_adapter = -1;
         int st_start = 0, st_stop = 0;            // max_elem.M_start_i / stop_i survive across align() calls (Q5)
         int pending = -1;                         // last adapter that shares a base with the read but was not aligned yet
 
-        for (uint32_t j = 0; j < A.n; ++j) {
+        // When every adapter shares a base with the read, an adapter the sweep did not flag cannot pass its threshold and its
+        // stale range (Q5) is never asked for: only the flagged adapters are visited, in order.
+        uint32_t j = 0;
+        const bool flagged_only = a.sweep && all_shared && a.n_seg > 0;
+        for (;; ++j) {
+            if (flagged_only) {
+                // next adapter the sweep flagged, or one it does not cover (longer than its limit: visited always)
+                uint32_t w = j >> 5, bits = w < cand_words ? (s_cand[w] | s_unswept[w]) & (0xffffffffu << (j & 31)) : 0u;
+                while (!bits && ++w < cand_words) bits = s_cand[w] | s_unswept[w];
+                j = bits ? (w << 5) + (uint32_t)__ffs(bits) - 1 : A.n;
+            }
+            if (j >= A.n) break;
             const uint32_t T = s_off[j + 1] - s_off[j];
             const uint8_t *t = s_codes + s_off[j];
             const uint32_t tl = thr_min ? min(thr_len, T) : T;
@@ -224,7 +368,10 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
             const bool shared = (read_or & A.or_bits[j]) && L && T;
             if (shared) {
                 bool candidate = true;
-                if (a.use_planes) {
+                const bool swept = a.sweep && T <= kSweepMaxLen;
+                if (swept && !((s_cand[j >> 5] >> (j & 31)) & 1u)) candidate = false;      // the sweep: no diagonal can reach the threshold
+                else if (swept && T <= 32) candidate = true;                                // one segment: the sweep's count was exact
+                else if (a.use_planes) {
                     // matches on every diagonal that is long enough to reach the threshold, 32 diagonals per round.
                     // Diagonal d pairs adapter position j with read position j - d: for each adapter word the
                     // facing 32 read bits are pulled out of the (zero padded) read planes with a funnel shift.

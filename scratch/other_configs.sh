@@ -1,6 +1,8 @@
 #!/bin/bash
-for wl in c4 c5 c3; do
-  extra=""; if [ $wl = c3 ]; then extra="--block-pairs 50000 --batch-pairs 200000 --steps 2 --warmup 3"; else extra="--steps 5 --warmup 3"; fi
-  timeout 500 python bench.py --workload $wl --no-cpu-baseline --e2e-steps 0 $extra 2>&1 | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$wl', round(d['value']/1e6,1), 'Mreads/s', round(d['config']['gbases_per_s'],1), 'Gb/s', d['roofline']['segments_ms'])"
+# Un-profiled bench lines of the other BASELINE configs (C3, C4, C5) with the in-tree library -> gpurun_out/other_<wl>.json
+for wl in c3 c4 c5; do
+  if [ $wl = c3 ]; then extra="--block-pairs 50000 --batch-pairs 400000 --batches-per-step 2 --steps 3 --warmup 3"; else extra="--batches-per-step 10 --steps 3 --warmup 3"; fi
+  timeout 600 python bench.py --workload $wl $extra --no-cpu-baseline --e2e-steps 0 > gpurun_out/other_$wl.json 2> gpurun_out/other_$wl.err
+  python -c "
+import json,sys; d=json.loads(open('gpurun_out/other_$wl.json').read()); print('$wl', round(d['value']/1e6,1), 'M reads/s', {k: round(x['ms'],4) for k,x in d['roofline']['kernels'].items()}, round(d['roofline']['frac'],4))"
 done
