@@ -390,6 +390,9 @@ def main():
             h1[k * w.r1.size:(k + 1) * w.r1.size] = w.r1
             h2[k * w.r2.size:(k + 1) * w.r2.size] = w.r2
         cb2 = CBatchOut()
+        # pieces mode (fq_set_output_pieces): the streams come back as pieces of THESE pinned input buffers plus the literal
+        # bytes of the records that changed -- what a writer hands to writev(2); checked against byte mode below
+        eng.set_output_pieces(True)
 
         def pipeline(n_b):
             """submit(i+1); run(i); wait(i-1): upload, kernels and download of three consecutive batches overlap."""
@@ -420,11 +423,22 @@ def main():
         ems = torch.tensor([max(f0.elapsed_time(f1), wall * 1e3)], device=dev)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        d2h = int(sum(int(cb2.bytes[i]) for i in range(4)))
+        d2h = int(sum(int(cb2.literal_bytes[i]) + 16 * int(cb2.n_pieces[i]) for i in range(4)))
+        # the pieces of the last timed batch must expand to exactly the byte-mode streams of the same batch
+        import hashlib
+        last = eng._collect(cb2, True)
+        expanded = last.expand(h1, h2)
+        eng.set_output_pieces(False)
+        ref = eng.process(h1, h2)
+        if [hashlib.sha256(x).digest() for x in expanded] != [hashlib.sha256(x).digest() for x in ref.streams]:
+            raise SystemExit("bench: pieces of the end-to-end leg do not expand to the byte-mode streams")
         e2e = {"value": world * reads_per_step * args.e2e_steps / (float(ems.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": (n1 + n2) * nb, "d2h_bytes_per_step": d2h * nb, "steps": args.e2e_steps,
                "ms_per_step": float(ems.item()) / args.e2e_steps,
-               "api": "fq_submit_host / fq_run / fq_wait (pinned host buffers; H2D, kernels and D2H of consecutive batches overlap)"}
+               "output_bytes_per_step": int(sum(int(cb2.bytes[i]) for i in range(4))) * nb,
+               "api": "fq_submit_host / fq_run / fq_wait in pieces mode (pinned host buffers in; out: each stream as pieces of those "
+                      "buffers + literal bytes of the changed records, expansion verified against byte mode after the timed region; "
+                      "H2D, kernels and D2H of consecutive batches overlap)"}
         eng.host_free(h1)
         eng.host_free(h2)
 

@@ -89,7 +89,11 @@ class CBatchOut(C.Structure):
         ("n_records", C.c_uint64), ("n_valid", C.c_uint64 * 2),
         ("paired_read_number", C.c_uint64), ("paired_base_length", C.c_uint64),
         ("results", C.POINTER(CReadResult) * 2),
+        ("pieces", C.c_void_p * NUM_STREAM), ("n_pieces", C.c_uint64 * NUM_STREAM), ("literal_bytes", C.c_uint64 * NUM_STREAM),
     ]
+
+
+PIECE_DTYPE = np.dtype([("offset", "<u8"), ("length", "<u4"), ("source", "<u4")])
 
 
 U64P = C.POINTER(C.c_uint64)
@@ -158,6 +162,24 @@ class BatchResult:
     paired_read_number: int
     paired_base_length: int
     results: List[Optional[np.ndarray]]
+    pieces: Optional[List[np.ndarray]] = None          # pieces mode: per stream, array of PIECE_DTYPE; `streams` then hold the literal bytes
+
+    def expand(self, r1, r2=None) -> List[bytes]:
+        """Pieces mode: materialise the four streams from the caller's inputs, the literal bytes and the piece lists."""
+        if self.pieces is None:
+            return self.streams
+        src = [np.frombuffer(r1, np.uint8) if isinstance(r1, (bytes, bytearray)) else np.asarray(r1, np.uint8),
+               None if r2 is None else (np.frombuffer(r2, np.uint8) if isinstance(r2, (bytes, bytearray)) else np.asarray(r2, np.uint8))]
+        out = []
+        for s in range(NUM_STREAM):
+            lit = np.frombuffer(self.streams[s], np.uint8)
+            parts = []
+            for off, ln, which in self.pieces[s]:
+                buf = lit if which == 2 else src[int(which)]
+                parts.append(buf[int(off):int(off) + int(ln)])
+            out.append(np.concatenate(parts).tobytes() if parts else b"")
+            assert len(out[-1]) == self.stream_bytes[s], (s, len(out[-1]), self.stream_bytes[s])
+        return out
 
 
 @dataclass
@@ -275,6 +297,7 @@ class Engine:
             L.fq_wait.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(CBatchOut)]
             L.fq_stats_reserve_rows.argtypes = [C.c_void_p, C.c_uint32]
             L.fq_set_check_pair_ids.argtypes = [C.c_void_p, C.c_int]
+            L.fq_set_output_pieces.argtypes = [C.c_void_p, C.c_int]
             L.fq_host_alloc.argtypes = [C.c_size_t]
             L.fq_host_alloc.restype = C.c_void_p
             L.fq_host_free.argtypes = [C.c_void_p]
@@ -316,6 +339,11 @@ class Engine:
     def set_debug_results(self, enable: bool = True):
         self._check(self._f("set_debug_results")(self.ctx, int(enable)))
 
+    def set_output_pieces(self, enable: bool = True):
+        """Pieces mode (fq_set_output_pieces): streams come back as lists of pieces of the caller's input + literal bytes."""
+        self._check(self.lib.fq_set_output_pieces(self.ctx, int(enable)))
+        self._pieces = bool(enable)
+
     def set_quality(self, quality: int):
         """Options::quality for the following batches (the reference's NextSeq adjustment, FaQCs.cpp:272-277)."""
         self._check(self._f("set_quality")(self.ctx, int(quality)))
@@ -339,8 +367,16 @@ class Engine:
 
     def _collect(self, out: CBatchOut, paired: bool, want_data: bool = True) -> BatchResult:
         streams = []
+        pieces = None
+        in_pieces = any(int(out.n_pieces[s]) for s in range(NUM_STREAM))
+        if in_pieces and want_data:
+            pieces = []
+            for s in range(NUM_STREAM):
+                k = int(out.n_pieces[s])
+                raw = C.string_at(out.pieces[s], k * PIECE_DTYPE.itemsize) if k else b""
+                pieces.append(np.frombuffer(raw, dtype=PIECE_DTYPE).copy())
         for s in range(NUM_STREAM):
-            n = int(out.bytes[s])
+            n = int(out.literal_bytes[s]) if in_pieces else int(out.bytes[s])
             streams.append(C.string_at(out.data[s], n) if (n and want_data and out.data[s]) else b"")
         results: List[Optional[np.ndarray]] = [None, None]
         for m in range(2 if paired else 1):
@@ -348,7 +384,7 @@ class Engine:
                 raw = C.string_at(out.results[m], int(out.n_records) * C.sizeof(CReadResult))
                 results[m] = np.frombuffer(raw, dtype=READ_RESULT_DTYPE).copy()
         return BatchResult(streams, [int(out.bytes[s]) for s in range(NUM_STREAM)], int(out.n_records), (int(out.n_valid[0]), int(out.n_valid[1])),
-                           int(out.paired_read_number), int(out.paired_base_length), results)
+                           int(out.paired_read_number), int(out.paired_base_length), results, pieces)
 
     def process(self, r1, r2=None, first_record_index: int = 0, is_final: bool = True) -> BatchResult:
         """Host buffers in, host buffers out (fq_process_host)."""

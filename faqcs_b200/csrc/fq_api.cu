@@ -95,7 +95,9 @@ struct fq_ctx {
     DevBuf d_info, d_stats, d_rows;
     BatchInfo *h_info = nullptr;       // pinned
     StatsLayout L{};
-    PinnedBuf h_out[2][4], h_dbg[2], h_stats;
+    PinnedBuf h_out[2][4], h_dbg[2], h_stats, h_pieces[2][4];
+    DevBuf d_pieces[2][4];
+    bool pieces = false;               // fq_set_output_pieces
     int out_slot = 0;                   // which d_out / h_out set process_common fills
     bool async_out = false;            // D2H on s_out, caller waits on ev_out
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -498,7 +500,8 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         ea.parts = 1;
         while (ea.parts < 8 && (32.0 / ea.parts) * avg * 1.08 + 32.0 > (double)kEmitSlab) ea.parts *= 2;
     }
-    CK(ctx->d_tile.ensure((size_t)ea.n_tiles * 4 * 4));
+    const bool pieces = ctx->pieces && !o.qc_only;
+    CK(ctx->d_tile.ensure((size_t)ea.n_tiles * (pieces ? 12 : 4) * 4));
     ea.tile_sum = ctx->d_tile.as<uint32_t>();
     ea.info = info;
     ea.stats = S;
@@ -517,12 +520,25 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         for (int s = 0; s < 4; ++s) {
             if (cap[s]) CK(ctx->d_out[ctx->out_slot][s].ensure(cap[s] + 16));
             ea.out[s] = ctx->d_out[ctx->out_slot][s].as<uint8_t>();
+            if (pieces && cap[s]) {       // at most one piece per record and mate
+                CK(ctx->d_pieces[ctx->out_slot][s].ensure(((size_t)n * (s == 3 && paired ? 2 : 1) + 1) * sizeof(fq_out_piece)));
+                ea.pieces[s] = ctx->d_pieces[ctx->out_slot][s].as<fq_out_piece>();
+            }
         }
     }
+    if (pieces) {
+        k_route_pieces<<<ea.n_tiles, kTile, 0, ctx->stream>>>(ea, o);
+        k_scan_tiles<<<12, 1024, 0, ctx->stream>>>(ea.tile_sum, ea.n_tiles, info);
+        using EmitKernel = void (*)(const EmitArgs, const DevOpts);
+        const EmitKernel kern = (!o.replace_q && o.in_off == o.out_off) ? (EmitKernel)k_emit_pieces<true> : (EmitKernel)k_emit_pieces<false>;
+        kern<<<ea.n_tiles, kTile, 0, ctx->stream>>>(ea, o);
+        ctx->launches += 3;
+    } else {
     k_route<<<ea.n_tiles, kTile, 0, ctx->stream>>>(ea, o);
     k_scan_tiles<<<4, 1024, 0, ctx->stream>>>(ea.tile_sum, ea.n_tiles, info);
     ctx->launches += 2;
-    if (!o.qc_only) {
+    }
+    if (!o.qc_only && !pieces) {
         using EmitKernel = void (*)(const EmitArgs, const DevOpts);
         const EmitKernel kern = (!o.replace_q && o.in_off == o.out_off) ? (EmitKernel)k_emit<true> : (EmitKernel)k_emit<false>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem));
@@ -548,6 +564,8 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     for (int s = 0; s < 4; ++s) {
         out->bytes[s] = o.qc_only ? 0 : hi.out_bytes[s];
         ctx->last_dev_out[s] = out->bytes[s] ? ctx->d_out[ctx->out_slot][s].p : nullptr;
+        out->n_pieces[s] = pieces ? hi.out_pieces[s] : 0;
+        out->literal_bytes[s] = pieces ? hi.out_literal[s] : 0;
     }
     if (copy_out) {
         // D2H of the four streams: on the compute stream (synchronous API) or, pipelined, on the copy-out
@@ -560,9 +578,19 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         }
         for (int s = 0; s < 4; ++s) {
             if (!out->bytes[s]) continue;
-            CK(ctx->h_out[ctx->out_slot][s].ensure(out->bytes[s]));
-            CK(cudaMemcpyAsync(ctx->h_out[ctx->out_slot][s].p, ctx->d_out[ctx->out_slot][s].p, out->bytes[s], cudaMemcpyDeviceToHost, cs));
-            out->data[s] = static_cast<const uint8_t *>(ctx->h_out[ctx->out_slot][s].p);
+            // pieces mode: only the literal bytes and the piece list travel
+            const size_t nb = pieces ? out->literal_bytes[s] : out->bytes[s];
+            if (nb) {
+                CK(ctx->h_out[ctx->out_slot][s].ensure(nb));
+                CK(cudaMemcpyAsync(ctx->h_out[ctx->out_slot][s].p, ctx->d_out[ctx->out_slot][s].p, nb, cudaMemcpyDeviceToHost, cs));
+                out->data[s] = static_cast<const uint8_t *>(ctx->h_out[ctx->out_slot][s].p);
+            }
+            if (pieces && out->n_pieces[s]) {
+                const size_t pb = out->n_pieces[s] * sizeof(fq_out_piece);
+                CK(ctx->h_pieces[ctx->out_slot][s].ensure(pb));
+                CK(cudaMemcpyAsync(ctx->h_pieces[ctx->out_slot][s].p, ctx->d_pieces[ctx->out_slot][s].p, pb, cudaMemcpyDeviceToHost, cs));
+                out->pieces[s] = static_cast<const fq_out_piece *>(ctx->h_pieces[ctx->out_slot][s].p);
+            }
         }
         if (ctx->async_out) CK(cudaEventRecord(ctx->ev_out[ctx->out_slot], ctx->s_out));
     }
@@ -647,7 +675,7 @@ void fq_destroy(fq_ctx *ctx)
         ctx->h_dbg[m].release();
     }
     for (int k = 0; k < 2; ++k) {
-        for (int s = 0; s < 4; ++s) { ctx->d_out[k][s].release(); ctx->h_out[k][s].release(); }
+        for (int s = 0; s < 4; ++s) { ctx->d_out[k][s].release(); ctx->h_out[k][s].release(); ctx->d_pieces[k][s].release(); ctx->h_pieces[k][s].release(); }
         for (int m = 0; m < 2; ++m) ctx->d_raw_slot[k][m].release();
         if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
         if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
@@ -670,6 +698,13 @@ fq_status fq_set_debug_results(fq_ctx *ctx, int enable)
 {
     if (!ctx) return FQ_ERR_ARG;
     ctx->debug_results = enable != 0;
+    return FQ_OK;
+}
+
+fq_status fq_set_output_pieces(fq_ctx *ctx, int enable)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    ctx->pieces = enable != 0;
     return FQ_OK;
 }
 

@@ -69,6 +69,8 @@ struct BatchInfo {
     uint32_t pad0;
     unsigned long long detect_key;   // autodetect: (record << 8 | offset), min over decisive reads
     unsigned long long out_bytes[4];
+    unsigned long long out_pieces[4];      // pieces mode: pieces / literal bytes per stream
+    unsigned long long out_literal[4];
     unsigned long long n_valid[2];
     unsigned long long paired_reads, paired_bases;
 };

@@ -28,7 +28,9 @@ struct EmitArgs {
     uint32_t check_ids;          // k_emit also compares the read ids of the two mates (FaQCs.cpp:383-389)
     uint32_t n_tiles;
     uint32_t *tile_sum;          // [4][n_tiles] -> exclusive bases after k_scan_tiles (u32: < 4 GiB per stream per batch)
-    uint8_t *out[4];
+                                 // pieces mode: [12][n_tiles]: stream bytes, pieces, literal bytes
+    uint8_t *out[4];             // pieces mode: the literal bytes of each stream
+    fq_out_piece *pieces[4];     // pieces mode: the streams as lists of pieces
     BatchInfo *info;
     unsigned long long *stats;   // global stats block (PAIRED_* counters are added here too)
     size_t filter_off;
@@ -146,7 +148,11 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t *tile_sum, uint32_
         if (threadIdx.x == 1023) s_carry = before + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) info->out_bytes[s] = s_carry;
+    if (threadIdx.x == 0) {
+        if (s < 4) info->out_bytes[s] = s_carry;
+        else if (s < 8) info->out_pieces[s - 4] = s_carry;
+        else info->out_literal[s - 8] = s_carry;
+    }
 }
 
 // Warp-cooperative copy of n bytes between arbitrarily aligned addresses.  The body is written
@@ -478,6 +484,224 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
                 if (tr) write_trimmed<8>(outp, src, rc, cn, ex, ey & kResLenMask, ey >> kResLenBits, o, sub);
                 else write_raw<8>(outp, src, rc, cn, sub);
             }
+        }
+    }
+}
+
+// ---- pieces mode ----------------------------------------------------------------------------------
+// The caller keeps its input buffers, and almost every surviving record of a real run is emitted exactly as it came in
+// (98.9 % of the C2 records).  In pieces mode a stream is therefore returned as a list of PIECES in stream order: a piece is
+// a byte range of one of the caller's input buffers (runs of consecutive untouched records of a warp are ONE piece; a
+// canonical discarded record is a piece of its own) or a range of the stream's literal bytes (trimmed, masked, re-encoded
+// or re-formatted records, written exactly as byte mode writes them).  Device -> host traffic drops from the size of the
+// output to the literal bytes plus 16 bytes per piece.
+struct LaneItems {
+    LaneRec L;
+    int stream[2];          // stream the mate goes to (-1: nowhere)
+    uint32_t bytes[2];      // its bytes in that stream
+    bool copy[2];           // the bytes are a range of the input (no literal bytes)
+    bool main[2];           // the mate sits in its main stream (R1 / R2 of a surviving pair, the only stream of single-end input)
+};
+
+__device__ __forceinline__ LaneItems lane_items(const EmitArgs &a, const DevOpts &o, uint32_t r)
+{
+    LaneItems I;
+    I.L = lane_record(a, o, r);
+    I.stream[0] = I.stream[1] = -1;
+    I.bytes[0] = I.bytes[1] = 0;
+    I.copy[0] = I.copy[1] = I.main[0] = I.main[1] = false;
+    if (r >= a.n_rec || o.qc_only) return I;
+    const LaneRec &L = I.L;
+    const int n_mates = o.paired ? 2 : 1;
+    const bool both = o.paired && L.valid[0] && L.valid[1];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (m >= n_mates) break;
+        if (L.valid[m]) {
+            I.main[m] = o.paired ? both : true;
+            I.stream[m] = both ? m : 2;
+            I.bytes[m] = L.tsize[m];
+            I.copy[m] = L.plain[m];
+        } else if (o.discard) {
+            I.stream[m] = 3;
+            I.bytes[m] = header_len(a.raw[m], L.rc[m], L.canon[m]) + 2 * L.rc[m].len + 5;
+            I.copy[m] = L.canon[m];
+        }
+    }
+    return I;
+}
+
+// Per lane and stream: pieces this record starts and literal bytes it adds.  Runs of copies in a main stream count once.
+__device__ __forceinline__ void piece_counts(const LaneItems &I, uint32_t lane, uint32_t (&pc)[4], uint32_t (&lb)[4], bool (&starts)[2], uint32_t (&run_mask)[2])
+{
+#pragma unroll
+    for (int s = 0; s < 4; ++s) pc[s] = lb[s] = 0;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const bool in_run = I.stream[m] >= 0 && I.main[m] && I.copy[m];
+        run_mask[m] = __ballot_sync(0xffffffffu, in_run);
+        const bool run_start = in_run && !(lane && ((run_mask[m] >> (lane - 1)) & 1u));
+        starts[m] = I.stream[m] >= 0 && (!in_run || run_start);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (I.stream[m] == s) {
+                pc[s] += starts[m] ? 1u : 0u;
+                lb[s] += I.copy[m] ? 0u : I.bytes[m];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTile) k_route_pieces(const EmitArgs a, const DevOpts o)
+{
+    __shared__ uint32_t s_sum[8][16];
+    const uint32_t r = blockIdx.x * kTile + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const LaneItems I = lane_items(a, o, r);
+    uint32_t pc[4], lb[4], run_mask[2];
+    bool starts[2];
+    piece_counts(I, lane, pc, lb, starts, run_mask);
+    uint32_t v[16];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        v[s] = (I.stream[0] == s ? I.bytes[0] : 0u) + (I.stream[1] == s ? I.bytes[1] : 0u);
+        v[4 + s] = pc[s];
+        v[8 + s] = lb[s];
+    }
+    const bool in = r < a.n_rec;
+    const bool both = o.paired && in && I.L.valid[0] && I.L.valid[1];
+    v[12] = in && I.L.valid[0];
+    v[13] = in && o.paired && I.L.valid[1];
+    v[14] = both ? 2u : 0u;                                                                   // PAIRED_READ_NUMBER (FaQCs.cpp:304-308)
+    v[15] = both ? (I.L.res[0].y & kResLenMask) + (I.L.res[1].y & kResLenMask) : 0u;          // PAIRED_BASE_LENGTH
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s_sum[wid][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        uint32_t t = 0;
+        for (int w = 0; w < (int)(kTile / 32); ++w) t += s_sum[w][threadIdx.x];
+        if (threadIdx.x < 12) a.tile_sum[threadIdx.x * a.n_tiles + blockIdx.x] = t;
+        else if (t) {
+            unsigned long long *dst = threadIdx.x == 12 ? &a.info->n_valid[0] : threadIdx.x == 13 ? &a.info->n_valid[1]
+                                    : threadIdx.x == 14 ? &a.info->paired_reads : &a.info->paired_bases;
+            atomicAdd(dst, (unsigned long long)t);
+            if (threadIdx.x == 14) atomicAdd(&a.stats[a.filter_off + FQ_PAIRED_READ_NUMBER], (unsigned long long)t);
+            if (threadIdx.x == 15) atomicAdd(&a.stats[a.filter_off + FQ_PAIRED_BASE_LENGTH], (unsigned long long)t);
+        }
+    }
+}
+
+// One warp owns 32 consecutive records.  Copies become piece descriptors; the other records are written into the stream's
+// literal bytes with the same writers byte mode uses (reading the raw bytes straight from global memory: they are few).
+template <bool PLAIN>
+__global__ void __launch_bounds__(kTile) k_emit_pieces(const EmitArgs a, const DevOpts o_in)
+{
+    DevOpts o = o_in;
+    if (PLAIN) {
+        o.replace_q = 0;
+        o.out_off = o.in_off;
+        o.qc_only = 0;
+    }
+    __shared__ uint32_t s_wsum[8][kTile / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * kTile + threadIdx.x;
+    const LaneItems I = lane_items(a, o, r);
+    uint32_t pc[4], lb[4], run_mask[2];
+    bool starts[2];
+    piece_counts(I, lane, pc, lb, starts, run_mask);
+    uint32_t inc[8], val[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        val[k] = k < 4 ? pc[k] : lb[k - 4];
+        inc[k] = warp_incl_scan(val[k], lane);
+        if (lane == 31) s_wsum[k][wid] = inc[k];
+    }
+    __syncthreads();
+    uint32_t poff[4], loff[4];      // first piece index / literal byte offset of this lane's record in each stream
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t before = a.tile_sum[(size_t)(4 + k) * a.n_tiles + blockIdx.x];
+        for (uint32_t w = 0; w < wid; ++w) before += s_wsum[k][w];
+        const uint32_t x = before + inc[k] - val[k];
+        if (k < 4) poff[k] = x; else loff[k - 4] = x;
+    }
+    if (o.qc_only) return;
+    const bool in = r < a.n_rec;
+    if (__ballot_sync(0xffffffffu, in) == 0) return;
+    const LaneRec &L = I.L;
+    if (a.check_ids && in && o.paired) {
+        if (pair_ids_differ(a.raw[0] + L.rc[0].hdr, L.rc[0].seq - L.rc[0].hdr - 1, a.raw[1] + L.rc[1].hdr, L.rc[1].seq - L.rc[1].hdr - 1)) {
+            atomicOr(&a.info->err, kErrPairId);
+            atomicMin(&a.info->err_record, r);
+        }
+    }
+    const int n_mates = o.paired ? 2 : 1;
+#pragma unroll 1
+    for (int m = 0; m < n_mates; ++m) {
+        const Rec rc = m ? L.rc[1] : L.rc[0];
+        const uint2 res = m ? L.res[1] : L.res[0];
+        const bool cn = m ? L.canon[1] : L.canon[0], ok = m ? L.valid[1] : L.valid[0];
+        const int st = m ? I.stream[1] : I.stream[0];
+        const uint32_t nbytes = m ? I.bytes[1] : I.bytes[0];
+        const bool is_copy = m ? I.copy[1] : I.copy[0], is_main = m ? I.main[1] : I.main[0], start = m ? starts[1] : starts[0];
+        const uint32_t mask = m ? run_mask[1] : run_mask[0];
+        // where this mate's piece / literal bytes go: behind mate 1's when both mates feed the same stream
+        uint32_t pidx = 0, lpos = 0;
+        if (st >= 0) {
+            pidx = st == 0 ? poff[0] : st == 1 ? poff[1] : st == 2 ? poff[2] : poff[3];
+            lpos = st == 0 ? loff[0] : st == 1 ? loff[1] : st == 2 ? loff[2] : loff[3];
+            if (m == 1 && I.stream[0] == st) {
+                pidx += starts[0] ? 1u : 0u;
+                lpos += I.copy[0] ? 0u : I.bytes[0];
+            }
+        }
+        fq_out_piece *plist = st == 0 ? a.pieces[0] : st == 1 ? a.pieces[1] : st == 2 ? a.pieces[2] : a.pieces[3];
+        // ---- copies: one piece per run of consecutive lanes in the main stream, one per record elsewhere
+        const bool in_run = st >= 0 && is_main && is_copy;
+        uint32_t run_len = nbytes;
+        {
+            const uint32_t rest = ~(mask >> lane);                         // this lane's run ends in front of the first clear bit above it
+            const int last = (int)lane + (rest ? __ffs(rest) - 1 : 32 - (int)lane) - 1;
+            const uint32_t end = __shfl_sync(0xffffffffu, rc.hdr + nbytes, in_run ? last : (int)lane);
+            if (in_run) run_len = end - rc.hdr;
+        }
+        if (st >= 0 && is_copy && start) plist[pidx] = fq_out_piece{(uint64_t)rc.hdr, run_len, (uint32_t)m};
+        // ---- literal records, four at a time (one per 8-lane group)
+        const bool lit = st >= 0 && !is_copy;
+        uint8_t *dstp = nullptr;
+        if (lit) {
+            dstp = (st == 0 ? a.out[0] : st == 1 ? a.out[1] : st == 2 ? a.out[2] : a.out[3]) + lpos;
+            plist[pidx] = fq_out_piece{(uint64_t)lpos, nbytes, 2u};
+        }
+        const uint8_t *src = m ? a.raw[1] : a.raw[0];
+        uint32_t todo = __ballot_sync(0xffffffffu, lit);
+        const uint32_t sub = lane & 7, grp = lane >> 3;
+        while (todo) {
+            int j = -1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int b = todo ? __ffs(todo) - 1 : -1;
+                if (b >= 0) todo &= todo - 1;
+                if ((int)grp == g) j = b;
+            }
+            const int js = j < 0 ? 0 : j;
+            Rec rj;
+            rj.hdr = __shfl_sync(0xffffffffu, rc.hdr, js);
+            rj.seq = __shfl_sync(0xffffffffu, rc.seq, js);
+            rj.qual = __shfl_sync(0xffffffffu, rc.qual, js);
+            rj.len = __shfl_sync(0xffffffffu, rc.len, js);
+            const uint32_t ex = __shfl_sync(0xffffffffu, res.x, js), ey = __shfl_sync(0xffffffffu, res.y, js);
+            const bool cj = __shfl_sync(0xffffffffu, (int)cn, js) != 0;
+            const bool tr = __shfl_sync(0xffffffffu, (int)ok, js) != 0;
+            const unsigned long long dp = __shfl_sync(0xffffffffu, (unsigned long long)dstp, js);
+            if (j < 0) continue;
+            uint8_t *const outp = reinterpret_cast<uint8_t *>(dp);
+            if (tr) write_trimmed<8>(outp, src, rj, cj, ex, ey & kResLenMask, ey >> kResLenBits, o, sub);
+            else write_raw<8>(outp, src, rj, cj, sub);
         }
     }
 }

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FQ_ABI_VERSION 2
+#define FQ_ABI_VERSION 3
 
 /* ---- FilterStat (FaQCs.h:46-75), same order, same meaning ---------------- */
 enum fq_filter_stat {
@@ -149,16 +149,28 @@ typedef struct fq_read_result {
 #define FQ_RR_QUAL_TRIMMED   0x0020  /* counted in READ_QUAL_TRIM */
 #define FQ_RR_ADAPTER        0x0040  /* an adapter clipped this read */
 
+/* One piece of an output stream (pieces mode, fq_set_output_pieces): `length` bytes starting at `offset` of
+ * source 0 = the r1 buffer handed to this batch, 1 = the r2 buffer, 2 = this stream's literal bytes (fq_batch_out.data). */
+typedef struct fq_out_piece {
+    uint64_t offset;
+    uint32_t length;
+    uint32_t source;
+} fq_out_piece;
+
 /* Result of one batch.  Host pointers are owned by the context and stay valid
  * until the next fq_process_* / fq_submit on the same context. */
 typedef struct fq_batch_out {
-    const uint8_t *data[FQ_NUM_STREAM];   /* emitted FASTQ bytes per stream (NULL if empty / qc_only) */
-    uint64_t       bytes[FQ_NUM_STREAM];
+    const uint8_t *data[FQ_NUM_STREAM];   /* emitted FASTQ bytes per stream (NULL if empty / qc_only); pieces mode: the literal bytes */
+    uint64_t       bytes[FQ_NUM_STREAM];  /* size of each stream (in pieces mode too) */
     uint64_t       n_records;             /* records per mate in this batch */
     uint64_t       n_valid[2];            /* surviving reads per mate */
     uint64_t       paired_read_number;    /* PAIRED_READ_NUMBER increment (FaQCs.cpp:304-308) */
     uint64_t       paired_base_length;
     const fq_read_result *results[2];     /* per-read verdicts (only if debug results were requested) */
+    /* pieces mode: each stream as a list of pieces in stream order (concatenating them gives the `bytes[s]` stream bytes) */
+    const fq_out_piece *pieces[FQ_NUM_STREAM];
+    uint64_t       n_pieces[FQ_NUM_STREAM];
+    uint64_t       literal_bytes[FQ_NUM_STREAM];
 } fq_batch_out;
 
 /* Flattened statistics.  All counters are u64 like the
@@ -197,6 +209,12 @@ fq_status fq_create(const fq_options *opt, int device, fq_ctx **out);
 void      fq_destroy(fq_ctx *ctx);
 const char *fq_last_error(const fq_ctx *ctx);   /* ctx may be NULL: last create error */
 
+/* Pieces mode (off by default).  The routing loops of the reference write every surviving read back out
+ * (FaQCs.cpp:296-361, 431-496, 634-659, 696-720; write_read, fastq.cpp:127-138) although almost all of them are untouched.
+ * With pieces on, fq_batch_out describes each stream as a list of fq_out_piece: byte ranges of the CALLER'S input buffers
+ * (runs of untouched records) and ranges of a small literal buffer (the records that changed).  A writer hands the list to
+ * writev(2); nothing but the literal bytes and the list crosses the PCIe link on the way back. */
+fq_status fq_set_output_pieces(fq_ctx *ctx, int enable);
 /* Ask for per-read verdicts in fq_batch_out.results (off by default). */
 fq_status fq_set_debug_results(fq_ctx *ctx, int enable);
 /* parse_id(r1.def) == parse_id(r2.def) check of FaQCs.cpp:383-389 (on by default). */

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, f"declared in include/faqcs_b200.h but not exported: {missing}"
     lib.fq_abi_version.restype = ctypes.c_int
-    assert lib.fq_abi_version() == 2
+    assert lib.fq_abi_version() == 3
     lib.fq_build_info.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.fq_build_info()
 
@@ -43,7 +43,7 @@ def test_struct_sizes_match_the_header():
     # sizes the C compiler gives the PODs (x86-64 SysV): guards the ctypes mirror against drift
     assert ctypes.sizeof(api.CReadResult) == 16
     assert ctypes.sizeof(api.COptions) == 80
-    assert ctypes.sizeof(api.CBatchOut) == 120
+    assert ctypes.sizeof(api.CBatchOut) == 216
     assert ctypes.sizeof(api.CStatsView) == 336
     assert api.READ_RESULT_DTYPE.itemsize == 16
 

@@ -170,6 +170,77 @@ def test_anticorrelated_mates_fill_the_unpaired_stream():
     both(a, b, lambda: Options(discard_output=True, input_quality_offset=33), batch_records=900)
 
 
+@pytest.mark.parametrize("case", ["c2", "c2_single", "c5", "crlf", "routing", "thirds"])
+def test_pieces_mode_expands_to_the_byte_streams(case):
+    """fq_set_output_pieces: every stream comes back as pieces of the caller's input plus literal bytes; expanding them must give
+    exactly the bytes byte mode emits (and the oracle), with the same statistics.  Most C2 records travel as pieces."""
+    rng = np.random.default_rng(31)
+    rnd = lambda n, al="ACGT": "".join(rng.choice(list(al), size=n))
+    r2 = None
+    kw = dict(discard_output=True)
+    if case == "c2":
+        w = synth.c2(20000); r1, r2 = w.r1, w.r2
+    elif case == "c2_single":
+        w = synth.c2(20000); r1 = w.r1; kw = dict(quality=20)
+    elif case == "c5":
+        w = synth.c5(15000); r1 = w.r1
+        kw = dict(mode=MODE_HARD, quality=20, average_quality=25.0, replace_to_N_q=10, discard_output=True)
+    elif case == "crlf":
+        recs = [(f"@c{i} x", rnd(int(rng.integers(60, 140))), None) for i in range(500)]
+        recs = [(h, s, "h" * (len(s) - 1) + "D") for h, s, _ in recs]
+        r1 = np.frombuffer(fastq_bytes(recs, "\r\n"), dtype=np.uint8); kw = dict(min_read_length=100, discard_output=True)
+    elif case == "routing":
+        a, b = [], []
+        for i in range(3000):
+            L = int(rng.integers(30, 130))
+            a.append((f"@p{i}/1", "NN" + rnd(L) + "TNN" if i % 3 == 0 else rnd(L, "ACGTN" if i % 5 == 0 else "ACGT"), None))
+            b.append((f"@p{i}/2", rnd(L) if i % 4 else "A" * L, None))
+        q = lambda s_: "".join(chr(int(x)) for x in rng.integers(35, 74, size=len(s_)))
+        r1 = np.frombuffer(fastq_bytes([(h, s_, q(s_)) for h, s_, _ in a]), dtype=np.uint8)
+        r2 = np.frombuffer(fastq_bytes([(h, s_, q(s_)) for h, s_, _ in b]), dtype=np.uint8)
+        kw = dict(discard_output=True, quality=12, input_quality_offset=33)
+    else:
+        thirds = ["+", "x", "+name 1", "", "+"]
+        buf = b""
+        for i in range(600):
+            L = int(rng.integers(60, 150))
+            buf += f"@t{i}\n{rnd(L)}\n{thirds[i % 5]}\n{'I' * (L - 1)}5\n".encode()
+        r1 = np.frombuffer(buf, dtype=np.uint8); kw = dict(discard_output=True, input_quality_offset=33, min_read_length=100)
+    with Engine(Options(**kw)) as plain, Engine(Options(**kw)) as pc, OracleEngine(Options(**kw)) as ora:
+        pc.set_output_pieces(True)
+        for e in (plain, pc, ora):
+            e.autodetect(r1, r2)
+        a = plain.process(r1, r2)
+        b = pc.process(r1, r2)
+        c = ora.process(r1, r2)
+        assert b.pieces is not None and b.stream_bytes == a.stream_bytes
+        got = b.expand(r1, r2)
+        assert [bytes(x) for x in got] == [bytes(x) for x in a.streams] == [bytes(x) for x in c.streams]
+        assert not plain.stats().diff(pc.stats()) and not pc.stats().diff(ora.stats())
+        if case == "c2":        # almost everything is a piece of the input: literal bytes are a small fraction
+            assert sum(len(x) for x in b.streams) < 0.2 * sum(a.stream_bytes)
+            assert sum(len(p) for p in b.pieces) < 0.4 * 2 * b.n_records
+        # several batches: pieces refer to the buffers of THEIR batch
+        cuts1 = [0] + [int(x) for x in np.flatnonzero(r1 == 10)[3::4][999::1000] + 1]
+        if cuts1[-1] != r1.size:
+            cuts1.append(int(r1.size))
+        if r2 is not None:
+            cuts2 = [0] + [int(x) for x in np.flatnonzero(r2 == 10)[3::4][999::1000] + 1]
+            if cuts2[-1] != r2.size:
+                cuts2.append(int(r2.size))
+        acc = [b"", b"", b"", b""]
+        with Engine(Options(**kw)) as many:
+            many.set_output_pieces(True)
+            many.autodetect(r1, r2)
+            for k in range(len(cuts1) - 1):
+                x1 = r1[cuts1[k]:cuts1[k + 1]]
+                x2 = r2[cuts2[k]:cuts2[k + 1]] if r2 is not None else None
+                res = many.process(x1, x2, 1000 * k, k == len(cuts1) - 2)
+                for s_, part in enumerate(res.expand(x1, x2)):
+                    acc[s_] += part
+        assert [bytes(x) for x in acc] == [bytes(x) for x in a.streams]
+
+
 def test_pipelined_submit_run_wait_equals_synchronous():
     from faqcs_b200 import shard
     w = synth.c2(12000)
