@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -262,24 +263,25 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
             CK(cudaMemsetAsync(&info->n_cr_eol[m], 0, 4, ctx->stream));
             CK(cudaMemsetAsync(&info->seg_overflow, 0, 4, ctx->stream));
         }
-        // the fast instance first (plain LF text); the exact instance right behind it does the work only if the fast one met
-        // a control character other than '\n' (CRLF input: remembered, later batches go straight to the exact instance)
-        if (!ctx->frame_exact[m]) {
-            k_frame_lines<true><<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, seg_bytes, n_seg, ctx->d_nl[m].as<uint32_t>(), seg_cap, seg_count, info, m, 0);
-            ctx->launches++;
+        // the fast instance first (plain LF text); the exact instance redoes the mate only if the fast one met a control
+        // character other than '\n' (CRLF input: remembered, later batches go straight to the exact instance)
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool exact = ctx->frame_exact[m];
+            if (exact) k_frame_lines<false><<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, seg_bytes, n_seg, ctx->d_nl[m].as<uint32_t>(), seg_cap, seg_count, info, m, 0);
+            else k_frame_lines<true><<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, seg_bytes, n_seg, ctx->d_nl[m].as<uint32_t>(), seg_cap, seg_count, info, m, 0);
+            k_scan_segments<<<1, 1024, 0, ctx->stream>>>(seg_count, n_seg, seg_base, info, m);
+            ctx->launches += 2;
+            CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (exact || !ctx->h_info->frame_exact[m]) break;
+            ctx->frame_exact[m] = true;                   // the fast instance gave up: run the exact one
         }
-        k_frame_lines<false><<<grid, kFrameThreads, 0, ctx->stream>>>(d_raw, n, seg_bytes, n_seg, ctx->d_nl[m].as<uint32_t>(), seg_cap, seg_count, info, m,
-                                                                     ctx->frame_exact[m] ? 0 : 1);
-        k_scan_segments<<<1, 1024, 0, ctx->stream>>>(seg_count, n_seg, seg_base, info, m);
-        ctx->launches += 2;
-        CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
         n_lines = ctx->h_info->n_lines[m];
-        if (ctx->h_info->frame_exact[m]) ctx->frame_exact[m] = true;
         if (ctx->h_info->seg_overflow == 0) break;
         seg_cap = ctx->h_info->seg_overflow + 64;           // very short lines: repeat once with the exact need
     }
-    if (ctx->h_info->n_cr[m]) {
+    const bool had_cr = ctx->h_info->n_cr[m] != 0;
+    if (had_cr) {
         // CRLF input (or stray CRs): exact CR count, to be compared with the CRs that sit right before a '\n'
         CK(cudaMemsetAsync(&info->n_cr[m], 0, 4, ctx->stream));
         k_count_byte<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_raw, n, '\r', &info->n_cr[m]);
@@ -297,6 +299,21 @@ fq_status frame_mate(fq_ctx *ctx, int m, const uint8_t *d_raw, size_t n, uint32_
     const LineIndex li{ctx->d_nl[m].as<uint32_t>(), seg_base, seg_cap, n_seg};
     k_build_records<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(li, n_rec, ctx->d_rec[m].as<Rec>(), ctx->d_canon[m].as<uint8_t>(), info, m);
     ctx->launches++;
+    if (had_cr) {
+        // exact CR count against the CRs that close a line: any other one cuts its line short (strpbrk, fastq.cpp:44)
+        CK(cudaMemcpyAsync(ctx->h_info, info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_info->n_cr[m] != ctx->h_info->n_cr_eol[m]) {
+            // the lengths (and a possible |seq| != |qual| verdict) of k_build_records are void for such lines: redo them
+            if ((ctx->h_info->err & ~kErrLenMismatch) == 0) {
+                const uint32_t zero = 0, none = 0xffffffffu;
+                CK(cudaMemcpyAsync(&info->err, &zero, 4, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(&info->err_record, &none, 4, cudaMemcpyHostToDevice, ctx->stream));
+            }
+            k_fix_lone_cr<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(d_raw, ctx->d_rec[m].as<Rec>(), ctx->d_canon[m].as<uint8_t>(), n_rec, info, m);
+            ctx->launches++;
+        }
+    }
     *n_rec_out = n_rec;
     return FQ_OK;
 }
@@ -307,13 +324,13 @@ fq_status map_device_error(fq_ctx *ctx, const BatchInfo &hi)
     char where[64];
     snprintf(where, sizeof where, " (record %u)", hi.err_record);
     if (hi.err & kErrLenMismatch) return fail(ctx, FQ_ERR_FORMAT, std::string("fastq.cpp:next_read: |Sequence| != |Quality|") + where);
-    if (hi.err & kErrLoneCR) return fail(ctx, FQ_ERR_FORMAT, std::string("carriage return inside a line is not supported") + where);
     if (hi.err & kErrPairId) return fail(ctx, FQ_ERR_FORMAT, std::string("FaQCs.cpp:trim: I/O error") + where);
     if (hi.err & kErrUnknownBase) return fail(ctx, FQ_ERR_BASE, std::string("seq_overlap.cpp:na_to_bits: Unknown base!") + where);
     if (hi.err & kErrQualGt41)
         return fail(ctx, FQ_ERR_QUALITY,
                     std::string("fastq.h:quality_score: Found a quality score value that is greater than the maximum allowed quality score") + where);
     if (hi.err & kErrReencode) return fail(ctx, FQ_ERR_QUALITY, std::string("trim.cpp: quality error!") + where);
+    if (hi.err & kErrInternal) return fail(ctx, FQ_ERR_CUDA, "internal: a bulk copy did not complete");
     return fail(ctx, FQ_ERR_STATE, "unknown device error");
 }
 
@@ -359,8 +376,6 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     CK(cudaStreamSynchronize(ctx->stream));
     {
         BatchInfo hi = *ctx->h_info;
-        for (int m = 0; m < n_mates; ++m)
-            if (hi.n_cr[m] != hi.n_cr_eol[m]) hi.err |= kErrLoneCR;
         st = map_device_error(ctx, hi);
         if (st != FQ_OK) return st;
     }
@@ -501,6 +516,8 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         while (ea.parts < 8 && (32.0 / ea.parts) * avg * 1.08 + 32.0 > (double)kEmitSlab) ea.parts *= 2;
     }
     const bool pieces = ctx->pieces && !o.qc_only;
+    ea.prefetch_tiles = (uint32_t)(ctx->sm_count * FQ_EMIT_MIN_CTAS);      // one wave of k_emit CTAs
+    if (const char *pf = getenv("FAQCS_B200_EMIT_PREFETCH_TILES")) ea.prefetch_tiles = (uint32_t)atoi(pf);
     CK(ctx->d_tile.ensure((size_t)ea.n_tiles * (pieces ? 12 : 4) * 4));
     ea.tile_sum = ctx->d_tile.as<uint32_t>();
     ea.info = info;

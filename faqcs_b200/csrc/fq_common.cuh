@@ -28,7 +28,7 @@ enum : uint32_t {
     kErrReencode = 1u << 2,     // trim.cpp:521-523
     kErrUnknownBase = 1u << 3,  // seq_overlap.cpp:409
     kErrPairId = 1u << 4,       // FaQCs.cpp:383-389
-    kErrLoneCR = 1u << 5,       // '\r' not followed by '\n' (unsupported line ending)
+    kErrInternal = 1u << 6,     // a bulk copy did not complete (should never happen; reported instead of hanging)
 };
 
 struct Rec {
@@ -137,6 +137,12 @@ constexpr uint32_t kFlagMasked = 0x80u;
 constexpr uint32_t kResPlusBad = 1u << 31;
 constexpr uint32_t kResLenBits = 24;            // reads < 16 Mi bases
 constexpr uint32_t kResLenMask = (1u << kResLenBits) - 1;
+
+// One instruction asks the L2 for a whole byte range (Blackwell / Hopper bulk prefetch): base 16-byte aligned, size a multiple of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 __host__ __device__ inline uint32_t pack_len_flags(uint32_t len, uint32_t flags) { return (len & kResLenMask) | (flags << kResLenBits); }
 

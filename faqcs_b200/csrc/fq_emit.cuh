@@ -22,9 +22,12 @@ struct EmitArgs {
     uint64_t raw_bytes[2];
     const Rec *rec[2];
     const uint2 *res[2];
-    const uint8_t *canon[2];     // 1 = LF line ends + bare '+' line (raw bytes == write_read output)
+    const uint8_t *canon[2];     // record code: 1 = LF line ends + one-character third line (canonical: raw bytes == write_read
+                                 // output once k_trim has seen the '+'), 0 = CRLF line ends or a longer third line, 2 = a '\r'
+                                 // somewhere inside a line (the content of a line ends at its FIRST '\r', fastq.cpp:44)
     uint32_t n_rec;
     uint32_t parts;              // k_emit stages the 32 records of a warp in this many rounds (1, 2, 4, 8)
+    uint32_t prefetch_tiles;     // k_emit asks the L2 for the slabs of the tile this many tiles ahead (0: off)
     uint32_t check_ids;          // k_emit also compares the read ids of the two mates (FaQCs.cpp:383-389)
     uint32_t n_tiles;
     uint32_t *tile_sum;          // [4][n_tiles] -> exclusive bases after k_scan_tiles (u32: < 4 GiB per stream per batch)
@@ -36,10 +39,16 @@ struct EmitArgs {
     size_t filter_off;
 };
 
-__device__ __forceinline__ uint32_t header_len(const uint8_t *raw, const Rec &rc, bool canon = false)
+__device__ __forceinline__ uint32_t header_len(const uint8_t *raw, const Rec &rc, uint32_t ccode = 0)
 {
     uint32_t n = rc.seq - rc.hdr - 1;
-    if (!canon && n && raw[rc.hdr + n - 1] == '\r') --n;
+    if (ccode == 1 || n == 0) return n;
+    if (ccode == 2) {                                   // strpbrk semantics: the header ends at its first '\r'
+        for (uint32_t i = 0; i < n; ++i)
+            if (raw[rc.hdr + i] == '\r') return i;
+        return n;
+    }
+    if (raw[rc.hdr + n - 1] == '\r') --n;
     return n;
 }
 
@@ -56,7 +65,7 @@ __device__ __forceinline__ void route_sizes(const EmitArgs &a, const DevOpts &o,
     for (int m = 0; m < n_mates; ++m) {
         const Rec rc = a.rec[m][r];
         const uint2 v = a.res[m][r];
-        const uint32_t hl = header_len(a.raw[m], rc, a.canon[m][r] != 0);
+        const uint32_t hl = header_len(a.raw[m], rc, a.canon[m][r]);
         wl[m] = v.y & kResLenMask;
         valid[m] = ((v.y >> kResLenBits) & FQ_RR_VALID) != 0;
         trimmed[m] = hl + 2 * wl[m] + 5;
@@ -215,10 +224,11 @@ __device__ __forceinline__ void copy_span(uint8_t *__restrict__ dst, const uint8
 // mutations trim_read leaves behind.  `plain`: the record is canonical, untrimmed and untouched,
 // so the output is its raw bytes.
 template <uint32_t W = 32>
-__device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, const Rec &rc, bool canon, uint32_t lo, uint32_t wl,
+__device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, const Rec &rc, uint32_t ccode, uint32_t lo, uint32_t wl,
                                               uint32_t flags, const DevOpts &o, uint32_t lane)
 {
-    const uint32_t hl = header_len(raw, rc, canon);
+    const bool canon = ccode == 1;
+    const uint32_t hl = header_len(raw, rc, ccode);
     const bool masked = (flags & kFlagMasked) != 0;
     const bool requal = o.in_off != o.out_off;
     if (canon && lo == 0 && wl == rc.len && !masked && !requal && o.replace_q == 0) {
@@ -267,9 +277,10 @@ __device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, 
 
 // Emit one discarded read: the raw, unmasked record (copy taken before trim(), FaQCs.cpp:279-285).
 template <uint32_t W = 32>
-__device__ __forceinline__ void write_raw(uint8_t *dst, const uint8_t *raw, const Rec &rc, bool canon, uint32_t lane)
+__device__ __forceinline__ void write_raw(uint8_t *dst, const uint8_t *raw, const Rec &rc, uint32_t ccode, uint32_t lane)
 {
-    const uint32_t hl = header_len(raw, rc, canon);
+    const bool canon = ccode == 1;
+    const uint32_t hl = header_len(raw, rc, ccode);
     if (canon) {
         copy_span<W>(dst, raw + rc.hdr, hl + 2 * rc.len + 5, lane);
         return;
@@ -287,7 +298,8 @@ __device__ __forceinline__ void write_raw(uint8_t *dst, const uint8_t *raw, cons
 struct LaneRec {
     Rec rc[2];
     uint2 res[2];
-    bool canon[2], valid[2], plain[2];
+    uint32_t ccode[2];      // record code (EmitArgs::canon) with the '+' check folded in: 1 only if the raw bytes are the canonical record
+    bool valid[2], plain[2];
     uint32_t tsize[2];      // bytes of the trimmed record
 };
 
@@ -301,12 +313,13 @@ __device__ __forceinline__ LaneRec lane_record(const EmitArgs &a, const DevOpts 
         L.rc[m] = a.rec[m][r];
         const uint2 rv = a.res[m][r];
         L.res[m] = make_uint2(rv.x & ~kResPlusBad, rv.y);
-        L.canon[m] = a.canon[m][r] != 0 && !(rv.x & kResPlusBad);
+        L.ccode[m] = a.canon[m][r];
+        if (L.ccode[m] == 1 && (rv.x & kResPlusBad)) L.ccode[m] = 0;
         const uint32_t fl = L.res[m].y >> kResLenBits, wl = L.res[m].y & kResLenMask;
         L.valid[m] = (fl & FQ_RR_VALID) != 0;
-        L.tsize[m] = header_len(a.raw[m], L.rc[m], L.canon[m]) + 2 * wl + 5;
+        L.tsize[m] = header_len(a.raw[m], L.rc[m], L.ccode[m]) + 2 * wl + 5;
         // untouched canonical record: the emitted bytes are the raw bytes
-        L.plain[m] = L.valid[m] && L.canon[m] && L.res[m].x == 0 && wl == L.rc[m].len && !(fl & kFlagMasked) && !requal && o.replace_q == 0;
+        L.plain[m] = L.valid[m] && L.ccode[m] == 1 && L.res[m].x == 0 && wl == L.rc[m].len && !(fl & kFlagMasked) && !requal && o.replace_q == 0;
     }
     return L;
 }
@@ -348,10 +361,40 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Bulk (TMA) copy global -> shared of a 16-byte aligned range, completion on an mbarrier (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// Waits for the phase with the given parity; gives up after a bounded number of polls (returns false) instead of hanging.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        uint32_t done;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
 extern __shared__ __align__(16) uint8_t g_emit_smem[];
 
 #ifndef FQ_EMIT_MIN_CTAS
 #define FQ_EMIT_MIN_CTAS 2
+#endif
+// stage the slabs with one bulk (TMA) copy per stage instead of 16-byte cp.async requests from every lane
+#ifndef FQ_EMIT_BULK
+#define FQ_EMIT_BULK 1
+#endif
+#ifndef FQ_EMIT_PREFETCH
+#define FQ_EMIT_PREFETCH 0      // measured: 0.656 -> 0.746 ms with it (C2); the staging loads are not what bounds the kernel
 #endif
 // PLAIN: no quality re-encoding and no G->N replacement (the default run): those branches of write_trimmed are compiled out.
 template <bool PLAIN>
@@ -366,9 +409,27 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
     __shared__ uint32_t s_wsum[4][kTile / 32];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kTile + threadIdx.x;
+#if FQ_EMIT_PREFETCH
+    // The tile one wave of CTAs ahead will be staged by the CTA that takes this one's place: ask the L2 for its slabs now
+    // (lanes 0 / 1: mate 1 / mate 2), so that its staging loads find them there instead of waiting for DRAM.
+    uint32_t pf_lo = 0, pf_hi = 0;
+    {
+        const uint32_t r_first = (blockIdx.x + a.prefetch_tiles) * kTile + wid * 32;
+        if (lane < (o.paired ? 2u : 1u) && a.prefetch_tiles && r_first < a.n_rec) {
+            const Rec *rec = lane ? a.rec[1] : a.rec[0];
+            const uint32_t r_last = min(r_first + 31u, a.n_rec - 1u);
+            pf_lo = rec[r_first].hdr & ~15u;
+            const Rec last = rec[r_last];
+            pf_hi = (uint32_t)min((uint64_t)((last.qual + last.len + 1 + 15) & ~15u), (lane ? a.raw_bytes[1] : a.raw_bytes[0]) & ~(uint64_t)15);
+        }
+    }
+#endif
     uint32_t sz[4], wl[2];
     bool valid[2];
     route_sizes(a, o, r, sz, valid, wl);
+#if FQ_EMIT_PREFETCH
+    if (pf_hi > pf_lo) prefetch_l2_bulk((lane ? a.raw[1] : a.raw[0]) + pf_lo, pf_hi - pf_lo);
+#endif
     uint32_t inc[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -397,6 +458,13 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
     const bool both = o.paired && in && L.valid[0] && L.valid[1];
     uint8_t *const slab = g_emit_smem + (size_t)wid * kEmitSlab;
     const uint32_t slab_s = (uint32_t)__cvta_generic_to_shared(slab);
+#if FQ_EMIT_BULK
+    __shared__ __align__(8) unsigned long long s_bar[kTile / 32];
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[wid]);
+    uint32_t bar_phase = 0;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+#endif
     const int n_mates = o.paired ? 2 : 1;
 
     // n_mates * P stages (mate, part): the slab of a stage is the raw bytes of 32 / P consecutive records; the host
@@ -406,9 +474,9 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
     const int P = (int)a.parts;
     const int n_stages = n_mates * P;
     // per-stage view of this lane's record
-    struct Mate { Rec rc; uint2 res; bool canon, valid, plain; uint32_t tsize; };
+    struct Mate { Rec rc; uint2 res; uint32_t ccode; bool valid, plain; uint32_t tsize; };
     auto mate_of = [&](int m) -> Mate {
-        return m ? Mate{L.rc[1], L.res[1], L.canon[1], L.valid[1], L.plain[1], L.tsize[1]} : Mate{L.rc[0], L.res[0], L.canon[0], L.valid[0], L.plain[0], L.tsize[0]};
+        return m ? Mate{L.rc[1], L.res[1], L.ccode[1], L.valid[1], L.plain[1], L.tsize[1]} : Mate{L.rc[0], L.res[0], L.ccode[0], L.valid[0], L.plain[0], L.tsize[0]};
     };
     auto extent = [&](int t, const Rec &rc, uint32_t &lo, uint32_t &hi, uint32_t &part_mask) -> bool {
         const int m = t / P, part = t % P;
@@ -432,8 +500,14 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
             const uint8_t *src = m ? a.raw[1] : a.raw[0];      // src[offset] = byte at raw offset `offset`
             if (hi - lo <= kEmitSlab) {
                 __syncwarp();                                  // everyone is done reading the previous slab
+#if FQ_EMIT_BULK
+                if (lane == 0) bulk_g2s(slab_s, src + lo, hi - lo, bar);
+                if (!mbar_wait(bar, bar_phase)) { atomicOr(&a.info->err, kErrInternal); return; }
+                bar_phase ^= 1u;
+#else
                 for (uint32_t c = lo + 16 * lane; c < hi; c += 16 * 32) cp_async16(slab_s + (c - lo), src + c);
                 cp_async_wait_all();
+#endif
                 __syncwarp();
                 src = slab - lo;
             }
@@ -457,7 +531,7 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
             if (trimmed) dstp = main ? out_main + off_main : a.out[2] + off[2];
             else if (disc) {
                 dstp = a.out[3] + off[3];
-                if (m == 1 && !L.valid[0]) dstp += header_len(a.raw[0], L.rc[0], L.canon[0]) + 2 * L.rc[0].len + 5;
+                if (m == 1 && !L.valid[0]) dstp += header_len(a.raw[0], L.rc[0], L.ccode[0]) + 2 * L.rc[0].len + 5;
             }
             uint32_t todo = __ballot_sync(0xffffffffu, trimmed || disc);
             const uint32_t sub = lane & 7, grp = lane >> 3;
@@ -476,7 +550,7 @@ __global__ void __launch_bounds__(kTile, FQ_EMIT_MIN_CTAS) k_emit(const EmitArgs
                 rc.qual = __shfl_sync(0xffffffffu, M.rc.qual, js);
                 rc.len = __shfl_sync(0xffffffffu, M.rc.len, js);
                 const uint32_t ex = __shfl_sync(0xffffffffu, M.res.x, js), ey = __shfl_sync(0xffffffffu, M.res.y, js);
-                const bool cn = __shfl_sync(0xffffffffu, (int)M.canon, js) != 0;
+                const uint32_t cn = __shfl_sync(0xffffffffu, M.ccode, js);
                 const bool tr = __shfl_sync(0xffffffffu, (int)trimmed, js) != 0;
                 const unsigned long long dp = __shfl_sync(0xffffffffu, (unsigned long long)dstp, js);
                 if (j < 0) continue;
@@ -524,8 +598,8 @@ __device__ __forceinline__ LaneItems lane_items(const EmitArgs &a, const DevOpts
             I.copy[m] = L.plain[m];
         } else if (o.discard) {
             I.stream[m] = 3;
-            I.bytes[m] = header_len(a.raw[m], L.rc[m], L.canon[m]) + 2 * L.rc[m].len + 5;
-            I.copy[m] = L.canon[m];
+            I.bytes[m] = header_len(a.raw[m], L.rc[m], L.ccode[m]) + 2 * L.rc[m].len + 5;
+            I.copy[m] = L.ccode[m] == 1;
         }
     }
     return I;
@@ -644,7 +718,8 @@ __global__ void __launch_bounds__(kTile) k_emit_pieces(const EmitArgs a, const D
     for (int m = 0; m < n_mates; ++m) {
         const Rec rc = m ? L.rc[1] : L.rc[0];
         const uint2 res = m ? L.res[1] : L.res[0];
-        const bool cn = m ? L.canon[1] : L.canon[0], ok = m ? L.valid[1] : L.valid[0];
+        const uint32_t cn = m ? L.ccode[1] : L.ccode[0];
+        const bool ok = m ? L.valid[1] : L.valid[0];
         const int st = m ? I.stream[1] : I.stream[0];
         const uint32_t nbytes = m ? I.bytes[1] : I.bytes[0];
         const bool is_copy = m ? I.copy[1] : I.copy[0], is_main = m ? I.main[1] : I.main[0], start = m ? starts[1] : starts[0];
@@ -695,7 +770,7 @@ __global__ void __launch_bounds__(kTile) k_emit_pieces(const EmitArgs a, const D
             rj.qual = __shfl_sync(0xffffffffu, rc.qual, js);
             rj.len = __shfl_sync(0xffffffffu, rc.len, js);
             const uint32_t ex = __shfl_sync(0xffffffffu, res.x, js), ey = __shfl_sync(0xffffffffu, res.y, js);
-            const bool cj = __shfl_sync(0xffffffffu, (int)cn, js) != 0;
+            const uint32_t cj = __shfl_sync(0xffffffffu, cn, js);
             const bool tr = __shfl_sync(0xffffffffu, (int)ok, js) != 0;
             const unsigned long long dp = __shfl_sync(0xffffffffu, (unsigned long long)dstp, js);
             if (j < 0) continue;

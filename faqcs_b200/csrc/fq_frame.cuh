@@ -108,6 +108,9 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane)
 #ifndef FQ_FRAME_MIN_CTAS
 #define FQ_FRAME_MIN_CTAS 4
 #endif
+#ifndef FQ_FRAME_PREFETCH
+#define FQ_FRAME_PREFETCH 1
+#endif
 template <bool FAST>
 __global__ void __launch_bounds__(kFrameThreads, FQ_FRAME_MIN_CTAS) k_frame_lines(const uint8_t *__restrict__ raw, uint64_t n, uint32_t seg_bytes, uint32_t n_seg,
                                                                uint32_t *__restrict__ nl_seg, uint32_t seg_cap, uint32_t *__restrict__ seg_count,
@@ -130,6 +133,11 @@ __global__ void __launch_bounds__(kFrameThreads, FQ_FRAME_MIN_CTAS) k_frame_line
         uint32_t cr_chunk = 0;                          // non-zero: this lane's bytes may hold a CR
         const uint32_t lane_base = (uint32_t)chunk_base + lane * 128;         // a batch is < 1 GiB per mate
         uint4 v[8];
+#if FQ_FRAME_PREFETCH
+        // one instruction asks the L2 for the chunk this warp reads FQ_FRAME_PREFETCH iterations from now
+        if (lane == 0 && aligned32 && chunk_base + (uint64_t)(FQ_FRAME_PREFETCH + 1) * kChunkBytes <= seg_hi)
+            prefetch_l2_bulk(raw + chunk_base + (uint64_t)FQ_FRAME_PREFETCH * kChunkBytes, kChunkBytes);
+#endif
         if (chunk_base + kChunkBytes <= seg_hi && aligned32) {
             // whole chunk inside the segment (warp-uniform): four 256-bit loads per lane (sm_100 LDG.256): each touches one
             // 32-byte sector once -- with 128-bit loads every sector is requested twice and the kernel is L1TEX-bound
@@ -347,10 +355,43 @@ __global__ void __launch_bounds__(256) k_build_records(const LineIndex li, uint3
     uint32_t m = len;
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(&info->max_len[mate], m);
+    // one atomic per warp on ONE address is what this kernel would spend its time on: look first, almost every warp then skips it
+    if ((threadIdx.x & 31) == 0 && m > *reinterpret_cast<volatile uint32_t *>(&info->max_len[mate])) atomicMax(&info->max_len[mate], m);
     if (bad) {
         atomicOr(&info->err, kErrLenMismatch);
         atomicMin(&info->err_record, r);
+    }
+}
+
+// A '\r' that is not the byte in front of a line's '\n' (rare: never in files written by sequencers or by FaQCs).  The
+// reference cuts the content of every line at its FIRST '\r' or '\n' (strpbrk, fastq.cpp:44,70,100) and drops the rest of
+// the line, so the lengths k_build_records derived from the line ends are too long for such lines.  One thread per record
+// re-reads the header, base and quality lines up to their first '\r' / '\n', rewrites the length, re-checks
+// |seq| == |qual| and marks the record with code 2 (the emitters then look for the first '\r' of the header as well).
+// Only launched when the batch holds such a '\r' (the exact framing instance counts them).
+__global__ void __launch_bounds__(256) k_fix_lone_cr(const uint8_t *__restrict__ raw, Rec *__restrict__ rec, uint8_t *__restrict__ canon, uint32_t n_rec,
+                                                     BatchInfo *info, int mate)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    Rec rc = rec[r];
+    auto content = [&](uint32_t from, bool &cr) -> uint32_t {       // bytes of the line starting at `from` up to its first '\r' or '\n'
+        uint32_t k = from;
+        while (raw[k] != '\n' && raw[k] != '\r') ++k;
+        cr = raw[k] == '\r' && raw[k + 1] != '\n';                  // a CR that is not part of a CRLF line end
+        return k - from;
+    };
+    bool cr_h, cr_s, cr_q;
+    content(rc.hdr, cr_h);
+    const uint32_t ls = content(rc.seq, cr_s), lq = content(rc.qual, cr_q);
+    if (ls != lq) {
+        atomicOr(&info->err, kErrLenMismatch);
+        atomicMin(&info->err_record, r);
+    }
+    if (cr_h || cr_s || cr_q) canon[r] = 2;
+    if (ls != rc.len) {
+        rc.len = ls;
+        rec[r] = rc;
     }
 }
 
@@ -417,8 +458,9 @@ __device__ __forceinline__ bool pair_ids_differ(const uint8_t *ha, uint32_t na, 
         }
         if (decided && same) return false;
     }
-    if (na && ha[na - 1] == '\r') --na;
-    if (nb && hb[nb - 1] == '\r') --nb;
+    // the content of a header line ends at its first '\r' (fastq.cpp:44)
+    for (uint32_t i = 0; i < na; ++i) if (ha[i] == '\r') { na = i; break; }
+    for (uint32_t i = 0; i < nb; ++i) if (hb[i] == '\r') { nb = i; break; }
     const uint32_t la = id_length(ha, na), lb = id_length(hb, nb);
     bool same = (la == lb);
     for (uint32_t i = 0; same && i < la; ++i) same = (ha[i] == hb[i]);

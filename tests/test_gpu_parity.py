@@ -133,6 +133,25 @@ def test_third_line_variants():
     both(r1, None, lambda: Options(discard_output=True, input_quality_offset=33, min_read_length=100))      # raw copies to discard
 
 
+def test_lone_carriage_returns_cut_the_line():
+    """A '\\r' that is not part of a CRLF line end: the content of the line ends there (strpbrk, fastq.cpp:44); pinned against the
+    reference binary in tests/test_oracle_micro.py, here CUDA vs oracle in byte mode, pieces mode and several batches."""
+    from test_oracle_micro import lone_cr_input
+    r1 = lone_cr_input()
+    both(r1, None, lambda: Options(discard_output=True, min_read_length=100, input_quality_offset=33))
+    both(r1, None, lambda: Options(discard_output=True, min_read_length=100, input_quality_offset=33), batch_records=70)
+    with Engine(Options(discard_output=True, min_read_length=100, input_quality_offset=33)) as a, \
+            Engine(Options(discard_output=True, min_read_length=100, input_quality_offset=33)) as b:
+        b.set_output_pieces(True)
+        x, y = a.process(r1), b.process(r1)
+        assert [bytes(s_) for s_ in y.expand(r1)] == [bytes(s_) for s_ in x.streams]
+    bad = b"@a\nACGT\rXX\n+\nIII5#\n"             # content lengths 4 vs 5 after the cut
+    with Engine(Options(input_quality_offset=33)) as e:
+        with pytest.raises(FaqcsError) as ei:
+            e.process(bad)
+        assert "|Sequence| != |Quality|" in str(ei.value)
+
+
 def test_pairs_routing_with_discard():
     rng = np.random.default_rng(7)
     rnd = lambda n, al="ACGT": "".join(rng.choice(list(al), size=n))

@@ -148,3 +148,37 @@ def test_avgq_boundary():
     recs = [("@e%d" % i, "ACGT" * 25, chr(33 + 30) * (100 - i) + chr(33 + 29) * i) for i in range(0, 6)]
     check_records(recs, Options(average_quality=30.0, quality=0, input_quality_offset=33, discard_output=True))
     check_records(recs, Options(average_quality=29.97, quality=0, input_quality_offset=33, discard_output=True))
+
+
+def lone_cr_input():
+    """Lines that hold a '\\r' which is not part of a CRLF line end: the reference keeps what precedes the FIRST '\\r' of a line
+    (strpbrk, fastq.cpp:44,70,100) and drops the rest of the line."""
+    rng = np.random.default_rng(77)
+    buf = b""
+    for i in range(300):
+        L = int(rng.integers(60, 140))
+        s, q = rnd(rng, L), "".join(chr(int(x)) for x in rng.integers(40, 74, size=L - 1)) + "5"
+        k = i % 6
+        if k == 0:          # junk behind a CR on the base and quality lines (equal content lengths)
+            buf += f"@cr{i}\n{s}\rJUNK\n+\n{q}\rMOREJUNK!\n".encode()
+        elif k == 1:        # CR inside the header
+            buf += f"@cr{i} left\rright side\n{s}\n+\n{q}\n".encode()
+        elif k == 2:        # CRLF record among them
+            buf += f"@cr{i}\r\n{s}\r\n+\r\n{q}\r\n".encode()
+        elif k == 3:        # CR on the '+' line (content is dropped anyway)
+            buf += f"@cr{i}\n{s}\n+x\ry\n{q}\n".encode()
+        elif k == 4:        # double CR before the line end
+            buf += f"@cr{i}\n{s}\r\r\n+\n{q}\r\r\n".encode()
+        else:
+            buf += f"@cr{i}\n{s}\n+\n{q}\n".encode()
+    return np.frombuffer(buf, dtype=np.uint8)
+
+
+def test_lone_carriage_returns_cut_the_line():
+    r1 = lone_cr_input()
+    opt = Options(discard_output=True, min_read_length=100, input_quality_offset=33)
+    ref = refcli.run_reference(unpaired=r1, flags=refcli.flags_for(opt), threads=1)
+    with OracleEngine(opt) as eng:
+        streams, _ = run_engine(eng, r1, None)
+        assert_matches_reference(ref, streams, eng.stats(), opt)
+    assert b"JUNK" not in ref["streams"][2] and b"right side" not in ref["streams"][2]
