@@ -464,7 +464,7 @@ def main():
             pass
         kernels = {}
         for k in ("frame", "adapter", "trim", "emit"):
-            if seg_ms[k] > 0:
+            if seg_ms[k] > 0.01:            # an idle segment (no adapter pass, emission fused or off) is two events apart
                 a = seg_bytes[k] / (seg_ms[k] / 1e3) / 1e9
                 kernels[k] = {"ms": seg_ms[k], "algorithmic_bytes": seg_bytes[k], "achieved": a, "frac": a / peak,
                               "dram_bytes": traffic.get(k), "traffic_ratio": (traffic[k] / seg_bytes[k]) if k in traffic and seg_bytes[k] else None}
