@@ -313,8 +313,17 @@ __global__ void __launch_bounds__(256) k_build_records(const LineIndex li, uint3
     __shared__ uint32_t s_seg;
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (threadIdx.x == 0) {
-        const uint32_t r0 = blockIdx.x * blockDim.x;
-        s_seg = li.find(r0 ? 4 * r0 - 1 : 0);          // the CTA's 1024 lines sit in this segment or the next few
+        // the CTA's 1024 lines sit in this segment or the next few.  The segments hold (nearly) equal numbers of bytes, so
+        // the line's share of all lines is a good first guess; a short walk fixes it, the binary search (a dozen dependent
+        // L2 round trips in front of every CTA: it was what this kernel spent its time on) is only the fallback
+        const uint32_t r0 = blockIdx.x * blockDim.x, g = r0 ? 4 * r0 - 1 : 0, n_lines = 4 * n_rec;
+        uint32_t s = (uint32_t)(((unsigned long long)g * li.n_seg) / n_lines);
+        if (s >= li.n_seg) s = li.n_seg - 1;
+        int steps = 0;
+        while (steps < 8 && s > 0 && li.seg_base[s] > g) { --s; ++steps; }
+        while (steps < 8 && s + 1 < li.n_seg && li.seg_base[s + 1] <= g) { ++s; ++steps; }
+        if (steps >= 8) s = li.find(g);
+        s_seg = s;
     }
     __syncthreads();
     uint32_t len = 0;
