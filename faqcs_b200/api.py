@@ -99,6 +99,11 @@ PIECE_DTYPE = np.dtype([("offset", "<u8"), ("length", "<u4"), ("source", "<u4")]
 U64P = C.POINTER(C.c_uint64)
 
 
+class CKmerView(C.Structure):
+    _fields_ = [("n_rarefaction", C.c_uint32), ("rarefaction", C.c_void_p),
+                ("n_frequency", C.c_uint64), ("frequency", C.POINTER(C.c_uint64))]
+
+
 class CStatsView(C.Structure):
     _fields_ = [
         ("filter_stats", C.c_uint64 * NUM_STAT), ("n_adapters", C.c_uint32),
@@ -281,6 +286,9 @@ class Engine:
         getattr(L, p + "process_host").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                    C.c_uint64, C.c_int, C.POINTER(CBatchOut)]
         getattr(L, p + "stats").argtypes = [C.c_void_p, C.POINTER(CStatsView)]
+        getattr(L, p + "kmer_enable").argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32]
+        getattr(L, p + "kmer_end_pass").argtypes = [C.c_void_p]
+        getattr(L, p + "kmer_results").argtypes = [C.c_void_p, C.POINTER(CKmerView)]
         if p == "fq_":
             L.fq_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                             C.c_uint64, C.c_int, C.c_int, C.POINTER(CBatchOut)]
@@ -343,6 +351,27 @@ class Engine:
         """Pieces mode (fq_set_output_pieces): streams come back as lists of pieces of the caller's input + literal bytes."""
         self._check(self.lib.fq_set_output_pieces(self.ctx, int(enable)))
         self._pieces = bool(enable)
+
+    def kmer_enable(self, k: int = 31, split_size: int = 1000000, num_subsample: int = 10):
+        """--kmer_rarefaction: k = Options::kmer (-m), Options::split_size, Options::num_subsample (--subset, already
+        doubled where options.cpp:506-523 doubles it).  Batches must then be multiples of 32768 records."""
+        self._check(self._f("kmer_enable")(self.ctx, int(k), int(split_size), int(num_subsample)))
+
+    def kmer_end_pass(self):
+        """End of one input (the paired files, then the unpaired file): FaQCs.cpp:518-537 / 737-756."""
+        self._check(self._f("kmer_end_pass")(self.ctx))
+
+    def kmer_results(self):
+        """(rarefaction [n,3] uint64 = num_seq, distinct, total; frequency [m,2] uint64 = count, k-mers), plot.cpp:683-733."""
+        v = CKmerView()
+        self._check(self._f("kmer_results")(self.ctx, C.byref(v)))
+        rare = np.zeros((v.n_rarefaction, 3), np.uint64)
+        if v.n_rarefaction:
+            rare[:] = np.ctypeslib.as_array(C.cast(v.rarefaction, C.POINTER(C.c_uint64)), (v.n_rarefaction, 3))
+        freq = np.zeros((v.n_frequency, 2), np.uint64)
+        if v.n_frequency:
+            freq[:] = np.ctypeslib.as_array(v.frequency, (v.n_frequency, 2))
+        return rare, freq
 
     def set_quality(self, quality: int):
         """Options::quality for the following batches (the reference's NextSeq adjustment, FaQCs.cpp:272-277)."""

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -20,6 +21,7 @@
 #include "fq_common.cuh"
 #include "fq_emit.cuh"
 #include "fq_frame.cuh"
+#include "fq_kmer.cuh"
 #include "fq_trim.cuh"
 
 using namespace fq;
@@ -110,6 +112,23 @@ struct fq_ctx {
     bool debug_results = false;
     bool check_pair_ids = true;
     bool frame_exact[2] = {false, false};      // this mate's input is not plain LF text: skip the fast framing instance
+
+    // k-mer rarefaction (fq_kmer_*): Options::kmer_rarefaction / kmer / split_size / num_subsample, PlotInfo::kmer_*
+    struct Kmer {
+        bool enabled = false, collecting = false;
+        uint32_t k = 31, num_subsample = 0;
+        uint64_t split_size = 1;
+        uint64_t total_reads = 0;                  // TOTAL_NUMBER
+        std::vector<fq_rarefaction> samples;       // finished points
+        std::map<uint64_t, uint64_t> freq;         // kmer_frequency_histogram
+        // current pass
+        uint32_t pass_calls = 0;                   // trim() calls of this pass so far
+        uint32_t pass_counted = 0;                 // calls [0, pass_counted) fed the table
+        std::vector<std::pair<uint32_t, uint64_t>> pass_points;   // (call, TOTAL_NUMBER): distinct / total filled in at the end of the pass
+        unsigned long long cap = 0, occupied_bound = 0;
+        DevBuf d_keys, d_count, d_first, d_call_total, d_call_distinct, d_small, d_big, d_scalars;
+        std::vector<uint64_t> flat;                // fq_kmer_view::frequency
+    } kmer;
 
     // host-side stats views handed out by fq_stats
     std::vector<uint64_t> v_adapter_reads, v_adapter_bases, v_pre_q, v_post_q, v_pre_b, v_post_b, v_hist[4], v_pre_comp,
@@ -334,6 +353,94 @@ fq_status map_device_error(fq_ctx *ctx, const BatchInfo &hi)
     return fail(ctx, FQ_ERR_STATE, "unknown device error");
 }
 
+// ---- k-mer rarefaction: host side of fq_kmer.cuh ---------------------------------------------------------
+KmerTable kmer_table_of(fq_ctx::Kmer &K)
+{
+    return KmerTable{K.d_keys.as<unsigned long long>(), K.d_count.as<uint32_t>(), K.d_first.as<uint32_t>(), K.cap - 1};
+}
+
+// (Re)allocate the table for at least `slots` slots (a power of two), keeping its entries.
+fq_status kmer_resize(fq_ctx *ctx, unsigned long long slots)
+{
+    fq_ctx::Kmer &K = ctx->kmer;
+    unsigned long long cap = 1ull << 20;
+    while (cap < slots) cap <<= 1;
+    if (cap <= K.cap) return FQ_OK;
+    DevBuf nk, nc, nf;
+    CK(nk.ensure(cap * 8));
+    CK(nc.ensure(cap * 4));
+    CK(nf.ensure(cap * 4));
+    KmerTable to{nk.as<unsigned long long>(), nc.as<uint32_t>(), nf.as<uint32_t>(), cap - 1};
+    k_kmer_clear<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(to);
+    if (K.cap) k_kmer_rehash<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(kmer_table_of(K), to);
+    ctx->launches += K.cap ? 2 : 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    K.d_keys.release(); K.d_count.release(); K.d_first.release();
+    K.d_keys = nk; K.d_count = nc; K.d_first = nf;
+    K.cap = cap;
+    return FQ_OK;
+}
+
+// One batch: which trim() calls of the reference it spans, which of them still feed the table, where curve points fall
+// (trim.cpp:157-185), then the counting kernel.
+fq_status kmer_batch(fq_ctx *ctx, const uint8_t *d_r1, const uint8_t *d_r2, uint32_t n, int n_mates, uint32_t max_len, uint64_t first_record_index, int is_final, bool trimmed)
+{
+    fq_ctx::Kmer &K = ctx->kmer;
+    if ((first_record_index % FQ_REF_BATCH) != 0 || (!is_final && (n % FQ_REF_BATCH) != 0))
+        return fail(ctx, FQ_ERR_ARG, "k-mer rarefaction needs batches that start on a 32768-record boundary and hold a multiple of 32768 records");
+    const uint32_t first_call = K.pass_calls;
+    uint64_t counted_reads = 0;
+    for (uint32_t b0 = 0; b0 < n; b0 += FQ_REF_BATCH) {
+        const uint32_t reads = std::min<uint32_t>(FQ_REF_BATCH, n - b0);
+        for (int m = 0; m < n_mates; ++m) {
+            const uint32_t call = K.pass_calls++;
+            if (K.collecting) {                              // this call's reads go through update_kmer (trim.cpp:260-262)
+                if (call >= kKmerMaxCalls) return fail(ctx, FQ_ERR_ARG, "k-mer rarefaction: more than 65536 trim() batches while the curve is collected");
+                K.pass_counted = call + 1;
+                counted_reads += reads;
+            }
+            K.total_reads += reads;
+            if (K.collecting) {                              // end of trim(): trim.cpp:157-185
+                const uint64_t index = K.total_reads / K.split_size;
+                const uint64_t n_points = K.samples.size() + K.pass_points.size();
+                if (index > n_points && n_points < K.num_subsample) K.pass_points.push_back(std::make_pair(call, K.total_reads));
+                if (n_points >= K.num_subsample) K.collecting = false;
+            }
+        }
+    }
+    if (K.pass_counted <= first_call || counted_reads == 0) return FQ_OK;
+    // room for every k-mer this batch can add (load factor <= 1/2); the bound on the occupied slots is made exact when it matters
+    const unsigned long long per_read = max_len >= K.k ? (unsigned long long)(max_len - K.k + 1) : 0ull;
+    unsigned long long need = K.occupied_bound + counted_reads * per_read;
+    if (2 * need > K.cap && K.cap) {
+        CK(cudaMemsetAsync(K.d_scalars.p, 0, 16, ctx->stream));
+        k_kmer_count<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(kmer_table_of(K), K.d_scalars.as<unsigned long long>());
+        ctx->launches++;
+        unsigned long long occ = 0;
+        CK(cudaMemcpyAsync(&occ, K.d_scalars.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        K.occupied_bound = occ;
+        need = occ + counted_reads * per_read;
+    }
+    if (2 * need > K.cap) {
+        fq_status st = kmer_resize(ctx, 2 * need);
+        if (st != FQ_OK) return st;
+    }
+    K.occupied_bound = need;
+    KmerArgs ka{};
+    ka.raw[0] = d_r1; ka.raw[1] = d_r2;
+    ka.rec[0] = ctx->d_rec[0].as<Rec>(); ka.rec[1] = ctx->d_rec[1].as<Rec>();
+    ka.res[0] = trimmed ? ctx->d_res[0].as<uint2>() : nullptr;
+    ka.res[1] = trimmed ? ctx->d_res[1].as<uint2>() : nullptr;
+    ka.n_rec = n; ka.n_mates = (uint32_t)n_mates; ka.k = K.k;
+    ka.first_call = first_call; ka.stop_call = K.pass_counted;
+    ka.T = kmer_table_of(K);
+    ka.call_total = K.d_call_total.as<unsigned long long>();
+    k_kmer<<<(n * n_mates + 255) / 256, 256, 0, ctx->stream>>>(ka);
+    ctx->launches++;
+    return FQ_OK;
+}
+
 fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint8_t *d_r2, size_t n2, bool paired,
                          uint64_t first_record_index, int is_final, int copy_out, fq_batch_out *out)
 {
@@ -504,6 +611,12 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    // ---- k-mer rarefaction: raw reads under --qc_only (trim.cpp:260-262), trimmed survivors otherwise (trim.cpp:545-547)
+    if (ctx->kmer.enabled) {
+        st = kmer_batch(ctx, d_r1, d_r2, n, n_mates, max_len, first_record_index, is_final, !o.qc_only);
+        if (st != FQ_OK) return st;
+    }
 
     // ---- route / scan / emit
     EmitArgs ea{};
@@ -702,6 +815,8 @@ void fq_destroy(fq_ctx *ctx)
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     ctx->d_tile.release(); ctx->d_info.release(); ctx->d_stats.release(); ctx->d_rows.release();
     ctx->d_adp_codes.release(); ctx->d_adp_off.release(); ctx->d_adp_or.release();
+    for (DevBuf *b : {&ctx->kmer.d_keys, &ctx->kmer.d_count, &ctx->kmer.d_first, &ctx->kmer.d_call_total, &ctx->kmer.d_call_distinct, &ctx->kmer.d_small,
+                      &ctx->kmer.d_big, &ctx->kmer.d_scalars}) b->release();
     ctx->h_stats.release();
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -927,6 +1042,91 @@ fq_status fq_stats_device_buffer(fq_ctx *ctx, void **d_u64, size_t *n_u64, void 
     if (d_u64) *d_u64 = ctx->d_stats.p;
     if (n_u64) *n_u64 = ctx->L.total;
     if (d_rows_u32x4) *d_rows_u32x4 = ctx->d_rows.p;
+    return FQ_OK;
+}
+
+fq_status fq_kmer_enable(fq_ctx *ctx, uint32_t k, uint64_t split_size, uint32_t num_subsample)
+{
+    if (!ctx || k < 2 || k > 31 || split_size == 0 || num_subsample == 0) return FQ_ERR_ARG;      // options.cpp:537-568
+    CK(cudaSetDevice(ctx->device));
+    fq_ctx::Kmer &K = ctx->kmer;
+    K.enabled = K.collecting = true;
+    K.k = k; K.split_size = split_size; K.num_subsample = num_subsample;
+    CK(K.d_call_total.ensure((size_t)kKmerMaxCalls * 8));
+    CK(K.d_call_distinct.ensure((size_t)kKmerMaxCalls * 8));
+    CK(K.d_small.ensure((size_t)kKmerSmallCounts * 8));
+    CK(K.d_big.ensure((size_t)(1u << 20) * 4));
+    CK(K.d_scalars.ensure(64));
+    CK(cudaMemset(K.d_call_total.p, 0, (size_t)kKmerMaxCalls * 8));
+    return kmer_resize(ctx, 1ull << 24);
+}
+
+fq_status fq_kmer_end_pass(fq_ctx *ctx)
+{
+    if (!ctx) return FQ_ERR_ARG;
+    fq_ctx::Kmer &K = ctx->kmer;
+    if (!K.enabled) return FQ_OK;
+    CK(cudaSetDevice(ctx->device));
+    // the pass's table -> distinct k-mers per first call, histogram of counts
+    const uint32_t big_cap = 1u << 20;
+    CK(cudaMemsetAsync(K.d_call_distinct.p, 0, (size_t)kKmerMaxCalls * 8, ctx->stream));
+    CK(cudaMemsetAsync(K.d_small.p, 0, (size_t)kKmerSmallCounts * 8, ctx->stream));
+    CK(cudaMemsetAsync(K.d_scalars.p, 0, 64, ctx->stream));
+    k_kmer_summarize<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(kmer_table_of(K), K.d_call_distinct.as<unsigned long long>(), K.d_small.as<unsigned long long>(),
+                                                              K.d_big.as<uint32_t>(), big_cap, reinterpret_cast<uint32_t *>(K.d_scalars.as<uint8_t>() + 16),
+                                                              K.d_scalars.as<unsigned long long>());
+    ctx->launches++;
+    const uint32_t nc = std::max(K.pass_calls, 1u);
+    std::vector<unsigned long long> call_total(nc), call_distinct(nc), small(kKmerSmallCounts);
+    unsigned long long n_distinct = 0;
+    uint32_t n_big = 0;
+    CK(cudaMemcpyAsync(call_total.data(), K.d_call_total.p, (size_t)std::min(nc, kKmerMaxCalls) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(call_distinct.data(), K.d_call_distinct.p, (size_t)std::min(nc, kKmerMaxCalls) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(small.data(), K.d_small.p, (size_t)kKmerSmallCounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&n_distinct, K.d_scalars.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&n_big, K.d_scalars.as<uint8_t>() + 16, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_big > big_cap) return fail(ctx, FQ_ERR_ARG, "k-mer rarefaction: more than 2^20 k-mers with counts above 65535");
+    std::vector<uint32_t> big(n_big);
+    if (n_big) CK(cudaMemcpy(big.data(), K.d_big.p, (size_t)n_big * 4, cudaMemcpyDeviceToHost));
+    // points of the curve taken in this pass (trim.cpp:165-178): table size and instances after their call
+    unsigned long long run_d = 0, run_t = 0, all_t = 0;
+    size_t next = 0;
+    for (uint32_t c = 0; c < std::min(nc, kKmerMaxCalls); ++c) {
+        run_d += call_distinct[c];
+        run_t += call_total[c];
+        while (next < K.pass_points.size() && K.pass_points[next].first == c) {
+            K.samples.push_back(fq_rarefaction{K.pass_points[next].second, run_d, run_t});
+            ++next;
+        }
+    }
+    all_t = run_t;
+    // FaQCs.cpp:518-537 / 737-756: frequency histogram of the table, and one point if the curve is still empty
+    for (uint32_t c = 1; c < kKmerSmallCounts; ++c)
+        if (small[c]) K.freq[c] += small[c];
+    for (uint32_t c : big) K.freq[c] += 1;
+    if (K.collecting && K.samples.empty()) K.samples.push_back(fq_rarefaction{K.total_reads, n_distinct, all_t});
+    // a new table for the next pass
+    K.pass_calls = K.pass_counted = 0;
+    K.pass_points.clear();
+    K.occupied_bound = 0;
+    k_kmer_clear<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(kmer_table_of(K));
+    ctx->launches++;
+    CK(cudaMemsetAsync(K.d_call_total.p, 0, (size_t)kKmerMaxCalls * 8, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FQ_OK;
+}
+
+fq_status fq_kmer_results(fq_ctx *ctx, fq_kmer_view *view)
+{
+    if (!ctx || !view) return FQ_ERR_ARG;
+    fq_ctx::Kmer &K = ctx->kmer;
+    K.flat.clear();
+    for (const auto &kv : K.freq) { K.flat.push_back(kv.first); K.flat.push_back(kv.second); }
+    view->n_rarefaction = (uint32_t)K.samples.size();
+    view->rarefaction = K.samples.data();
+    view->n_frequency = K.flat.size() / 2;
+    view->frequency = K.flat.data();
     return FQ_OK;
 }
 

@@ -2,8 +2,8 @@
 // QC.stats.txt layout, running the trim / filter / statistics path on the GPU through the C ABI
 // (include/faqcs_b200.h).  Host side only: option parsing (options.cpp:72-774), gz/plain input
 // (zlib), batching at record boundaries, ordered writers, write_stats (FaQCs.cpp:759-1034) and
-// the --debug data files of plot() (plot.cpp:540-681).  The R/PDF report and k-mer rarefaction
-// are out of scope.
+// the --debug data files of plot() (plot.cpp:540-733), the k-mer rarefaction files included.  The R/PDF
+// report is out of scope.
 //
 //   faqcs_b200 -1 r1.fq -2 r2.fq -d outdir [FaQCs flags]        extra: --device N | --devices 0,1,.., --batch_mb N
 #include <fcntl.h>
@@ -134,7 +134,7 @@ static void usage()
     cerr << "Q_Format:\n\t--ascii\t\t\tEncoding type: 33 or 64 or autoCheck (default)\n\t--out_ascii\t\tOutput encoding. (default: 33)\n";
     cerr << "Output:\n\t--prefix\t\t<TEXT> Output file prefix. (default: QC)\n\t--stats\t\t\t<File> Statistical numbers output file (default: prefix.stats.txt)\n\t-d\t\t\t<PATH> Output directory.\n";
     cerr << "Options:\n\t-t\t\t\t<INT > # of CPUs the reference would run with (only reproduces its -t dependent adapter threshold)\n";
-    cerr << "\t--split_size\t\t<INT> (kept for compatibility)\n\t--qc_only\t\t<bool> no Filters, no Trimming, report numbers.\n\t--discard\t\t<bool> Output discarded reads\n";
+    cerr << "\t--split_size\t\t<INT> reads per point of the k-mer rarefaction curve (default: 1000000)\n\t--kmer_rarefaction\t<bool> count canonical 31-mers; prefix.Kmercount.txt / prefix.kmerH.txt with --debug\n\t--subset\t\t<INT> points of the curve = 2 x this (default: 10)\n\t--qc_only\t\t<bool> no Filters, no Trimming, report numbers.\n\t--discard\t\t<bool> Output discarded reads\n";
     cerr << "\t--substitute\t\t<bool> (not implemented, as in FaQCs)\n\t--trim_only\t\t<bool> No quality report. Output trimmed reads only.\n\t--replace_to_N_q\t<INT> Replace base G to N when below this quality score (default:0, off)\n";
     cerr << "\t--5trim_off\t\t<bool> Turn off trimming from 5'end.\n\t--debug\t\t\t<bool> Keep intermediate files\n\t--version\t\t<bool> Print the version and exit\n";
     cerr << "GPU:\n\t--device\t\t<INT> CUDA device (default 0)\n\t--devices\t\t<INT,INT,..> several CUDA devices: batches are dealt out in order, statistics merged with one NCCL all-reduce\n"
@@ -270,7 +270,17 @@ static void parse_options(int argc, char *argv[], Cli &o)
         o.print_usage = true;
         return;
     }
-    if (o.kmer_rarefaction) cerr << "**Warning** --kmer_rarefaction is outside the scope of faqcs_b200 and is ignored" << endl;
+    if (o.split_size == 0) {
+        cerr << "Please specify a split_size (--split_size) value greater than 0" << endl;
+        o.print_usage = true;
+        return;
+    }
+    if (o.num_subsample == 0) {
+        cerr << "Please specify a subset (--subset) value greater than 0" << endl;
+        o.print_usage = true;
+        return;
+    }
+    o.num_subsample *= 2;      // options.cpp:519-523: doubled on every command line that gets this far, paired input or not
     if (o.replace_N) cerr << "**Warning** \"-substitue\" is not currently implemented" << endl;
     if (o.filter_adapter) {                               // built-in adapters, options.cpp:576-618 (sequence data)
         static const char *builtin[][2] = {
@@ -594,7 +604,8 @@ static void process(Run &R, bool paired)
     for (int k = 0; k < 2; ++k)
         for (int m = 0; m < n_mates; ++m)
             if (!(buf[k][m] = (uint8_t *)fq_host_alloc(cap))) throw "unable to allocate pinned host memory";
-    const bool emulate = o.filter_adapter || o.filter_phiX;             // Q3: keep batches on 32768-record boundaries
+    // Q3 and the k-mer rarefaction curve (points are taken where trim() calls end): keep batches on 32768-record boundaries
+    const bool emulate = o.filter_adapter || o.filter_phiX || o.kmer_rarefaction;
     struct Filled { size_t n = 0, lines = 0; } filled[2];
     double t_read = 0, t_gpu = 0, t_write_wait = 0, t_cut = 0;
     {
@@ -643,6 +654,7 @@ static void process(Run &R, bool paired)
                     }
                     throw "record larger than the batch buffer: raise --batch_mb";
                 }
+                if (o.kmer_rarefaction && nrec % FQ_REF_BATCH) throw "--kmer_rarefaction needs batches of at least 32768 records: raise --batch_mb";
                 use1 = offset_after_line(buf[slot][0], n1, filled[0].lines, 4 * nrec);
                 if (paired) use2 = offset_after_line(buf[slot][1], n2, filled[1].lines, 4 * nrec);
                 // the tails open the next batch; its buffers are free (their batch has been run)
@@ -875,6 +887,27 @@ static void remove_file(const string &fn)      // FaQCs.cpp:1046-1053
     }
 }
 
+// plot.cpp:81-91, writers :683-733: prefix.kmerH.txt ("count number", ascending count) and prefix.Kmercount.txt (reads since
+// the previous point, distinct k-mers, k-mer instances), only when some k-mer was counted.
+static void write_kmer_files(const fq_kmer_view &kv, const Cli &o)
+{
+    if (kv.n_frequency == 0) return;
+    const string base = o.output_dir + "/" + o.prefix;
+    {
+        ofstream fout((base + ".kmerH.txt").c_str());
+        if (!fout) cerr << "Warning: Unable to write kmer histogram file: " << base << ".kmerH.txt" << endl;
+        else
+            for (uint64_t i = 0; i < kv.n_frequency; ++i) fout << kv.frequency[2 * i] << ' ' << kv.frequency[2 * i + 1] << '\n';
+    }
+    ofstream fout((base + ".Kmercount.txt").c_str());
+    if (!fout) { cerr << "Warning: Unable to write kmer rarefaction file: " << base << ".Kmercount.txt" << endl; return; }
+    uint64_t last = 0;
+    for (uint32_t i = 0; i < kv.n_rarefaction; ++i) {
+        fout << kv.rarefaction[i].num_seq - last << '\t' << kv.rarefaction[i].distinct_kmer << '\t' << kv.rarefaction[i].total_kmer << '\n';
+        last = kv.rarefaction[i].num_seq;
+    }
+}
+
 int main(int argc, char *argv[])
 {
     Cli o;
@@ -903,16 +936,25 @@ int main(int argc, char *argv[])
         const bool timing = getenv("FAQCS_B200_TIMING") != nullptr;
         const double t_start = now_s();
         if (o.devices.empty()) o.devices.push_back(o.device);
+        if (o.kmer_rarefaction && o.devices.size() > 1) {
+            cerr << "**Warning** --kmer_rarefaction keeps one k-mer table: running on device " << o.devices[0] << " only" << endl;
+            o.devices.resize(1);
+        }
         if (fq_create(&f, o.devices[0], &ctx) != FQ_OK) throw string(fq_last_error(nullptr));
+        if (o.kmer_rarefaction && fq_kmer_enable(ctx, o.kmer, o.split_size, o.num_subsample) != FQ_OK) throw string(fq_last_error(ctx));
         const double t_created = now_s();
         Run R(o);
         R.ctx = ctx;
         R.ctxs.push_back(ctx);
         R.fopt = f;
-        if (o.has_paired()) process(R, true);
+        if (o.has_paired()) {
+            process(R, true);
+            R.check(fq_kmer_end_pass(ctx));        // FaQCs.cpp:518-537
+        }
         if (o.has_unpaired()) {
             R.first_batch = true;      // offset detection only if still unknown; the NextSeq check runs per input (FaQCs.cpp:586,673-683)
             process(R, false);
+            R.check(fq_kmer_end_pass(ctx));        // FaQCs.cpp:737-756
         }
         const double t_processed = now_s();
         if (R.ctxs.size() > 1) {
@@ -926,7 +968,12 @@ int main(int argc, char *argv[])
         fq_stats_view v;
         if (fq_stats(ctx, &v) != FQ_OK) throw string(fq_last_error(ctx));
         write_stats(v, o);
-        if (!o.trim_only && o.debug) write_debug_files(v, o);    // the reference deletes these unless --debug (plot.cpp:517-537)
+        if (!o.trim_only && o.debug) {                           // the reference deletes these unless --debug (plot.cpp:517-537)
+            write_debug_files(v, o);
+            fq_kmer_view kv;
+            if (fq_kmer_results(ctx, &kv) != FQ_OK) throw string(fq_last_error(ctx));
+            write_kmer_files(kv, o);
+        }
         const double t_stats = now_s();
         for (size_t k = 1; k < R.ctxs.size(); ++k) fq_destroy(R.ctxs[k]);
         fq_destroy(ctx);

@@ -206,6 +206,30 @@ def c5(n_reads: int, seed: int = SEEDS["C5"], start: int = 0) -> Workload:
                     ["--mode", "HARD", "-q", "20", "--avg_q", "25", "--replace_to_N_q", "10", "--discard"])
 
 
+def shotgun(n_pairs: int, genome_len: int = 60000, seed: int = 77, start: int = 0, paired: bool = True, L: int = 150) -> Workload:
+    """Reads drawn from a small random genome (both strands, 0.5 % substitutions, a few N): the workload of
+    --kmer_rarefaction, where k-mers must repeat for the curve and the frequency histogram to mean anything."""
+    g = _BASES[np.random.default_rng(seed).integers(0, 4, size=genome_len + 2 * L)]
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[list(b"ACGTN")] = list(b"TGCAN")
+    rng = np.random.default_rng(seed + 1 + start)
+    mates = []
+    pos = rng.integers(0, genome_len, size=n_pairs)
+    for mate in (1, 2) if paired else (1,):
+        off = pos if mate == 1 else (pos + rng.integers(0, L, size=n_pairs)) % genome_len
+        s = g[off[:, None] + np.arange(L)[None, :]]
+        rev = rng.random(n_pairs) < 0.5
+        s = np.where(rev[:, None], comp[s][:, ::-1], s)
+        err = rng.random((n_pairs, L)) < 0.005
+        s = np.where(err, _BASES[rng.integers(0, 4, size=(n_pairs, L))], s)
+        s = np.where(rng.random((n_pairs, L)) < 0.001, np.uint8(ord("N")), s)
+        lower = rng.random(n_pairs) < 0.01                 # soft-masked reads: update_kmer folds case (trim.cpp:903-918)
+        s = np.where(lower[:, None], s | 0x20, s)
+        q = _qualities(rng, n_pairs, L, 30, 40, 0.12, 3.0, 2, 41, 0.10, 59)
+        mates.append(_assemble(_headers(n_pairs, "SG", mate, start), s, q + 33))
+    return Workload("shotgun", mates[0], mates[1] if paired else None, ["--kmer_rarefaction"])
+
+
 def fastq_bytes(records: List[Tuple[str, str, str]], eol: str = "\n") -> bytes:
     """Hand-written records -> FASTQ bytes (micro-cases)."""
     return "".join(f"{h}{eol}{s}{eol}+{eol}{q}{eol}" for h, s, q in records).encode()

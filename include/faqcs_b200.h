@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FQ_ABI_VERSION 3
+#define FQ_ABI_VERSION 4
 
 /* ---- FilterStat (FaQCs.h:46-75), same order, same meaning ---------------- */
 enum fq_filter_stat {
@@ -325,6 +325,34 @@ void      fq_comm_destroy(fq_comm *comm);
 fq_status fq_allreduce_stats(fq_ctx *const *ctx, int n, fq_comm *const *comm);
 /* Device milliseconds of the last fq_allreduce_stats on this context (CUDA events around the three collectives). */
 float     fq_last_allreduce_ms(const fq_ctx *ctx);
+
+/*
+ * k-mer rarefaction (--kmer_rarefaction with --qc_only).  Replaces update_kmer (trim.cpp:887-931, called from
+ * trim_read, trim.cpp:260-262), the sampling block at the end of trim() (trim.cpp:157-185) and the end-of-pass code of
+ * process_paired / process_unpaired (FaQCs.cpp:518-537, 737-756).  The canonical k-mers of the raw reads go to a hash table
+ * in device memory while the curve is being collected (one table per pass over an input, as in the reference); the points
+ * of the curve are taken where the reference takes them -- at the end of the trim() call (32768 reads of one mate) whose
+ * running read count crossed another multiple of split_size -- so batches must start on 32768-record boundaries and, unless
+ * final, hold a multiple of 32768 records.  Single context only (the table does not shard).
+ *   fq_kmer_enable    once, before the first batch: k (Options::kmer, 2..31), Options::split_size, Options::num_subsample
+ *                     (already doubled where the reference doubles it, options.cpp:506-523)
+ *   fq_kmer_end_pass  after the last batch of an input (paired files, then the unpaired file)
+ *   fq_kmer_results   PlotInfo::kmer_rarefaction and PlotInfo::kmer_frequency_histogram (what plot.cpp:683-733 prints)
+ */
+typedef struct fq_rarefaction {
+    uint64_t num_seq;          /* TOTAL_NUMBER when the point was taken */
+    uint64_t distinct_kmer;
+    uint64_t total_kmer;
+} fq_rarefaction;
+typedef struct fq_kmer_view {
+    uint32_t n_rarefaction;
+    const fq_rarefaction *rarefaction;
+    uint64_t n_frequency;              /* pairs in `frequency` */
+    const uint64_t *frequency;         /* {count, number of k-mers with that count}, ascending count */
+} fq_kmer_view;
+fq_status fq_kmer_enable(fq_ctx *ctx, uint32_t k, uint64_t split_size, uint32_t num_subsample);
+fq_status fq_kmer_end_pass(fq_ctx *ctx);
+fq_status fq_kmer_results(fq_ctx *ctx, fq_kmer_view *view);
 
 /* Zero the accumulators (new run on the same context). */
 fq_status fq_reset_stats(fq_ctx *ctx);

@@ -23,7 +23,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -275,6 +277,18 @@ struct fqo_ctx {
     // batch outputs (owned here)
     std::string out[FQ_NUM_STREAM];
     std::vector<fq_read_result> results[2];
+    // k-mer rarefaction (Options::kmer_rarefaction / kmer / split_size / num_subsample, PlotInfo::kmer_*)
+    struct Kmer {
+        bool enabled = false, collecting = false;         // collecting = m_opt.kmer_rarefaction (cleared at trim.cpp:180-184)
+        uint32_t k = 31;
+        uint64_t split_size = 1000000, num_subsample = 10;
+        uint64_t total_number = 0;                        // FilterStat::TOTAL_NUMBER as trim() sees it after each call
+        std::unordered_map<uint64_t, uint64_t> table;     // one per pass (FaQCs.cpp:235, 588)
+        uint64_t table_total = 0;                         // sum of the table's counts
+        std::vector<fq_rarefaction> samples;              // PlotInfo::kmer_rarefaction
+        std::map<uint64_t, uint64_t> freq;                // PlotInfo::kmer_frequency_histogram
+        std::vector<uint64_t> flat;
+    } kmer;
 };
 
 namespace {
@@ -699,6 +713,56 @@ void trim_mate(fqo_ctx &c, std::vector<Read> &reads, uint64_t first_record_index
     for (size_t i = 0; i < n; ++i) trim_read(c, reads[i], results ? &(*results)[i] : nullptr);
 }
 
+// trim.cpp:887-931 update_kmer: canonical k-mers of one sequence, two bits per base (FaQCs.h BASE_A=0, T=1, C=2, G=3 --
+// pinned by the reference's .kmerH.txt / .Kmercount.txt only through the min() of the two strands)
+void update_kmer(fqo_ctx::Kmer &K, const std::string &seq)
+{
+    const uint64_t comp_shift = 2 * (K.k - 1), mask = (1ull << (2 * K.k)) - 1;
+    uint64_t w = 0, comp = 0;
+    uint32_t word_len = 0;
+    for (char ch : seq) {
+        ++word_len;
+        switch (ch) {
+            case 'A': case 'a': w = (w << 2) | 0; comp = (comp >> 2) | (1ull << comp_shift); break;
+            case 'T': case 't': w = (w << 2) | 1; comp = (comp >> 2) | (0ull << comp_shift); break;
+            case 'G': case 'g': w = (w << 2) | 3; comp = (comp >> 2) | (2ull << comp_shift); break;
+            case 'C': case 'c': w = (w << 2) | 2; comp = (comp >> 2) | (3ull << comp_shift); break;
+            default: word_len = 0; break;
+        }
+        if (word_len >= K.k) {
+            ++K.table[std::min(w & mask, comp & mask)];
+            ++K.table_total;
+        }
+    }
+}
+
+// The k-mer side of the trim() calls a batch stands for: FaQCs.cpp reads 32768 records, calls trim() on mate 1, then on
+// mate 2 (FaQCs.cpp:287-291, 424-428, 628-629, 692-693).  `raw` = the reads as parsed, `done` = after trim_read.
+void kmer_calls(fqo_ctx &c, const std::vector<Read> *raw, const std::vector<Read> *done, int n_mates)
+{
+    fqo_ctx::Kmer &K = c.kmer;
+    const size_t n = raw[0].size();
+    for (size_t b0 = 0; b0 < n; b0 += FQ_REF_BATCH) {
+        const size_t b1 = std::min<size_t>(n, b0 + FQ_REF_BATCH);
+        for (int m = 0; m < n_mates; ++m) {
+            if (K.collecting) {
+                for (size_t i = b0; i < b1; ++i) {
+                    if (c.opt.qc_only) update_kmer(K, raw[m][i].seq);                  // trim.cpp:260-262 (before any trimming)
+                    else if (!done[m][i].seq.empty()) update_kmer(K, done[m][i].seq);  // trim.cpp:527, 545-547 (survivors, trimmed)
+                }
+            }
+            K.total_number += b1 - b0;
+            if (K.collecting) {                                                        // trim.cpp:157-185
+                const uint64_t index = K.total_number / K.split_size;
+                const uint64_t num_rarefaction = K.samples.size();
+                if (index > num_rarefaction && num_rarefaction < K.num_subsample)
+                    K.samples.push_back(fq_rarefaction{K.total_number, (uint64_t)K.table.size(), K.table_total});
+                if (num_rarefaction >= K.num_subsample) K.collecting = false;
+            }
+        }
+    }
+}
+
 void write_read(std::string &out, const std::string &def, const std::string &seq, const std::string &qual)
 {   // fastq.cpp:127-138
     out += def; out += '\n'; out += seq; out += "\n+\n"; out += qual; out += '\n';
@@ -813,9 +877,14 @@ fq_status fqo_process_host(fqo_ctx *ctx, const uint8_t *r1, size_t n1, const uin
                     throw OracleError{FQ_ERR_FORMAT, "FaQCs.cpp:trim: I/O error"};   // FaQCs.cpp:383-389
         }
         const fq_options &o = ctx->opt;
-        if (o.discard_output) { raw1 = b1; raw2 = b2; }       // FaQCs.cpp:279-285
+        if (o.discard_output || ctx->kmer.enabled) { raw1 = b1; raw2 = b2; }       // FaQCs.cpp:279-285
         trim_mate(*ctx, b1, first_record_index, ctx->debug_results ? &ctx->results[0] : nullptr);
         if (paired) trim_mate(*ctx, b2, first_record_index, ctx->debug_results ? &ctx->results[1] : nullptr);
+        if (ctx->kmer.enabled) {
+            if (first_record_index % FQ_REF_BATCH) throw OracleError{FQ_ERR_ARG, "k-mer rarefaction: batch does not start on a 32768-record boundary"};
+            const std::vector<Read> raws[2] = {raw1, raw2}, dones[2] = {b1, b2};
+            kmer_calls(*ctx, raws, dones, paired ? 2 : 1);
+        }
         const size_t n = b1.size();
         out->n_records = n;
         for (size_t i = 0; i < n; ++i) {
@@ -860,6 +929,39 @@ fq_status fqo_process_host(fqo_ctx *ctx, const uint8_t *r1, size_t n1, const uin
         out->results[0] = ctx->results[0].data();
         out->results[1] = r2 ? ctx->results[1].data() : nullptr;
     }
+    return FQ_OK;
+}
+
+fq_status fqo_kmer_enable(fqo_ctx *ctx, uint32_t k, uint64_t split_size, uint32_t num_subsample)
+{
+    if (!ctx || k < 2 || k > 31 || !split_size || !num_subsample) return FQ_ERR_ARG;
+    ctx->kmer.enabled = ctx->kmer.collecting = true;
+    ctx->kmer.k = k; ctx->kmer.split_size = split_size; ctx->kmer.num_subsample = num_subsample;
+    return FQ_OK;
+}
+
+fq_status fqo_kmer_end_pass(fqo_ctx *ctx)
+{   // FaQCs.cpp:518-537, 737-756
+    if (!ctx) return FQ_ERR_ARG;
+    fqo_ctx::Kmer &K = ctx->kmer;
+    if (!K.enabled) return FQ_OK;
+    for (const auto &kv : K.table) ++K.freq[kv.second];
+    if (K.collecting && K.samples.empty()) K.samples.push_back(fq_rarefaction{K.total_number, (uint64_t)K.table.size(), K.table_total});
+    K.table.clear();
+    K.table_total = 0;
+    return FQ_OK;
+}
+
+fq_status fqo_kmer_results(fqo_ctx *ctx, fq_kmer_view *view)
+{
+    if (!ctx || !view) return FQ_ERR_ARG;
+    fqo_ctx::Kmer &K = ctx->kmer;
+    K.flat.clear();
+    for (const auto &kv : K.freq) { K.flat.push_back(kv.first); K.flat.push_back(kv.second); }
+    view->n_rarefaction = (uint32_t)K.samples.size();
+    view->rarefaction = K.samples.data();
+    view->n_frequency = K.flat.size() / 2;
+    view->frequency = K.flat.data();
     return FQ_OK;
 }
 

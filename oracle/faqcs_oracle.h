@@ -31,6 +31,11 @@ fq_status   fqo_process_host(fqo_ctx *ctx, const uint8_t *r1, size_t n1,
                              uint64_t first_record_index, int is_final,
                              fq_batch_out *out);
 fq_status   fqo_stats(fqo_ctx *ctx, fq_stats_view *view);
+/* k-mer rarefaction: update_kmer (trim.cpp:887-931), the sampling at the end of trim() (trim.cpp:157-185), the end of a
+ * pass (FaQCs.cpp:518-537, 737-756) -- see fq_kmer_* in include/faqcs_b200.h */
+fq_status   fqo_kmer_enable(fqo_ctx *ctx, uint32_t k, uint64_t split_size, uint32_t num_subsample);
+fq_status   fqo_kmer_end_pass(fqo_ctx *ctx);
+fq_status   fqo_kmer_results(fqo_ctx *ctx, fq_kmer_view *view);
 
 /* Single-function probes used by unit tests of the micro-semantics. */
 /* BWA_plus / BWA / HARD trim of one quality string: returns new length, *f5 = 5' cut. */

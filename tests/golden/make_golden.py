@@ -78,10 +78,40 @@ CASES = {
 }
 
 
+# k-mer rarefaction (--kmer_rarefaction): paired pass + unpaired pass, inputs regenerated from the seeded generator;
+# the fixture holds the reference's QC.Kmercount.txt and QC.kmerH.txt.  (-m is not reachable through the reference's
+# getopt_long_only -- it is an ambiguous abbreviation of --mode / --min_L -- so the reference always runs k = 31.)
+KMER_CASES = {
+    # name: (paired generator, unpaired generator, Options kwargs, split_size, subset, threads)
+    "qc_only": ("synth.shotgun(70000)", "synth.shotgun(40000, seed=78, paired=False, L=100)", dict(qc_only=True), 30000, 2, 3),
+    "qc_only_early_stop": ("synth.shotgun(70000)", "synth.shotgun(40000, seed=78, paired=False, L=100)", dict(qc_only=True), 10000, 3, 2),
+    "qc_only_one_point": ("synth.shotgun(40000)", "synth.shotgun(10000, seed=78, paired=False, L=100)", dict(qc_only=True), 1000000, 10, 2),
+    "trimmed": ("synth.shotgun(70000)", "synth.shotgun(40000, seed=78, paired=False, L=100)", dict(trim_5=3, quality=20), 50000, 1, 3),
+}
+
+
+def make_kmer(only):
+    os.makedirs(os.path.join(HERE, "kmer"), exist_ok=True)
+    for name, (gp, gu, okw, split, subset, threads) in KMER_CASES.items():
+        if only and "kmer_" + name not in only:
+            continue
+        w, u = eval(gp, {"synth": synth}), eval(gu, {"synth": synth})
+        flags = refcli.flags_for(Options(**okw)) + ["--kmer_rarefaction", "--split_size", str(split), "--subset", str(subset)]
+        ref = refcli.run_reference(w.r1, w.r2, unpaired=u.r1, flags=flags, threads=threads)
+        assert ref["returncode"] == 0, ref["stderr"]
+        b = lambda x: np.frombuffer(x if isinstance(x, bytes) else x.encode(), dtype=np.uint8)
+        path = os.path.join(HERE, "kmer", name + ".npz")
+        np.savez_compressed(path, paired=b(gp), unpaired=b(gu), options=b(repr(okw)), params=np.array([31, split, subset], dtype=np.int64),
+                            kmercount=b(ref["files"]["QC.Kmercount.txt"]), kmerh=b(ref["files"]["QC.kmerH.txt"]),
+                            cmd=b(" ".join(["FaQCs"] + flags + ["-t", str(threads)])))
+        print(f"kmer/{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     import hashlib
     assert refcli.have_ref(), "build the reference first: make -C oracle ref"
     only = set(sys.argv[1:])
+    make_kmer(only)
     for name, (factory, okw, extra) in CASES.items():
         if only and name not in only:
             continue

@@ -160,3 +160,38 @@ def assert_engines_equal(a_streams, a_stats: Stats, b_streams, b_stats: Stats, a
                         k = int(np.flatnonzero(x[f] != y[f])[0])
                         raise AssertionError(f"read result {f} differs at mate {m} read {k}: {x[k]} vs {y[k]}")
                 assert np.array_equal(x["avg_q"].view(np.uint32), y["avg_q"].view(np.uint32)), "avg_q bits differ"
+
+
+def kmer_files(rare: np.ndarray, freq: np.ndarray) -> Tuple[bytes, bytes]:
+    """PlotInfo::kmer_rarefaction / kmer_frequency_histogram as plot.cpp:683-733 prints them
+    (prefix.Kmercount.txt, prefix.kmerH.txt)."""
+    last = 0
+    kc = []
+    for num_seq, distinct, total in rare.tolist():
+        kc.append(f"{num_seq - last}\t{distinct}\t{total}\n")
+        last = num_seq
+    kh = [f"{c} {n}\n" for c, n in freq.tolist()]
+    return "".join(kc).encode(), "".join(kh).encode()
+
+
+def run_kmer(engine: Engine, passes, k: int, split_size: int, subset: int, batch_records: int = 32768):
+    """Drive the k-mer rarefaction API over `passes` = [(r1, r2 or None), ...] the way FaQCs.cpp does (the paired pass,
+    then the unpaired pass); --subset is doubled as options.cpp:506-523 does for every accepted command line."""
+    engine.kmer_enable(k, split_size, 2 * subset)
+    first = True
+    for r1, r2 in passes:
+        r1 = np.frombuffer(bytes(r1), np.uint8)
+        r2 = np.frombuffer(bytes(r2), np.uint8) if r2 is not None else None
+        if first:
+            engine.autodetect(r1, r2)
+            first = False
+        cuts1 = record_cuts(r1, batch_records)
+        cuts2 = record_cuts(r2, batch_records) if r2 is not None else None
+        done = 0
+        for j in range(len(cuts1) - 1):
+            a1 = r1[cuts1[j]:cuts1[j + 1]]
+            a2 = r2[cuts2[j]:cuts2[j + 1]] if r2 is not None else None
+            res = engine.process(a1, a2, done, j == len(cuts1) - 2)
+            done += res.n_records
+        engine.kmer_end_pass()
+    return kmer_files(*engine.kmer_results())

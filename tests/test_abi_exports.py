@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, f"declared in include/faqcs_b200.h but not exported: {missing}"
     lib.fq_abi_version.restype = ctypes.c_int
-    assert lib.fq_abi_version() == 3
+    assert lib.fq_abi_version() == 4
     lib.fq_build_info.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.fq_build_info()
 

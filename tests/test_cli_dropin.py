@@ -224,3 +224,16 @@ def test_c1_example_reads_through_the_cli():
     assert_same_files(run_both({"-u": ("u.fq", u["r1"])}, ["--discard"], threads=2))
     assert_same_files(run_both({"-1": ("r1.fq", z["r1"]), "-2": ("r2.fq", z["r2"]), "-u": ("u.fq", u["r1"])}, [], threads=2,
                                extra_cli=["--batch_mb", "1"]))
+
+
+@pytest.mark.parametrize("flags", [["--qc_only", "--split_size", "30000", "--subset", "2"],
+                                   ["--split_size", "10000", "--subset", "3", "-q", "20"]], ids=["qc_only", "trimmed"])
+def test_kmer_rarefaction_files(flags):
+    """--kmer_rarefaction: QC.Kmercount.txt and QC.kmerH.txt next to the other --debug files, paired pass
+    then unpaired pass, batches cut at multiples of 32768 records."""
+    w = synth.shotgun(70000)
+    u = synth.shotgun(40000, seed=78, paired=False, L=100)
+    outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "-u": ("u.fq", u.r1)}, ["--kmer_rarefaction"] + flags, threads=3,
+                    extra_cli=["--batch_mb", "16"])
+    assert "QC.Kmercount.txt" in outs["ref"] and "QC.kmerH.txt" in outs["ref"]
+    assert_same_files(outs)

@@ -82,3 +82,20 @@ def test_fuzz_reads_and_options(seed):
     polyA = bool(kw.pop("adapters", None))
     threads = kw.get("num_thread", 0) or 2
     check(synth.Workload("fuzz", r1, r2, []), Options(**kw), threads=threads, polyA=polyA)
+
+
+@pytest.mark.parametrize("qc_only", [True, False], ids=["qc_only", "trimmed"])
+def test_kmer_rarefaction_files(qc_only):
+    """--kmer_rarefaction: QC.Kmercount.txt / QC.kmerH.txt of a paired pass followed by an unpaired pass, curve cut short
+    by --subset (the reference is always at k = 31: -m is an ambiguous abbreviation under its getopt_long_only)."""
+    from parity import run_kmer
+    w = synth.shotgun(40000, genome_len=30000)
+    u = synth.shotgun(35000, genome_len=30000, seed=78, paired=False, L=100)
+    opt = Options(qc_only=qc_only)
+    flags = refcli.flags_for(opt) + ["--kmer_rarefaction", "--split_size", "25000", "--subset", "2"]
+    ref = refcli.run_reference(w.r1, w.r2, unpaired=u.r1, flags=flags, threads=3)
+    assert ref["returncode"] == 0, ref["stderr"][:500]
+    with OracleEngine(opt) as eng:
+        kc, kh = run_kmer(eng, [(w.r1, w.r2), (u.r1, None)], 31, 25000, 2)
+    assert kc == ref["files"]["QC.Kmercount.txt"]
+    assert kh == ref["files"]["QC.kmerH.txt"]
