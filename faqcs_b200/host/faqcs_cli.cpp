@@ -388,25 +388,127 @@ static size_t count_newlines(const uint8_t *buf, size_t n)
 
 // ---- input: gz or plain, whole records per batch -------------------------------------------------
 // Plain files are read with read(2) straight into the pinned batch buffer; gzip input (magic 1f 8b) goes
-// through zlib like the reference's reader (fastq.cpp:8-30).
+// through zlib like the reference's reader (fastq.cpp:8-30) -- except blocked gzip (BGZF: bgzip, bcl-convert, samtools),
+// whose members carry their compressed size in the header and are inflated by several threads at once.
+static int inflate_threads()      // per input file: half the cores, at most 16
+{
+    static const int v = (int)min(16u, max(2u, thread::hardware_concurrency() / 2));
+    return v;
+}
+
+// A BGZF member at p[0..avail): its total size, or 0 if the bytes are not a complete BGZF header (RFC 1952 member with
+// FEXTRA holding the subfield 'B','C',2,BSIZE; SAM specification 4.1).
+static size_t bgzf_member_size(const uint8_t *p, size_t avail)
+{
+    if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+    const size_t xlen = p[10] | (size_t)p[11] << 8;
+    if (avail < 12 + xlen) return 0;
+    for (size_t q = 12; q + 4 <= 12 + xlen;) {
+        const size_t slen = p[q + 2] | (size_t)p[q + 3] << 8;
+        if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) return (size_t)(p[q + 4] | (size_t)p[q + 5] << 8) + 1;
+        q += 4 + slen;
+    }
+    return 0;
+}
+
 struct Source {
     int fd = -1;
     gzFile gz = nullptr;
     bool eof = false;
+    bool bgzf = false;
+    off_t cpos = 0, csize = 0;            // BGZF: next member, file size
+    vector<uint8_t> cbuf;                 // BGZF: compressed members of one fill
     bool open(const string &fn)
     {
         fd = ::open(fn.c_str(), O_RDONLY);
         if (fd < 0) return false;
-        unsigned char magic[2] = {0, 0};
-        const ssize_t got = ::read(fd, magic, 2);
+        unsigned char head[64];
+        const ssize_t got = ::read(fd, head, sizeof(head));
         lseek(fd, 0, SEEK_SET);
-        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-            gz = gzdopen(fd, "r");
-            if (!gz) return false;
-            gzbuffer(gz, 1 << 20);
+        struct stat st;
+        if (got >= 18 && bgzf_member_size(head, (size_t)got) && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && !getenv("FAQCS_B200_NO_BGZF")) {
+            bgzf = true;
+            csize = st.st_size;
+            return true;
         }
+        if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b) return open_zlib();
         detect_sliced();
         return true;
+    }
+    bool open_zlib()
+    {
+        gz = gzdopen(fd, "r");
+        if (!gz) return false;
+        gzbuffer(gz, 1 << 20);
+        return true;
+    }
+    // BGZF: members up to the buffer's capacity, inflated by inflate_threads() threads into their places.  Anything that is
+    // not a BGZF member (plain gzip members appended to the file) hands the rest of the file to zlib.
+    size_t fill_bgzf(uint8_t *buf, size_t have, size_t cap, size_t *new_lines)
+    {
+        struct Member { size_t in, in_len, out, out_len; uint32_t crc; };
+        vector<Member> members;
+        size_t n = have;
+        const size_t want = (size_t)min<off_t>(csize - cpos, (off_t)(cap - have) + (1 << 16));
+        cbuf.resize(want);
+        for (size_t done = 0; done < want;) {
+            const ssize_t got = pread(fd, cbuf.data() + done, want - done, cpos + (off_t)done);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) throw "fastq.cpp:next_read: Unable to read header";
+            done += (size_t)got;
+        }
+        size_t p = 0;
+        bool to_zlib = false;
+        while (p < want) {
+            const size_t size = bgzf_member_size(cbuf.data() + p, want - p);
+            if (size == 0) { to_zlib = want - p >= 18 || cpos + (off_t)want >= csize; break; }   // not BGZF (or a cut header: next fill)
+            if (p + size > want) break;                                                          // cut member: next fill
+            const uint8_t *m = cbuf.data() + p;
+            const size_t hdr = 12 + (m[10] | (size_t)m[11] << 8);
+            if (size < hdr + 8) throw "corrupt BGZF member";
+            const uint32_t crc = m[size - 8] | (uint32_t)m[size - 7] << 8 | (uint32_t)m[size - 6] << 16 | (uint32_t)m[size - 5] << 24;
+            const size_t isize = m[size - 4] | (size_t)m[size - 3] << 8 | (size_t)m[size - 2] << 16 | (size_t)m[size - 1] << 24;
+            if (n + isize > cap) break;
+            members.push_back(Member{p + hdr, size - hdr - 8, n, isize, crc});
+            n += isize;
+            p += size;
+        }
+        const int nt = (int)max<size_t>(1, min<size_t>((size_t)inflate_threads(), members.size() / 4));
+        vector<size_t> lines(nt, 0);
+        vector<int> bad(nt, 0);
+        vector<thread> th;
+        for (int t = 0; t < nt; ++t) {
+            auto job = [&, t] {
+                z_stream zs{};
+                if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
+                const size_t lo = members.size() * t / nt, hi = members.size() * (t + 1) / nt;
+                for (size_t k = lo; k < hi; ++k) {
+                    const Member &mb = members[k];
+                    zs.next_in = cbuf.data() + mb.in; zs.avail_in = (uInt)mb.in_len;
+                    zs.next_out = buf + mb.out; zs.avail_out = (uInt)mb.out_len;
+                    const int rc = mb.out_len || mb.in_len ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+                    if (rc != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf + mb.out, (uInt)mb.out_len) != mb.crc) { bad[t] = 1; break; }
+                    inflateReset(&zs);
+                }
+                inflateEnd(&zs);
+                if (hi > lo) lines[t] = count_newlines(buf + members[lo].out, members[hi - 1].out + members[hi - 1].out_len - members[lo].out);
+            };
+            if (t + 1 < nt) th.emplace_back(job); else job();
+        }
+        for (thread &x : th) x.join();
+        for (int t = 0; t < nt; ++t) {
+            if (bad[t]) throw "fastq.cpp:next_read: Unable to read header";       // what a failed gzgets turns into
+            *new_lines += lines[t];
+        }
+        cpos += (off_t)p;
+        if (cpos >= csize) eof = true;
+        if (to_zlib) {                       // the rest of the file through zlib, from this member on
+            bgzf = false;
+            lseek(fd, cpos, SEEK_SET);
+            if (!open_zlib()) throw "fastq.cpp:next_read: Unable to read header";
+            if (n < cap) return fill(buf, n, cap, new_lines);
+        }
+        return n;
     }
     void close()
     {
@@ -428,6 +530,7 @@ struct Source {
     size_t fill(uint8_t *buf, size_t have, size_t cap, size_t *new_lines)
     {
         size_t n = have;
+        if (bgzf) return fill_bgzf(buf, have, cap, new_lines);
         if (sliced) {
             const size_t want = (size_t)min<off_t>((off_t)(cap - have), size - pos);
             const int nt = want >= io_slice_min() && want >= (size_t)kIoThreads ? kIoThreads : 1;

@@ -20,13 +20,33 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refcli.have_ref(), reason=
               pytest.mark.skipif(not os.path.exists(CLI), reason="CLI not built")]
 
 
+def bgzf_bytes(data: bytes, block: int = 0xff00, level: int = 1, eof_marker: bool = True) -> bytes:
+    """Blocked gzip as bgzip writes it (SAM specification 4.1): members of <= 64 KiB with their size in a 'BC' extra field."""
+    import struct
+    import zlib
+    out = bytearray()
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + ([b""] if eof_marker else [])
+    for c in chunks:
+        z = zlib.compressobj(level, zlib.DEFLATED, -15)
+        payload = z.compress(c) + z.flush()
+        out += struct.pack("<4BI2BH2BHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, 66, 67, 2, len(payload) + 25)
+        out += payload + struct.pack("<II", zlib.crc32(c), len(c))
+    return bytes(out)
+
+
 def run_both(inputs, flags, threads=2, extra_cli=(), env=None):
     tmp = tempfile.mkdtemp(prefix="faqcs_cli_")
     try:
         args = []
         for flag, (name, data) in inputs.items():
             path = os.path.join(tmp, name)
-            if name.endswith(".gz"):
+            if name.endswith(".bgz.gz"):
+                open(path, "wb").write(bgzf_bytes(bytes(data)))
+            elif name.endswith(".mixed.gz"):       # blocked members first, ordinary gzip members appended
+                d = bytes(data)
+                cut = d.index(b"\n", len(d) // 2) + 1
+                open(path, "wb").write(bgzf_bytes(d[:cut], eof_marker=False) + gzip.compress(d[cut:], 1))
+            elif name.endswith(".gz"):
                 with gzip.open(path, "wb", compresslevel=1) as fh:
                     fh.write(bytes(data))
             else:
@@ -236,4 +256,15 @@ def test_kmer_rarefaction_files(flags):
     outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "-u": ("u.fq", u.r1)}, ["--kmer_rarefaction"] + flags, threads=3,
                     extra_cli=["--batch_mb", "16"])
     assert "QC.Kmercount.txt" in outs["ref"] and "QC.kmerH.txt" in outs["ref"]
+    assert_same_files(outs)
+
+
+def test_blocked_gzip_inputs_are_inflated_in_parallel():
+    """BGZF input: members are inflated by several threads straight into the batch buffer; a file that
+    continues with ordinary gzip members falls through to zlib.  Same files as the reference reading the same .gz."""
+    w = synth.c2(60000)
+    outs = run_both({"-1": ("r1.bgz.gz", w.r1), "-2": ("r2.mixed.gz", w.r2)}, ["--discard"], threads=3, extra_cli=["--batch_mb", "7"])
+    assert_same_files(outs)
+    u = synth.c5(30000)
+    outs = run_both({"-u": ("u.bgz.gz", u.r1)}, ["--mode", "HARD", "-q", "20", "--avg_q", "25"], threads=2, extra_cli=["--batch_mb", "2"])
     assert_same_files(outs)
