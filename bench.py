@@ -256,6 +256,9 @@ def main():
     ap.add_argument("--batch-pairs", type=int, default=2_000_000, help="pairs per device batch (block replicated in HBM)")
     ap.add_argument("--batches-per-step", type=int, default=50,
                     help="device batches per step: 50 x 2 M pairs = the 100 M pairs of BASELINE configs[1] (the resident batch is replayed, SURVEY 8(d))")
+    ap.add_argument("--contexts-per-gpu", type=int, default=2,
+                    help="contexts (one batch in flight each, own stream, own host thread) sharing a GPU in the device-resident leg: "
+                         "consecutive batches overlap on the device (one context's k_trim with another's framing / emit)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default: min(steps, 4); 0 disables)")
     ap.add_argument("--cpu-pairs", type=int, default=500_000, help="sample size of the cpu_baseline leg")
     ap.add_argument("--ref-pairs", type=int, default=500_000, help="pairs per step of --impl reference (bounded sample)")
@@ -307,21 +310,54 @@ def main():
             "c3": Options(filter_adapter=True, adapters=list(BUILTIN_ADAPTERS) + [POLYA_ADAPTER] + list(w.artifacts or [])),
             "c4": Options(qc_only=True),
             "c5": Options(mode=MODE_HARD, quality=20, average_quality=25.0, replace_to_N_q=10, discard_output=True)}[args.workload]
-    eng = Engine(opts, device=local_rank)
-    eng.autodetect(w.r1, w.r2)
+    n_ctx = max(1, args.contexts_per_gpu)
+    engines = [Engine(opts, device=local_rank) for _ in range(n_ctx)]
+    for e in engines:
+        e.autodetect(w.r1, w.r2)
+    eng = engines[0]
     ext = torch.cuda.ExternalStream(eng.stream(), device=dev)
+    exts = [torch.cuda.ExternalStream(e.stream(), device=dev) for e in engines]
 
-    def batch():
-        return eng.process_device(d_r1.data_ptr(), n1, d_r2.data_ptr() if paired else None, n2, 0, True, copy_out=False)
+    def batch(e=eng):
+        return e.process_device(d_r1.data_ptr(), n1, d_r2.data_ptr() if paired else None, n2, 0, True, copy_out=False)
+
+    def run_batches(total, seg=None):
+        """`total` batches dealt out to the contexts in order, each context on its own host thread (the C ABI call blocks
+        until its batch is done; ctypes releases the GIL); returns when all are done."""
+        errs = []
+
+        def work(j):
+            try:
+                for _ in range(j, total, n_ctx):
+                    batch(engines[j])
+                    if seg is not None:
+                        t = engines[j].last_timing()
+                        for k in seg[j]:
+                            seg[j][k] += t[k]
+            except BaseException as ex:          # surfaced below: a failed batch must fail the bench
+                errs.append(ex)
+
+        if n_ctx == 1:
+            work(0)
+        else:
+            th = [threading.Thread(target=work, args=(j,)) for j in range(n_ctx)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        if errs:
+            raise errs[0]
 
     # one batch alone: its statistics are the unit the final check multiplies
     res = batch()
     one = stats_arrays(eng.stats())
     n_batches_done = 1
+    for e in engines[1:]:
+        batch(e)
+        n_batches_done += 1
     for _ in range(max(args.warmup, 3)):
-        for _ in range(nb):
-            batch()
-            n_batches_done += 1
+        run_batches(nb)
+        n_batches_done += nb
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -330,16 +366,13 @@ def main():
     sampler = ClockSampler(phys)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = eng.launch_count()
-    seg = {k: 0.0 for k in ("all", "frame", "adapter", "trim", "emit")}
+    launches0 = sum(e.launch_count() for e in engines)
+    seg_ctx = [{k: 0.0 for k in ("all", "frame", "adapter", "trim", "emit")} for _ in engines]
     torch.cuda.synchronize()
-    e0.record(ext)
-    for _ in range(args.steps):
-        for _ in range(nb):
-            batch()
-            t = eng.last_timing()
-            for k in seg:
-                seg[k] += t[k]
+    e0.record(ext)                                   # the device is idle: every context's stream starts after this point
+    run_batches(args.steps * nb, seg_ctx)
+    for x in exts[1:]:
+        ext.wait_stream(x)                           # the end event follows the last kernel of every context
     e1.record(ext)
     torch.cuda.synchronize()
     n_batches_done += args.steps * nb
@@ -347,7 +380,23 @@ def main():
         dist.barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
-    launches = eng.launch_count() - launches0
+    launches = sum(e.launch_count() for e in engines) - launches0
+    seg_overlapped = {k: sum(s_[k] for s_ in seg_ctx) for k in seg_ctx[0]}
+    # per-kernel durations: with several contexts the events of one context's segment also span the other contexts' kernels,
+    # so the kernels are timed once more on ONE context alone (same batch, after the timed region)
+    iso_batches = min(nb, 20)
+    seg = {k: 0.0 for k in seg_ctx[0]}
+    if n_ctx > 1:
+        for _ in range(iso_batches):
+            batch()
+            t = eng.last_timing()
+            for k in seg:
+                seg[k] += t[k]
+        n_batches_done += iso_batches
+    else:
+        seg, iso_batches = seg_overlapped, args.steps * nb
+    for e in engines[1:]:                            # contexts of one device: dst += src (fq_merge_stats)
+        eng.merge_stats_from(e)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -452,7 +501,7 @@ def main():
         # the sequence and quality lines (2L per read) -- or, when emission is fused into it, B_in's share + B_out --;
         # a separate emit kernel reads B_in and writes B_out
         total_len = float(one["filter_stats"][2])
-        seg_ms = {k: v / steps_batches for k, v in seg.items()}
+        seg_ms = {k: v / iso_batches for k, v in seg.items()}
         fused = seg_ms["emit"] <= 0.0 and sum(out_bytes) > 0
         seg_bytes = {"frame": n1 + n2, "trim": (n1 + n2 + sum(out_bytes)) if fused else 2 * total_len + 8 * reads_per_batch,
                      "emit": 0 if fused else n1 + n2 + sum(out_bytes), "adapter": total_len}
@@ -466,7 +515,8 @@ def main():
         for k in ("frame", "adapter", "trim", "emit"):
             if seg_ms[k] > 0.01:            # an idle segment (no adapter pass, emission fused or off) is two events apart
                 a = seg_bytes[k] / (seg_ms[k] / 1e3) / 1e9
-                kernels[k] = {"ms": seg_ms[k], "algorithmic_bytes": seg_bytes[k], "achieved": a, "frac": a / peak,
+                kernels[k] = {"ms": seg_ms[k], "ms_in_timed_region": seg_overlapped[k] / steps_batches,
+                              "algorithmic_bytes": seg_bytes[k], "achieved": a, "frac": a / peak,
                               "dram_bytes": traffic.get(k), "traffic_ratio": (traffic[k] / seg_bytes[k]) if k in traffic and seg_bytes[k] else None}
         dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
         cfg = workload_config(args, world)
@@ -476,7 +526,11 @@ def main():
         cfg.update({"read_length": rl, "bytes_in_per_batch": n1 + n2, "bytes_out_per_batch": sum(out_bytes),
                     "gbases_per_s": rl * value / 1e9, "l2": "inputs (%.0f MB per device batch) exceed the 126 MB L2" % ((n1 + n2) / 1e6),
                     "reads_total": int(st.filter_stats[1]), "reads_kept": int(st.filter_stats[3]),
-                    "stats_allreduce_ms": allreduce_ms, "result_check": checked})
+                    "stats_allreduce_ms": allreduce_ms, "result_check": checked,
+                    "contexts_per_gpu": n_ctx,
+                    "kernel_timing": ("kernels[].ms: CUDA events of one context running alone (%d batches after the timed region); "
+                                      "ms_in_timed_region: the same events while %d contexts share the device" % (iso_batches, n_ctx))
+                                     if n_ctx > 1 else "kernels[].ms: CUDA events inside the timed region"})
         try:        # un-profiled bench lines of the other BASELINE configs, measured with this code (profiles/)
             cfg["other_workloads"] = json.load(open(os.path.join(ROOT, "profiles", "r2_other_workloads.json")))
         except Exception:
@@ -499,7 +553,8 @@ def main():
                 os.sched_setaffinity(0, affinity0)
             line["cpu_baseline"] = cpu_baseline(args.cpu_pairs)
         print(json.dumps(line))
-    eng.close()
+    for e in engines:
+        e.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -317,6 +317,7 @@ class Engine:
             L.fq_comm_destroy.argtypes = [C.c_void_p]
             L.fq_comm_destroy.restype = None
             L.fq_allreduce_stats.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+            L.fq_merge_stats.argtypes = [C.c_void_p, C.c_void_p]
             L.fq_last_allreduce_ms.argtypes = [C.c_void_p]
             L.fq_last_allreduce_ms.restype = C.c_float
             L.fq_device_outputs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p * NUM_STREAM)]
@@ -351,6 +352,10 @@ class Engine:
         """Pieces mode (fq_set_output_pieces): streams come back as lists of pieces of the caller's input + literal bytes."""
         self._check(self.lib.fq_set_output_pieces(self.ctx, int(enable)))
         self._pieces = bool(enable)
+
+    def merge_stats_from(self, other: "Engine"):
+        """fq_merge_stats: add another context's accumulators (same device) into this one and zero them there."""
+        self._check(self.lib.fq_merge_stats(self.ctx, other.ctx))
 
     def kmer_enable(self, k: int = 31, split_size: int = 1000000, num_subsample: int = 10):
         """--kmer_rarefaction: k = Options::kmer (-m), Options::split_size, Options::num_subsample (--subset, already

@@ -162,6 +162,18 @@ fq_status fail(fq_ctx *c, fq_status code, const std::string &msg)
 uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 // (Re)allocate the stats block for at least `rows` position rows, keeping the contents.
+__global__ void __launch_bounds__(256) k_merge_stats(unsigned long long *dst, unsigned long long *src, size_t n, uint32_t *dst_rows, uint32_t *src_rows)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        dst[i] += src[i];
+        src[i] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4) {
+        dst_rows[threadIdx.x] = max(dst_rows[threadIdx.x], src_rows[threadIdx.x]);
+        src_rows[threadIdx.x] = 0;
+    }
+}
+
 fq_status ensure_stats_rows(fq_ctx *ctx, uint32_t rows)
 {
     rows = std::max(64u, round_up(rows, 64));
@@ -605,6 +617,10 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         int per_sm = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         per_sm = std::max(per_sm, 1);
+        {   // tuning knob: cap the resident k_trim CTAs per SM (room for another context's kernels on the same device)
+            static const int cap = [] { const char *e = getenv("FAQCS_B200_TRIM_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+            if (cap > 0) per_sm = std::min(per_sm, cap);
+        }
         const uint32_t groups = ((n + 31) / 32) * n_mates;
         const int grid = std::max(1, std::min<int>((groups + threads / 32 - 1) / (threads / 32), ctx->sm_count * per_sm));
         kern<<<grid, threads, smem, ctx->stream>>>(ta, o);
@@ -1360,6 +1376,29 @@ fq_status fq_allreduce_stats(fq_ctx *const *ctxs, int n, fq_comm *const *comms)
         cudaEventElapsedTime(&ctxs[i]->allreduce_ms, ctxs[i]->ev[0], ctxs[i]->ev[1]);
         d_cap[i].release();
     }
+    return FQ_OK;
+}
+
+// Contexts that share a device (one in-flight batch each, so that consecutive batches overlap on the device): dst += src,
+// src = 0.  The same merge as the all-reduce (sum of the block, max of the row counters) without a communicator.
+fq_status fq_merge_stats(fq_ctx *dst, fq_ctx *src)
+{
+    if (!dst || !src || dst == src) return FQ_ERR_ARG;
+    if (dst->device != src->device) return fail(dst, FQ_ERR_ARG, "fq_merge_stats: contexts on different devices (use fq_allreduce_stats)");
+    if (dst->opt.n_adapters != src->opt.n_adapters) return fail(dst, FQ_ERR_ARG, "fq_merge_stats: contexts with different adapter lists");
+    fq_ctx *const ctx = dst;
+    CK(cudaSetDevice(dst->device));
+    CK(cudaStreamSynchronize(src->stream));
+    CK(cudaStreamSynchronize(dst->stream));
+    const uint32_t rows = std::max(dst->L.rows, src->L.rows);
+    fq_status st = ensure_stats_rows(dst, rows);
+    if (st == FQ_OK) st = ensure_stats_rows(src, rows);
+    if (st != FQ_OK) return st;
+    if (dst->L.total != src->L.total) return fail(dst, FQ_ERR_STATE, "fq_merge_stats: row capacities disagree");
+    k_merge_stats<<<dst->sm_count * 4, 256, 0, dst->stream>>>(dst->d_stats.as<unsigned long long>(), src->d_stats.as<unsigned long long>(), dst->L.total,
+                                                           dst->d_rows.as<uint32_t>(), src->d_rows.as<uint32_t>());
+    dst->launches++;
+    CK(cudaStreamSynchronize(dst->stream));
     return FQ_OK;
 }
 

@@ -323,6 +323,9 @@ fq_status fq_comm_init_rank(fq_ctx *ctx, int n_ranks, int rank, const uint8_t id
 fq_status fq_comm_init_all(fq_ctx *const *ctx, int n, fq_comm **out);
 void      fq_comm_destroy(fq_comm *comm);
 fq_status fq_allreduce_stats(fq_ctx *const *ctx, int n, fq_comm *const *comm);
+/* Contexts on the SAME device (a context holds one batch in flight; two of them driven by two host threads overlap
+ * consecutive batches on the device): dst += src, src = 0 -- the merge of trim.cpp:120-154 without a communicator. */
+fq_status fq_merge_stats(fq_ctx *dst, fq_ctx *src);
 /* Device milliseconds of the last fq_allreduce_stats on this context (CUDA events around the three collectives). */
 float     fq_last_allreduce_ms(const fq_ctx *ctx);
 

@@ -428,3 +428,46 @@ def test_quality_change_between_batches():
         eng.process(w1.r1, w1.r2, 0, False)
         c = eng.process(w2.r1, w2.r2, 3000, True)
     assert c.streams != sg[1]
+
+
+@pytest.mark.gpu
+def test_two_contexts_on_one_device_overlap_batches_and_merge():
+    """Two contexts on the same device, each driven by its own host thread (one batch in flight per context, so that one
+    context's k_trim overlaps the other's framing / emit): streams in batch order and the merged statistics
+    (fq_merge_stats: dst += src, src = 0) equal one context over the whole input, reads of 600 bases on one context only."""
+    import threading
+    from faqcs_b200 import shard
+    w = synth.c2(24000)
+    long_reads = synth.fastq_bytes([(f"@long{i}", "ACGT" * 150, "I" * 599 + "5") for i in range(64)])
+    r1 = np.concatenate([np.asarray(w.r1), np.frombuffer(long_reads, dtype=np.uint8)])
+    r2 = np.concatenate([np.asarray(w.r2), np.frombuffer(long_reads, dtype=np.uint8)])
+    okw = dict(discard_output=True, quality=15)
+    batch_records = 3000
+    b1, b2 = shard.record_batches(r1, batch_records), shard.record_batches(r2, batch_records)
+    with Engine(Options(**okw)) as one:
+        one.autodetect(r1, r2)
+        single = one.process(r1, r2)
+        single_stats = one.stats()
+    engines = [Engine(Options(**okw)), Engine(Options(**okw))]
+    try:
+        for e in engines:
+            e.autodetect(r1, r2)
+        results = [None] * len(b1)
+
+        def work(j):
+            for k in range(j, len(b1), 2):
+                results[k] = engines[j].process(r1[b1[k][0]:b1[k][1]], r2[b2[k][0]:b2[k][1]], k * batch_records, k == len(b1) - 1)
+
+        th = [threading.Thread(target=work, args=(j,)) for j in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for i in range(4):
+            assert b"".join(bytes(r.streams[i]) for r in results) == bytes(single.streams[i])
+        engines[0].merge_stats_from(engines[1])
+        assert not engines[0].stats().diff(single_stats), engines[0].stats().diff(single_stats)
+        assert int(engines[1].stats().filter_stats.sum()) == 0
+    finally:
+        for e in engines:
+            e.close()
