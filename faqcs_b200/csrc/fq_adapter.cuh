@@ -61,9 +61,13 @@ struct AdapterArgs {
 constexpr uint32_t kSweepMaxLen = 96;
 struct SegInfo {
     uint16_t owner;     // adapter index
-    uint8_t len;        // bases in this segment
+    uint8_t len;        // bases in this segment (an adapter is cut into ceil(T / 32) segments of equal length, +-1)
     uint8_t total;      // bases in the adapter
+    uint8_t start;      // first adapter base of the segment
+    uint8_t bound_full; // matches the segment needs when the threshold is taken from the whole adapter (the read is not shorter)
+    uint16_t pad;
 };
+constexpr int kSweepWindows = 6;        // windows of 32 diagonals held in registers per pass over the segments
 
 // seq_overlap.cpp:372-411; 0xff = unknown base (the reference throws)
 __device__ __forceinline__ uint32_t na_to_bits(uint32_t c)
@@ -117,6 +121,75 @@ __device__ __forceinline__ int exact_align(const uint8_t *s_read, uint32_t L, co
     return (int)(kmax >> 48);
 }
 
+// One pass of the segment sweep: NW windows of 32 diagonals (lane = diagonal) against every segment.
+struct SweepCtx {
+    const uint32_t *rx;         // read masks x, y, u, v: 4 planes of `rstride` words, zero outside the read
+    uint32_t rstride;
+    const uint4 *seg;           // [n_seg] {x, y, u, v}
+    const uint4 *segp;          // [n_seg] {x, valid, u, bound from the whole adapter}: plain A/C/G/T segments
+    const SegInfo *info;
+    const uint8_t *wbound;      // per-read bounds (read shorter than an adapter)
+    uint32_t *cand;
+    uint32_t n_seg, lane;
+    int S, n_windows;
+    bool full, pure;
+};
+
+template <int NW>
+__device__ __forceinline__ void sweep_windows(const SweepCtx &c, int w0, uint32_t *s_segflag)
+{
+    uint32_t wx[NW], wy[NW], wu[NW], wv[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const int p0 = -c.S + 32 * (w0 + i) + (int)c.lane;
+        const uint32_t sh = (uint32_t)p0 & 31u;
+        const uint32_t *p = c.rx + (p0 >> 5);
+        wx[i] = wy[i] = wu[i] = wv[i] = 0;
+        if (w0 + i < c.n_windows) {
+            wx[i] = __funnelshift_r(p[0], p[1], sh);
+            wy[i] = __funnelshift_r(p[c.rstride], p[c.rstride + 1], sh);
+            wu[i] = __funnelshift_r(p[2 * c.rstride], p[2 * c.rstride + 1], sh);
+            wv[i] = __funnelshift_r(p[3 * c.rstride], p[3 * c.rstride + 1], sh);
+        }
+    }
+    if (c.full && c.pure) {
+        // plain A/C/G/T segments, bounds known up front: y = ~x and v = ~u inside the segment, so each pair of planes is a bit
+        // select; a lane keeps one bit per segment ("no diagonal of mine reached the bound"), merged once per 32 segments
+        for (uint32_t k0 = 0; k0 < c.n_seg; k0 += 32) {
+            const uint32_t n_here = min(32u, c.n_seg - k0);
+            uint32_t miss = 0;
+#pragma unroll 2
+            for (uint32_t j = 0; j < n_here; ++j) {
+                const uint4 sm = c.segp[k0 + j];
+                uint32_t best = 0;
+#pragma unroll
+                for (int i = 0; i < NW; ++i)
+                    best = max(best, (uint32_t)__popc(((sm.x & wx[i]) | (~sm.x & wy[i])) & ((sm.z & wu[i]) | (~sm.z & wv[i])) & sm.y));
+                miss = __funnelshift_l(best - sm.w, miss, 1);        // (miss << 1) | sign(best - bound)
+            }
+            uint32_t hit = ~miss & (n_here == 32 ? 0xffffffffu : ((1u << n_here) - 1u));     // bit n_here-1-j: segment k0 + j
+            hit = __reduce_or_sync(0xffffffffu, hit);
+            if (c.lane == 0 && hit) s_segflag[k0 >> 5] |= hit;
+        }
+        return;
+    }
+    for (uint32_t k = 0; k < c.n_seg; ++k) {
+        const uint4 sm = c.seg[k];
+        const SegInfo si = c.info[k];
+        const uint32_t bound = c.full ? (uint32_t)si.bound_full : (uint32_t)c.wbound[k];
+        const uint32_t va = sm.x | sm.y;
+        uint32_t best = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            uint32_t m;
+            if (c.pure) m = ((sm.x & wx[i]) | (~sm.x & wy[i])) & ((sm.z & wu[i]) | (~sm.z & wv[i])) & va;
+            else m = ((sm.x & wx[i]) | (sm.y & wy[i])) & ((sm.z & wu[i]) | (sm.w & wv[i]));
+            best = max(best, (uint32_t)__popc(m));
+        }
+        if (__any_sync(0xffffffffu, best >= bound) && c.lane == 0) c.cand[si.owner >> 5] |= 1u << (si.owner & 31);
+    }
+}
+
 // Shared memory: [offsets n+1][plane offsets n+1][adapter codes][adapter bit planes][segment masks][segment infos]
 //                [per warp: read codes, mask words, read planes (5 + 4 sweep masks), candidate bits]
 //
@@ -128,7 +201,7 @@ __device__ __forceinline__ int exact_align(const uint8_t *s_read, uint32_t L, co
 // produced lazily by aligning the nearest earlier adapter that shares a base with the read.
 __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevOpts o, const AdapterSet A)
 {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(16) uint32_t smem_u32[];
     uint32_t *s_off = smem_u32;
     uint32_t *s_poff = s_off + A.n + 1;
     uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_poff + A.n + 1);
@@ -139,16 +212,22 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
     uint32_t *s_planes = reinterpret_cast<uint32_t *>(s_codes + codes_pad);
     const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cand_words = (A.n + 31) >> 5;
-    const uint32_t per_warp_words = read_pad / 4 + mask_words + (a.use_planes ? 5 * rstride : 0) + (a.sweep ? 4 * rstride + cand_words : 0);
-    uint4 *s_seg = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(s_planes + a.plane_words) + 15) & ~(uintptr_t)15);   // [n_seg] masks {x, y, u, v}
-    SegInfo *s_seginfo = reinterpret_cast<SegInfo *>(s_seg + a.n_seg);                                                         // [n_seg]
+    const uint32_t bound_words = (a.n_seg + 3) >> 2;           // per-read segment bounds (bytes) of a read shorter than an adapter
+    const uint32_t per_warp_words = read_pad / 4 + mask_words + (a.use_planes ? 5 * rstride : 0) + (a.sweep ? 4 * rstride + cand_words + bound_words : 0);
+    // [n_seg] masks {x, y, u, v}, 16-byte aligned (an offset from the array keeps the pointer in the shared address space)
+    uint4 *s_seg = reinterpret_cast<uint4 *>(smem_u32 + (((uint32_t)(s_planes + a.plane_words - smem_u32) + 3u) & ~3u));
+    uint4 *s_segp = s_seg + a.n_seg;                                                  // [n_seg] {x, valid, u, whole-adapter bound}
+    SegInfo *s_seginfo = reinterpret_cast<SegInfo *>(s_segp + a.n_seg);               // [n_seg]
     uint32_t *s_unswept = reinterpret_cast<uint32_t *>(s_seginfo + a.n_seg);          // [cand_words] adapters the sweep does not cover (longer than its limit)
-    uint32_t *warp_base = (a.sweep ? s_unswept + cand_words : s_planes + a.plane_words) + (size_t)warp_in_cta * per_warp_words;
+    uint32_t *s_meta = s_unswept + cand_words;                 // [2] sweep origin S (diagonals start S bases left of the read), longest swept adapter
+    uint32_t *warp_base = (a.sweep ? s_meta + 2 : s_planes + a.plane_words) + (size_t)warp_in_cta * per_warp_words;
     uint8_t *s_read = reinterpret_cast<uint8_t *>(warp_base);
     uint32_t *s_mask = warp_base + read_pad / 4;
     uint32_t *s_rp = s_mask + mask_words;                      // read planes [5][rstride], data at word offset rpad
     uint32_t *s_rxy = s_rp + 5 * rstride;                      // sweep masks of the read x, y, u, v: [4][rstride]
     uint32_t *s_cand = s_rxy + 4 * rstride;                    // adapters flagged by the sweep
+    uint8_t *s_wbound = reinterpret_cast<uint8_t *>(s_cand + cand_words);
+    uint32_t *s_segflag = s_cand + cand_words;                 // plain segments with whole-adapter bounds: flagged segments (same words)
 
     for (uint32_t i = threadIdx.x; i <= A.n; i += blockDim.x) s_off[i] = A.offset[i];
     for (uint32_t i = threadIdx.x; i < A.total; i += blockDim.x) s_codes[i] = A.codes[i];
@@ -168,23 +247,34 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
         if (a.sweep) {
             for (uint32_t i = lane; i < 4 * rstride; i += 32) s_rxy[i] = 0;
             if (threadIdx.x == 0) {                // segment -> (adapter, part): serial walk, the set is small
-                uint32_t k = 0;
+                uint32_t k = 0, origin = 0, longest = 0;
                 for (uint32_t w = 0; w < cand_words; ++w) s_unswept[w] = 0;
                 for (uint32_t j = 0; j < A.n; ++j) {
                     const uint32_t T = s_off[j + 1] - s_off[j];
                     if (T > kSweepMaxLen) s_unswept[j >> 5] |= 1u << (j & 31);
                     if (T == 0 || T > kSweepMaxLen) continue;
-                    for (uint32_t p = 0; p < T; p += 32) s_seginfo[k++] = SegInfo{(uint16_t)j, (uint8_t)min(32u, T - p), (uint8_t)T};
+                    longest = max(longest, T);
+                    // equal parts: a short tail segment would reach its (tiny) bound on almost every read
+                    const uint32_t parts = (T + 31) / 32, base = T / parts, rem = T % parts;
+                    const int threshold = __float2int_rz(__fmul_rn(o.match_rate, (float)T));
+                    uint32_t start = 0;
+                    for (uint32_t i = 0; i < parts; ++i) {
+                        const uint32_t len = base + (i < rem ? 1u : 0u);
+                        const uint32_t bound = threshold <= 0 ? 0u : ((uint32_t)threshold * len + T - 1) / T;      // ceil(threshold * len / T)
+                        s_seginfo[k++] = SegInfo{(uint16_t)j, (uint8_t)len, (uint8_t)T, (uint8_t)start, (uint8_t)bound, 0};
+                        origin = max(origin, len - min(len, bound));      // a diagonal further left cannot hold `bound` matches
+                        start += len;
+                    }
                 }
+                s_meta[0] = min(origin, 32u);
+                s_meta[1] = longest;
             }
         }
         __syncthreads();
         if (a.sweep) {
             for (uint32_t k = threadIdx.x; k < a.n_seg; k += blockDim.x) {
                 const SegInfo si = s_seginfo[k];
-                uint32_t first = k;                // segments of one adapter are consecutive: its first one
-                while (first > 0 && s_seginfo[first - 1].owner == si.owner) --first;
-                const uint8_t *codes = s_codes + s_off[si.owner] + 32 * (k - first);
+                const uint8_t *codes = s_codes + s_off[si.owner] + si.start;
                 uint32_t m[4] = {0, 0, 0, 0};
                 for (uint32_t p = 0; p < si.len; ++p) {
                     const uint32_t code = codes[p], bit = 1u << p;
@@ -194,6 +284,7 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
                     if (code & (1u | 8u | 16u)) m[3] |= bit;
                 }
                 s_seg[k] = make_uint4(m[0], m[1], m[2], m[3]);
+                s_segp[k] = make_uint4(m[0], m[0] | m[1], m[2], si.bound_full);
             }
         }
         __syncthreads();
@@ -294,52 +385,38 @@ __global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevO
             all_shared = __all_sync(0xffffffffu, sh_ok);
             __syncwarp();
             const uint32_t *rx = s_rxy + a.rpad;
-            const int last_word = (int)((L - 1) >> 5);
-            for (uint32_t c0 = 0; c0 < a.n_seg; c0 += 96) {          // three segments per lane: the windows are extracted once for all three
-                uint4 sm[3];
-                uint32_t va[3], bound[3], owner[3], best[3];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const uint32_t k = c0 + 32 * q + lane;
-                    sm[q] = make_uint4(0, 0, 0, 0);
-                    bound[q] = 0xffffffffu;
-                    owner[q] = 0;
-                    best[q] = 0;
-                    if (k < a.n_seg) {
-                        sm[q] = s_seg[k];
-                        const SegInfo si = s_seginfo[k];
-                        owner[q] = si.owner;
-                        const uint32_t T = si.total;
-                        const uint32_t tl = thr_min ? min(thr_len, T) : T;
-                        const int threshold = __float2int_rz(__fmul_rn(o.match_rate, (float)tl));
-                        bound[q] = threshold <= 0 ? 0u : ((uint32_t)threshold * si.len + T - 1) / T;      // ceil(threshold * len / T)
-                    }
-                    va[q] = sm[q].x | sm[q].y;
+            // Bounds: from the whole adapter (precomputed) unless this read's threshold length is shorter than some adapter
+            const bool full = !thr_min || thr_len >= s_meta[1];
+            if (!full) {
+                for (uint32_t k = lane; k < a.n_seg; k += 32) {
+                    const SegInfo si = s_seginfo[k];
+                    const uint32_t T = si.total;
+                    const int threshold = __float2int_rz(__fmul_rn(o.match_rate, (float)min(thr_len, T)));
+                    s_wbound[k] = (uint8_t)(threshold <= 0 ? 0u : ((uint32_t)threshold * si.len + T - 1) / T);
                 }
-                // windows of 32 read positions starting at p0 = 32 * idx + sh, from -31 (only the last base of a segment on the
-                // first base of the read) to the last base of the read; the planes are zero outside the read
-                for (int idx = -1; idx <= last_word; ++idx) {
-                    const uint32_t *p = rx + idx;
-                    const uint32_t x0 = p[0], x1 = p[1], y0 = p[rstride], y1 = p[rstride + 1];
-                    const uint32_t u0 = p[2 * rstride], u1 = p[2 * rstride + 1], v0 = p[3 * rstride], v1 = p[3 * rstride + 1];
-#pragma unroll 4
-                    for (uint32_t sh = 0; sh < 32; ++sh) {
-                        const uint32_t wx = __funnelshift_r(x0, x1, sh), wy = __funnelshift_r(y0, y1, sh);
-                        const uint32_t wu = __funnelshift_r(u0, u1, sh), wv = __funnelshift_r(v0, v1, sh);
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            uint32_t m;
-                            if (a.sweep_pure)       // plain A/C/G/T segments: y = ~x and v = ~u inside the segment, so each pair is a bit select
-                                m = ((sm[q].x & wx) | (~sm[q].x & wy)) & ((sm[q].z & wu) | (~sm[q].z & wv)) & va[q];
-                            else
-                                m = ((sm[q].x & wx) | (sm[q].y & wy)) & ((sm[q].z & wu) | (sm[q].w & wv));
-                            best[q] = max(best[q], (uint32_t)__popc(m));
-                        }
+                __syncwarp();
+            }
+            // Lane = diagonal.  Window w, lane l: segment bit i faces read position p0 + i with p0 = -S + 32 w + l; the planes are
+            // zero outside the read.  The windows of one pass stay in registers while the segments stream past them (their masks
+            // are warp-uniform shared-memory reads), one popcount per (diagonal, segment).
+            const int S = full ? (int)s_meta[0] : 32;
+            const int n_windows = ((int)L + S + 31) >> 5;
+            const SweepCtx sc{rx, rstride, s_seg, s_segp, s_seginfo, s_wbound, s_cand, a.n_seg, lane, S, n_windows, full, a.sweep_pure != 0};
+            const bool fast = full && a.sweep_pure;
+            if (fast)
+                for (uint32_t w = lane; w < (a.n_seg + 31) >> 5; w += 32) s_segflag[w] = 0;
+            if (n_windows <= 5) sweep_windows<5>(sc, 0, s_segflag);
+            else
+                for (int w0 = 0; w0 < n_windows; w0 += 6) sweep_windows<6>(sc, w0, s_segflag);
+            if (fast) {             // segment flags -> adapters
+                __syncwarp();
+                for (uint32_t k = lane; k < a.n_seg; k += 32) {
+                    const uint32_t n_here = min(32u, a.n_seg - (k & ~31u));
+                    if ((s_segflag[k >> 5] >> (n_here - 1 - (k & 31))) & 1u) {
+                        const uint32_t owner = s_seginfo[k].owner;
+                        atomicOr(&s_cand[owner >> 5], 1u << (owner & 31));
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    if (c0 + 32 * q + lane < a.n_seg && best[q] >= bound[q]) atomicOr(&s_cand[owner[q] >> 5], 1u << (owner[q] & 31));
             }
             __syncwarp();
         }

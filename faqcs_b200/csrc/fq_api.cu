@@ -548,7 +548,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         const size_t base_fixed = (size_t)(ctx->aset.n + 1) * 8 + ((ctx->aset.total + 3) & ~3u);
         const size_t per_warp_plain = ((max_len + 3) & ~3u) + 4 * (size_t)mask_words;
         const size_t per_warp_planes = per_warp_plain + 20 * ((size_t)mask_words + 2 * rpad);
-        // segment sweep: four more read masks and the candidate bits per warp; 16 + 4 bytes per 32-base segment of the adapters
+        // segment sweep: four more read masks, the candidate bits and per-read bounds per warp; two 16-byte mask sets + 8 bytes per segment of the adapters
         uint32_t n_seg = 0, sweep_pure = 1;
         for (uint32_t j = 0; j < ctx->aset.n; ++j) {
             const size_t T = ctx->adapter_seqs[j].size();
@@ -557,8 +557,8 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
                 if (ctx->adapter_seqs[j].find_first_not_of("ACGTacgt") != std::string::npos) sweep_pure = 0;
             }
         }
-        const size_t per_warp_sweep = 16 * ((size_t)mask_words + 2 * rpad) + 4 * (((size_t)ctx->aset.n + 31) / 32);
-        const size_t fixed_sweep = 20 * (size_t)n_seg + 16 + 4 + 4 * (((size_t)ctx->aset.n + 31) / 32);          // + alignment, + unswept bits
+        const size_t per_warp_sweep = 16 * ((size_t)mask_words + 2 * rpad) + 4 * (((size_t)ctx->aset.n + 31) / 32) + (((size_t)n_seg + 3) & ~(size_t)3);
+        const size_t fixed_sweep = 40 * (size_t)n_seg + 16 + 8 + 4 * (((size_t)ctx->aset.n + 31) / 32);          // + alignment, + unswept bits, + origin / longest
         aa.use_planes = base_fixed + (size_t)plane_words * 4 + 4 * per_warp_planes <= ctx->smem_optin ? 1 : 0;
         aa.sweep = aa.use_planes && n_seg && base_fixed + (size_t)plane_words * 4 + fixed_sweep + 4 * (per_warp_planes + per_warp_sweep) <= ctx->smem_optin ? 1 : 0;
         aa.n_seg = aa.sweep ? n_seg : 0;

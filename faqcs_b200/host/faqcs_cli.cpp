@@ -1062,11 +1062,22 @@ int main(int argc, char *argv[])
         const double t_processed = now_s();
         if (R.ctxs.size() > 1) {
             // the path's only collective: one ncclAllReduce of the integer statistics over NVLink
-            vector<fq_comm *> comms(R.ctxs.size(), nullptr);
-            R.check(fq_comm_init_all(R.ctxs.data(), (int)R.ctxs.size(), comms.data()));
-            const fq_status st = fq_allreduce_stats(R.ctxs.data(), (int)R.ctxs.size(), comms.data());
-            for (fq_comm *c : comms) fq_comm_destroy(c);
-            R.check(st);
+            // (a device listed more than once = several contexts on it, so that its batches overlap: those merge locally first)
+            vector<fq_ctx *> heads;
+            vector<int> head_dev;
+            for (size_t k = 0; k < R.ctxs.size(); ++k) {
+                size_t h = 0;
+                while (h < heads.size() && head_dev[h] != o.devices[k]) ++h;
+                if (h == heads.size()) { heads.push_back(R.ctxs[k]); head_dev.push_back(o.devices[k]); }
+                else R.check(fq_merge_stats(heads[h], R.ctxs[k]), heads[h]);
+            }
+            if (heads.size() > 1) {
+                vector<fq_comm *> comms(heads.size(), nullptr);
+                R.check(fq_comm_init_all(heads.data(), (int)heads.size(), comms.data()));
+                const fq_status st = fq_allreduce_stats(heads.data(), (int)heads.size(), comms.data());
+                for (fq_comm *c : comms) fq_comm_destroy(c);
+                R.check(st);
+            }
         }
         fq_stats_view v;
         if (fq_stats(ctx, &v) != FQ_OK) throw string(fq_last_error(ctx));

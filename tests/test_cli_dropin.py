@@ -268,3 +268,12 @@ def test_blocked_gzip_inputs_are_inflated_in_parallel():
     u = synth.c5(30000)
     outs = run_both({"-u": ("u.bgz.gz", u.r1)}, ["--mode", "HARD", "-q", "20", "--avg_q", "25"], threads=2, extra_cli=["--batch_mb", "2"])
     assert_same_files(outs)
+
+
+def test_two_contexts_on_one_device():
+    """--devices 0,0: two contexts on the same GPU take alternate batches (their kernels overlap on the device); the
+    statistics merge locally (fq_merge_stats), the files are the reference's."""
+    w = synth.c2(50000)
+    outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, ["--discard", "-q", "15"], threads=4,
+                    extra_cli=["--batch_mb", "2", "--devices", "0,0"])
+    assert_same_files(outs)
