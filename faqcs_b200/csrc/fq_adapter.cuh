@@ -67,6 +67,9 @@ struct SegInfo {
     uint8_t bound_full; // matches the segment needs when the threshold is taken from the whole adapter (the read is not shorter)
     uint16_t pad;
 };
+#ifndef FQ_ADAPTER_MIN_CTAS
+#define FQ_ADAPTER_MIN_CTAS 3
+#endif
 constexpr int kSweepWindows = 6;        // windows of 32 diagonals held in registers per pass over the segments
 
 // seq_overlap.cpp:372-411; 0xff = unknown base (the reference throws)
@@ -199,7 +202,7 @@ __device__ __forceinline__ void sweep_windows(const SweepCtx &c, int w0, uint32_
 // matches an adapter base iff their IUPAC bit sets intersect), 32 diagonals per round, one per lane.  Only
 // adapters that survive get the exact alignment; the stale range an all-mismatch adapter inherits (Q5) is
 // produced lazily by aligning the nearest earlier adapter that shares a base with the read.
-__global__ void __launch_bounds__(256) k_adapter(const AdapterArgs a, const DevOpts o, const AdapterSet A)
+__global__ void __launch_bounds__(256, FQ_ADAPTER_MIN_CTAS) k_adapter(const AdapterArgs a, const DevOpts o, const AdapterSet A)
 {
     extern __shared__ __align__(16) uint32_t smem_u32[];
     uint32_t *s_off = smem_u32;
