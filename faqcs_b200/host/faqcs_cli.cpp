@@ -56,6 +56,8 @@ struct Cli {
     vector<pair<string, string>> adapter;
     int device = 0;
     size_t batch_mb = 64;
+    bool gz_out = false;            // trimmed reads as blocked gzip (BGZF), deflated by several threads
+    bool keep_unpaired = false;     // the -u pass appends to prefix.unpaired.trimmed.fastq instead of truncating it (the reference's Q11 quirk, fixed)
     vector<int> devices;            // --devices 0,1,...: consecutive batches go to consecutive GPUs, one NCCL all-reduce at the end
     bool has_paired() const { return !input_read1_file.empty(); }       // has_paired() tests read1 twice, FaQCs.h:135-138
     bool has_unpaired() const { return !input_unpaired_file.empty(); }
@@ -138,7 +140,9 @@ static void usage()
     cerr << "\t--substitute\t\t<bool> (not implemented, as in FaQCs)\n\t--trim_only\t\t<bool> No quality report. Output trimmed reads only.\n\t--replace_to_N_q\t<INT> Replace base G to N when below this quality score (default:0, off)\n";
     cerr << "\t--5trim_off\t\t<bool> Turn off trimming from 5'end.\n\t--debug\t\t\t<bool> Keep intermediate files\n\t--version\t\t<bool> Print the version and exit\n";
     cerr << "GPU:\n\t--device\t\t<INT> CUDA device (default 0)\n\t--devices\t\t<INT,INT,..> several CUDA devices: batches are dealt out in order, statistics merged with one NCCL all-reduce\n"
-            "\t--batch_mb\t\t<INT> MiB of FASTQ per mate per batch (default 64)\n";
+            "\t--batch_mb\t\t<INT> MiB of FASTQ per mate per batch (default 64)\n"
+            "Output (extensions):\n\t--gz_out\t\t<bool> write the trimmed reads as blocked gzip (prefix.*.trimmed.fastq.gz), deflated in parallel\n"
+            "\t--keep_unpaired\t\t<bool> with -1/-2 and -u: append the -u pass to prefix.unpaired.trimmed.fastq instead of overwriting it\n";
 }
 
 static void parse_options(int argc, char *argv[], Cli &o)
@@ -163,7 +167,7 @@ static void parse_options(int argc, char *argv[], Cli &o)
         {"qc_only", false, &config_opt, 17}, {"kmer_rarefaction", false, &config_opt, 18}, {"subset", true, &config_opt, 19},
         {"discard", false, &config_opt, 20}, {"substitute", false, &config_opt, 21}, {"trim_only", false, &config_opt, 22},
         {"5trim_off", false, &config_opt, 23}, {"debug", false, &config_opt, 24}, {"version", false, &config_opt, 25}, {"R1", true, &config_opt, 26},
-        {"R2", true, &config_opt, 27}, {"replace_to_N_q", true, &config_opt, 31}, {"device", true, &config_opt, 40}, {"batch_mb", true, &config_opt, 41}, {"devices", true, &config_opt, 42},
+        {"R2", true, &config_opt, 27}, {"replace_to_N_q", true, &config_opt, 31}, {"device", true, &config_opt, 40}, {"batch_mb", true, &config_opt, 41}, {"devices", true, &config_opt, 42}, {"gz_out", false, &config_opt, 43}, {"keep_unpaired", false, &config_opt, 44},
         {0, 0, 0, 0}};
     int opt_code;
     opterr = 0;
@@ -227,6 +231,8 @@ static void parse_options(int argc, char *argv[], Cli &o)
                         }
                         break;
                     }
+                    case 43: o.gz_out = true; break;
+                    case 44: o.keep_unpaired = true; break;
                     default: cerr << "Unknown flag!" << endl; break;
                 }
                 break;
@@ -308,6 +314,9 @@ static void parse_options(int argc, char *argv[], Cli &o)
     }
     o.trimmed_unpaired_file = base + ".unpaired.trimmed.fastq";
     o.trimmed_discard_file = o.discard_output ? base + ".discard.trimmed.fastq" : "";
+    if (o.gz_out)
+        for (string *f : {&o.trimmed_read1_file, &o.trimmed_read2_file, &o.trimmed_unpaired_file, &o.trimmed_discard_file})
+            if (!f->empty()) *f += ".gz";
     if (o.plots_file.empty()) o.plots_file = base + "_qc_report.pdf";
     if (o.stats_file.empty()) o.stats_file = base + ".stats.txt";
     if (o.mode < 0) {
@@ -626,9 +635,10 @@ struct Run {
     void set_quality_everywhere(int q) { for (fq_ctx *c : ctxs) check(fq_set_quality(c, q), c); }
 };
 
-static int open_out(const string &fn, const char *what)
+static int open_out(const string &fn, const char *what, bool append = false)
 {
-    const int fd = ::open(fn.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);      // O_RDWR: shared mappings need read access
+    const int fd = ::open(fn.c_str(), O_RDWR | O_CREAT | (append ? 0 : O_TRUNC), 0666);      // O_RDWR: shared mappings need read access
+    if (fd >= 0 && append) lseek(fd, 0, SEEK_END);
     if (fd < 0) { cerr << "Unable to open " << fn << " for writing " << what << endl; throw "I/O error"; }
     return fd;
 }
@@ -644,6 +654,59 @@ static void write_all(int fd, const uint8_t *p, size_t n)
         n -= (size_t)w;
     }
 }
+// --gz_out: one batch of a stream as BGZF members (<= 0xff00 bytes of text each, SAM specification 4.1), deflated by
+// kIoThreads threads into per-thread buffers and written in order.  Concatenated members are a valid gzip file; the empty
+// end-of-file member is written when the stream is closed.
+static void bgzf_member(vector<uint8_t> &out, z_stream &zs, const uint8_t *p, size_t n)
+{
+    const size_t at = out.size();
+    out.resize(at + 18 + compressBound((uLong)n) + 8);
+    uint8_t *h = out.data() + at;
+    const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    memcpy(h, head, 16);
+    deflateReset(&zs);
+    zs.next_in = const_cast<uint8_t *>(p); zs.avail_in = (uInt)n;
+    zs.next_out = h + 18; zs.avail_out = (uInt)(out.size() - at - 18 - 8);
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) throw "I/O error while compressing the trimmed reads";
+    const size_t clen = zs.total_out, total = 18 + clen + 8;
+    if (total > 0x10000) throw "I/O error while compressing the trimmed reads";       // cannot happen: 0xff00 bytes of input
+    h[16] = (uint8_t)((total - 1) & 0xff); h[17] = (uint8_t)((total - 1) >> 8);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), p, (uInt)n), isize = (uint32_t)n;
+    uint8_t *t = h + 18 + clen;
+    for (int i = 0; i < 4; ++i) { t[i] = (uint8_t)(crc >> (8 * i)); t[4 + i] = (uint8_t)(isize >> (8 * i)); }
+    out.resize(at + total);
+}
+static void write_bgzf(int fd, const uint8_t *p, size_t n)
+{
+    constexpr size_t kBlock = 0xff00;
+    const size_t blocks = (n + kBlock - 1) / kBlock;
+    const int nt = (int)max<size_t>(1, min<size_t>(kIoThreads, blocks / 8));
+    vector<vector<uint8_t>> part(nt);
+    vector<int> bad(nt, 0);
+    vector<thread> th;
+    for (int t = 0; t < nt; ++t) {
+        auto job = [&, t] {
+            z_stream zs{};
+            if (deflateInit2(&zs, 4, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad[t] = 1; return; }
+            try {
+                for (size_t b = blocks * t / nt; b < blocks * (t + 1) / nt; ++b) bgzf_member(part[t], zs, p + b * kBlock, min(kBlock, n - b * kBlock));
+            } catch (...) { bad[t] = 1; }
+            deflateEnd(&zs);
+        };
+        if (t + 1 < nt) th.emplace_back(job); else job();
+    }
+    for (thread &x : th) x.join();
+    for (int t = 0; t < nt; ++t) {
+        if (bad[t]) throw "I/O error while compressing the trimmed reads";
+        write_all(fd, part[t].data(), part[t].size());
+    }
+}
+static void close_bgzf(int fd)
+{
+    static const uint8_t eof_member[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    write_all(fd, eof_member, sizeof(eof_member));
+}
+
 // Large appends to a regular file: reserve the range (posix_fallocate reports a full disk as an error instead of a
 // SIGBUS later), map it and let kIoThreads threads copy disjoint slices -- write(2) calls on one file serialise on its
 // inode lock, page faults into a shared mapping do not.  Anything unusual falls back to write(2).
@@ -699,7 +762,8 @@ static void process(Run &R, bool paired)
             fout[0] = open_out(o.trimmed_read1_file, "read one sequences");
             fout[1] = open_out(o.trimmed_read2_file, "read two sequences");
         }
-        fout[2] = open_out(o.trimmed_unpaired_file, "unpaired sequences");      // re-opened (truncated) by the -u pass: Q11
+        // re-opened (truncated) by the -u pass: Q11 -- unless --keep_unpaired asks for the paired pass's orphans to survive
+        fout[2] = open_out(o.trimmed_unpaired_file, "unpaired sequences", !paired && o.keep_unpaired && o.has_paired());
         if (!o.trimmed_discard_file.empty()) fout[3] = open_out(o.trimmed_discard_file, "discarded sequences");
     }
     const size_t cap = o.batch_mb << 20;
@@ -732,7 +796,8 @@ static void process(Run &R, bool paired)
                     const uint8_t *p = out.data[s];
                     const size_t n = out.bytes[s];
                     const int fd = fout[s];
-                    writers[s].post([fd, p, n] { write_mapped(fd, p, n); });
+                    const bool gz = o.gz_out;
+                    writers[s].post([fd, p, n, gz] { if (gz) write_bgzf(fd, p, n); else write_mapped(fd, p, n); });
                 }
         };
         for (int slot = 0;; slot ^= 1) {
@@ -840,7 +905,12 @@ static void process(Run &R, bool paired)
              << " s, waiting for writers " << t_write_wait << " s" << endl;
     for (int k = 0; k < 2; ++k)
         for (int m = 0; m < 2; ++m) fq_host_free(buf[k][m]);
-    for (int fd : fout) if (fd >= 0) ::close(fd);
+    for (int s = 0; s < 4; ++s)
+        if (fout[s] >= 0) {
+            // a gzip stream ends with the empty member -- except the unpaired file of the paired pass when the -u pass will append to it
+            if (o.gz_out && !(s == 2 && paired && o.keep_unpaired && o.has_unpaired())) close_bgzf(fout[s]);
+            ::close(fout[s]);
+        }
     src[0].close();
     src[1].close();
 }

@@ -277,3 +277,53 @@ def test_two_contexts_on_one_device():
     outs = run_both({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, ["--discard", "-q", "15"], threads=4,
                     extra_cli=["--batch_mb", "2", "--devices", "0,0"])
     assert_same_files(outs)
+
+
+def run_cli_only(inputs, flags, extra_cli=()):
+    tmp = tempfile.mkdtemp(prefix="faqcs_cli_")
+    try:
+        args = []
+        for flag, (name, data) in inputs.items():
+            path = os.path.join(tmp, name)
+            open(path, "wb").write(bytes(data))
+            args += [flag, path]
+        out = os.path.join(tmp, "gpu")
+        p = subprocess.run([CLI, "-d", out, "-t", "2", "--debug"] + args + list(flags) + list(extra_cli), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert p.returncode == 0, p.stderr.decode(errors="replace")[-600:]
+        return {n: open(os.path.join(out, n), "rb").read() for n in sorted(os.listdir(out)) if not n.endswith(".pdf")}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def test_gz_out_holds_the_reference_files():
+    """--gz_out: the four streams as blocked gzip, deflated by several threads per batch; gunzip gives the
+    reference's files byte for byte, every other file is unchanged."""
+    w = synth.c2(60000)
+    inputs = {"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}
+    outs = run_both(inputs, ["--discard"], threads=2, extra_cli=["--batch_mb", "8", "--gz_out"])
+    gpu = {}
+    for name, data in outs["gpu"].items():
+        if name.endswith(".fastq.gz"):
+            assert data[:4] == b"\x1f\x8b\x08\x04" and data.endswith(b"\x1b\x00\x03\x00" + b"\x00" * 8)     # BGZF members, end-of-file member
+            gpu[name[:-3]] = gzip.decompress(data)
+        else:
+            gpu[name] = data
+    assert_same_files({"ref": outs["ref"], "gpu": gpu})
+
+
+def test_keep_unpaired_appends_the_single_end_pass():
+    """--keep_unpaired: the opt-in fix of the reference's Q11 quirk (the -u pass truncates the orphans the paired pass wrote to
+    prefix.unpaired.trimmed.fastq): orphans of the paired pass, then the reads of the -u pass; plain and --gz_out."""
+    w = synth.c2(20000)
+    u = synth.c4(8000)
+    paired_only = run_cli_only({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2)}, [])
+    single_only = run_cli_only({"-u": ("u.fq", u.r1)}, [])
+    want = paired_only["QC.unpaired.trimmed.fastq"] + single_only["QC.unpaired.trimmed.fastq"]
+    assert paired_only["QC.unpaired.trimmed.fastq"] and single_only["QC.unpaired.trimmed.fastq"]
+    both = run_cli_only({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "-u": ("u.fq", u.r1)}, ["--keep_unpaired"])
+    assert both["QC.unpaired.trimmed.fastq"] == want
+    quirk = run_cli_only({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "-u": ("u.fq", u.r1)}, [])
+    assert quirk["QC.unpaired.trimmed.fastq"] == single_only["QC.unpaired.trimmed.fastq"]          # the reference's behaviour (Q11)
+    gz = run_cli_only({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "-u": ("u.fq", u.r1)}, ["--keep_unpaired", "--gz_out"])
+    assert gzip.decompress(gz["QC.unpaired.trimmed.fastq.gz"]) == want
+    assert gzip.decompress(gz["QC.1.trimmed.fastq.gz"]) == both["QC.1.trimmed.fastq"]
