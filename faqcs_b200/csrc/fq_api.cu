@@ -445,6 +445,7 @@ fq_status kmer_batch(fq_ctx *ctx, const uint8_t *d_r1, const uint8_t *d_r2, uint
     ka.res[0] = trimmed ? ctx->d_res[0].as<uint2>() : nullptr;
     ka.res[1] = trimmed ? ctx->d_res[1].as<uint2>() : nullptr;
     ka.n_rec = n; ka.n_mates = (uint32_t)n_mates; ka.k = K.k;
+    ka.replace_q = ctx->dopt.replace_q; ka.in_off = ctx->dopt.in_off;
     ka.first_call = first_call; ka.stop_call = K.pass_counted;
     ka.T = kmer_table_of(K);
     ka.call_total = K.d_call_total.as<unsigned long long>();

@@ -34,6 +34,8 @@ struct KmerArgs {
     const uint2 *res[2];            // trim verdicts: count the trimmed sequence of surviving reads; null = the raw read (--qc_only)
     uint32_t n_rec, n_mates;
     uint32_t k;
+    uint32_t replace_q;             // --replace_to_N_q of a trimming run: a 'G' below this score has become 'N' (trim.cpp:389-403)
+    int32_t in_off;
     uint32_t first_call;            // call index of (mate 0, record 0) inside the pass
     uint32_t stop_call;             // calls >= this one do not count (the curve is complete)
     KmerTable T;
@@ -71,12 +73,15 @@ __global__ void __launch_bounds__(256) k_kmer(const KmerArgs a)
     if (call >= a.stop_call) return;
     const Rec rc = (mate ? a.rec[1] : a.rec[0])[r];
     const uint8_t *s = (mate ? a.raw[1] : a.raw[0]) + rc.seq;
-    uint32_t len = rc.len;
+    const signed char *q = reinterpret_cast<const signed char *>((mate ? a.raw[1] : a.raw[0]) + rc.qual);
+    uint32_t len = rc.len, replace_q = 0;
     if (const uint2 *res = mate ? a.res[1] : a.res[0]) {
         const uint2 v = res[r];
         if (!((v.y >> kResLenBits) & FQ_RR_VALID)) return;
         s += v.x & ~kResPlusBad;
+        q += v.x & ~kResPlusBad;
         len = v.y & kResLenMask;
+        replace_q = a.replace_q;
     }
     const unsigned long long mask = (1ull << (2 * a.k)) - 1ull;
     const uint32_t comp_shift = 2 * (a.k - 1);
@@ -85,7 +90,9 @@ __global__ void __launch_bounds__(256) k_kmer(const KmerArgs a)
     for (uint32_t i = 0; i < len; ++i) {
         ++word_len;
         uint32_t b;
-        switch (s[i] | 0x20u) {
+        uint32_t ch = s[i];
+        if (replace_q && ch == 'G' && max(0, (int)q[i] - a.in_off) < (int)replace_q) ch = 'N';
+        switch (ch | 0x20u) {
             case 'a': b = 0; break;
             case 't': b = 1; break;
             case 'c': b = 2; break;

@@ -53,3 +53,49 @@ def fuzz_options(rng, in_off, adapters=False):
         kw.update(filter_adapter=True, adapters=list(BUILTIN_ADAPTERS) + [POLYA_ADAPTER], num_thread=int(rng.choice([1, 3])),
                   adapter_mismatch_rate=float(rng.choice([0.2, 0.1])))
     return kw
+
+
+def adapter_fuzz_case(seed):
+    """Adapter-centred case for the segment sweep: adapter sets of every shape (1..3 segments, more than 32 segments in all,
+    IUPAC letters and gaps, one adapter beyond the sweep's 96 bases), reads that carry mutated pieces of them at either end
+    or inside, short reads (threshold taken from the read), reads beyond 160 bases (several window passes), 'N' in the reads,
+    mismatch rates from 0 to 1, the -t dependent threshold groups."""
+    rng = np.random.default_rng(7000 + seed)
+    bases = np.array(list("ACGT"))
+    rnd = lambda n, al=bases: "".join(rng.choice(al, size=n))
+    n_ad = int(rng.choice([1, 3, 12, 45]))
+    adapters = []
+    for j in range(n_ad):
+        T = int(rng.choice([8, 20, 31, 32, 33, 40, 64, 65, 80, 96])) if j else int(rng.choice([33, 64, 97, 130]))
+        s = rnd(T)
+        if seed % 3 == 2 and j % 2:              # IUPAC / gap letters: the general (non bit-select) form of the sweep
+            s = list(s)
+            for p in rng.integers(0, T, size=max(1, T // 10)):
+                s[p] = str(rng.choice(list("RYKMSWBDHVN-")))
+            s = "".join(s)
+        adapters.append((f"A{j}", s))
+    if seed % 4 == 1:
+        adapters += list(BUILTIN_ADAPTERS) + [POLYA_ADAPTER]
+    n = 600
+    recs = []
+    for i in range(n):
+        kind = int(rng.integers(0, 8))
+        L = int(rng.integers(1, 40)) if kind == 0 else int(rng.integers(161, 330)) if kind == 1 else int(rng.integers(40, 161))
+        s = list(rnd(L, np.array(list("ACGTN")) if kind == 2 else bases))
+        if kind >= 3 and adapters:
+            a = list(adapters[int(rng.integers(0, len(adapters)))][1].replace("-", "A"))
+            a = [c if c in "ACGT" else "A" for c in a]
+            for p in rng.integers(0, len(a), size=int(rng.integers(0, max(1, len(a) // 5)))):
+                a[p] = str(rng.choice(bases))
+            cut = int(rng.integers(0, len(a)))
+            piece = a[cut:] if kind == 3 else a[:len(a) - cut] if kind == 4 else a
+            pos = 0 if kind == 3 else max(0, L - len(piece)) if kind == 4 else int(rng.integers(0, max(1, L - len(piece) + 1)))
+            for k, c in enumerate(piece):
+                if pos + k < L:
+                    s[pos + k] = c
+        q = "".join(chr(33 + int(x)) for x in rng.integers(2, 41, size=L))
+        recs.append((f"@A{i}", "".join(s), q))
+    kw = dict(filter_adapter=True, adapters=adapters, num_thread=int(rng.choice([0, 1, 3, 7])),
+              adapter_mismatch_rate=float(rng.choice([0.2, 0.2, 0.1, 0.0, 0.5, 1.0])), min_read_length=int(rng.choice([1, 30])),
+              quality=int(rng.choice([2, 5, 20])), input_quality_offset=33, discard_output=True)
+    return recs, kw

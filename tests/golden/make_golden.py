@@ -87,6 +87,8 @@ KMER_CASES = {
     "qc_only_early_stop": ("synth.shotgun(70000)", "synth.shotgun(40000, seed=78, paired=False, L=100)", dict(qc_only=True), 10000, 3, 2),
     "qc_only_one_point": ("synth.shotgun(40000)", "synth.shotgun(10000, seed=78, paired=False, L=100)", dict(qc_only=True), 1000000, 10, 2),
     "trimmed": ("synth.shotgun(70000)", "synth.shotgun(40000, seed=78, paired=False, L=100)", dict(trim_5=3, quality=20), 50000, 1, 3),
+    # G -> N below --replace_to_N_q happens before the k-mers of a surviving read are counted (trim.cpp:389-403, 545-547)
+    "trimmed_replace_to_n": ("synth.shotgun(40000)", "synth.shotgun(35000, seed=78, paired=False, L=100)", dict(replace_to_N_q=30, quality=10), 30000, 2, 2),
 }
 
 

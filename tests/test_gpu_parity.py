@@ -370,6 +370,16 @@ def test_randomized_options_and_reads(seed):
     both(r1, r2, lambda: Options(**kw), batch_records=batch)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_adapter_sweep_fuzz(seed):
+    """The segment sweep is a filter in front of the exact alignment: whatever it does, results must equal the oracle's
+    (which aligns every adapter against every read): adapter sets and reads built to reach every branch of it."""
+    from fuzz import adapter_fuzz_case
+    recs, kw = adapter_fuzz_case(seed)
+    r1 = np.frombuffer(fastq_bytes(recs), dtype=np.uint8)
+    both(r1, None, lambda: Options(**kw))
+
+
 def test_full_batch_size_properties():
     """BASELINE-size batch (2 M pairs = 4 M reads in one call, the bench's step): properties that do not need the oracle.
     Linearity: a batch made of 8 copies of a 250 k-pair block must give exactly 8 x the block's statistics and 8 x its

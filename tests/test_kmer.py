@@ -27,11 +27,14 @@ def load(path):
 
 
 def test_fixtures_exist():
-    assert len(FIXTURES) >= 4
+    assert len(FIXTURES) >= 5 and len(CPU_CASES) == 2
 
 
-# two of the four on the CPU (the oracle's std::unordered_map needs ~6 s per case)
-@pytest.mark.parametrize("path", FIXTURES[1:3], ids=IDS[1:3])
+# two of the five on the CPU (the oracle's std::unordered_map needs ~6 s per case)
+CPU_CASES = [p for p in FIXTURES if os.path.basename(p)[:-4] in ("qc_only_early_stop", "trimmed_replace_to_n")]
+
+
+@pytest.mark.parametrize("path", CPU_CASES, ids=[os.path.basename(p)[:-4] for p in CPU_CASES])
 def test_oracle_reproduces_reference_kmer_files(path):
     passes, opt, k, split, subset, kc, kh = load(path)
     with OracleEngine(opt) as eng:
@@ -140,3 +143,32 @@ def test_cuda_kmer_rejects_unaligned_batches():
         eng.autodetect(w.r1, None)
         with pytest.raises(FaqcsError):
             eng.process(w.r1, None, 100, True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_cuda_kmer_fuzz_against_oracle(seed):
+    """Random option sets (trimming modes, clips, --replace_to_N_q, --qc_only, adapters) over random reads (IUPAC letters, lower
+    case, N runs, CRLF): the k-mer curve and histogram must equal the oracle's, whose rule is the reference's -- count what
+    trim_read left in the read (trim.cpp:260-262, 389-403, 545-547)."""
+    from fuzz import fuzz_bytes, fuzz_options, fuzz_reads
+    rng = np.random.default_rng(4000 + seed)
+    in_off = 64 if seed % 4 == 3 else 33
+    paired = seed % 2 == 0
+    eol = "\r\n" if seed % 5 == 4 else "\n"
+    r1 = fuzz_bytes(fuzz_reads(rng, 500, in_off, "1" if paired else None), rng, eol)
+    r2 = fuzz_bytes(fuzz_reads(rng, 500, in_off, "2"), rng, eol) if paired else None
+    kw = fuzz_options(rng, in_off, adapters=seed % 3 == 1)
+    if seed % 2:
+        kw["replace_to_N_q"] = 20
+        kw["qc_only"] = False
+    k, split = int(rng.choice([2, 5, 11, 21, 31])), int(rng.choice([100, 400, 100000]))
+    res = []
+    for cls in (Engine, OracleEngine):
+        with cls(Options(**kw)) as e:
+            e.kmer_enable(k, split, 4)
+            e.process(r1, r2, 0, True)
+            e.kmer_end_pass()
+            rare, freq = e.kmer_results()
+            res.append((rare.tolist(), freq.tolist()))
+    assert res[0] == res[1]
