@@ -1,0 +1,61 @@
+"""Command-line fuzz campaign: random option sets x random reads through the reference binary and through faqcs_b200; every
+file both leave must be byte-identical, and a run the reference refuses must be refused.  python scratch/cli_fuzz.py FIRST LAST"""
+import os, shutil, signal, subprocess, sys, tempfile
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import numpy as np
+import refcli
+from faqcs_b200.api import Options
+from fuzz import fuzz_bytes, fuzz_options, fuzz_reads
+CLI = "/root/repo/faqcs_b200/host/faqcs_b200"
+bad = 0
+for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+    rng = np.random.default_rng(9000 + seed)
+    in_off = 64 if seed % 4 == 3 else 33
+    paired = seed % 2 == 0
+    eol = "\r\n" if seed % 5 == 4 else "\n"
+    n = int(rng.choice([300, 2000]))
+    r1 = fuzz_bytes(fuzz_reads(rng, n, in_off, "1" if paired else None), rng, eol)
+    r2 = fuzz_bytes(fuzz_reads(rng, n, in_off, "2"), rng, eol) if paired else None
+    kw = fuzz_options(rng, in_off, adapters=False)
+    adapter = seed % 3 == 1
+    polyA = seed % 6 == 1
+    kw.pop("input_quality_offset")
+    if seed % 7 == 0:
+        kw["input_quality_offset"] = in_off               # explicit --ascii, else autodetection
+    opt = Options(**kw)
+    threads = int(rng.choice([1, 2, 5]))
+    flags = refcli.flags_for(opt, polyA=polyA, adapter=adapter)
+    if seed % 8 == 5:
+        flags += ["--kmer_rarefaction", "--split_size", str(int(rng.choice([200, 1000]))), "--subset", "2"]
+    tmp = tempfile.mkdtemp(prefix="faqcs_clifuzz_")
+    try:
+        args = []
+        if paired:
+            open(f"{tmp}/r1.fq", "wb").write(bytes(r1)); open(f"{tmp}/r2.fq", "wb").write(bytes(r2))
+            args = ["-1", f"{tmp}/r1.fq", "-2", f"{tmp}/r2.fq"]
+        else:
+            open(f"{tmp}/u.fq", "wb").write(bytes(r1))
+            args = ["-u", f"{tmp}/u.fq"]
+        outs, rcs = {}, {}
+        for tag, exe in (("ref", refcli.REF_BIN), ("gpu", CLI)):
+            out = f"{tmp}/{tag}"
+            p = subprocess.run([exe, "-d", out, "-t", str(threads), "--debug"] + args + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                               preexec_fn=lambda: signal.signal(signal.SIGPIPE, signal.SIG_IGN))
+            rcs[tag] = p.returncode
+            outs[tag] = {f: open(f"{out}/{f}", "rb").read() for f in sorted(os.listdir(out)) if not f.endswith(".pdf")} if os.path.isdir(out) else {}
+            if tag == "gpu" and p.returncode != 0:
+                gpu_err = p.stderr.decode(errors="replace")[-300:]
+        if (rcs["ref"] == 0) != (rcs["gpu"] == 0):
+            bad += 1
+            print("seed", seed, "exit codes differ", rcs, flags, flush=True)
+            continue
+        if rcs["ref"] != 0:
+            continue
+        names = sorted(set(outs["ref"]) | set(outs["gpu"]))
+        diff = [f for f in names if outs["ref"].get(f) != outs["gpu"].get(f)]
+        if diff:
+            bad += 1
+            print("seed", seed, "files differ:", diff, " ".join(flags), "paired" if paired else "single", "t", threads, flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+print("seeds", sys.argv[1], "..", sys.argv[2], "failures", bad)
