@@ -220,6 +220,52 @@ __device__ __forceinline__ void copy_span(uint8_t *__restrict__ dst, const uint8
     for (uint32_t i = head + 16 * body + lane; i < n; i += W) dst[i] = src[i];
 }
 
+// copy_span with a byte-wise transformation applied on the way (16 bytes at a time through SIMD-in-word video instructions,
+// single bytes at the unaligned ends).  F::vec(a, b) / F::one(a, b): a = bytes of `src`, b = bytes of `src2` at the same offsets.
+struct XfRequal {           // quality re-encoding (trim.cpp:516-525): max(0, q - in_off) + out_off
+    uint32_t in4, out4;
+    int in_off, out_off;
+    __device__ __forceinline__ XfRequal(int i, int o) : in4(0x01010101u * (uint32_t)(i & 0xff)), out4(0x01010101u * (uint32_t)(o & 0xff)), in_off(i), out_off(o) {}
+    __device__ __forceinline__ uint32_t vec(uint32_t q, uint32_t) const { return __vadd4(__vmaxs4(__vsubss4(q, in4), 0u), out4); }
+    __device__ __forceinline__ uint8_t one(uint8_t q, uint8_t) const { return (uint8_t)(max(0, (int)(signed char)q - in_off) + out_off); }
+};
+struct XfLowG {             // G -> N below --replace_to_N_q (trim.cpp:389-403); a = base, b = its quality character
+    uint32_t in4, rq4;
+    int in_off, rq;
+    __device__ __forceinline__ XfLowG(int i, uint32_t r) : in4(0x01010101u * (uint32_t)(i & 0xff)), rq4(0x01010101u * min(r, 255u)), in_off(i), rq((int)r) {}
+    __device__ __forceinline__ uint32_t vec(uint32_t s, uint32_t q) const
+    {
+        const uint32_t qv = __vmaxs4(__vsubss4(q, in4), 0u);                      // 0..127 per byte
+        const uint32_t m = __vcmpeq4(s, 0x47474747u) & __vcmpltu4(qv, rq4);       // 0xff where a 'G' is below the score
+        return (s & ~m) | (0x4e4e4e4eu & m);
+    }
+    __device__ __forceinline__ uint8_t one(uint8_t s, uint8_t q) const
+    {
+        return (s == 'G' && max(0, (int)(signed char)q - in_off) < rq) ? (uint8_t)'N' : s;
+    }
+};
+
+template <uint32_t W, class F>
+__device__ __forceinline__ void xf_span(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, const uint8_t *__restrict__ src2, uint32_t n,
+                                        uint32_t lane, const F f)
+{
+    const bool two = src2 != nullptr;
+    if (n < 48) {
+        for (uint32_t i = lane; i < n; i += W) dst[i] = f.one(src[i], two ? src2[i] : (uint8_t)0);
+        return;
+    }
+    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    for (uint32_t i = lane; i < head; i += W) dst[i] = f.one(src[i], two ? src2[i] : (uint8_t)0);
+    const uint32_t body = (n - head) >> 4;
+    for (uint32_t c = lane; c < body; c += W) {
+        const uint4 a = gather16(src + head + 16 * c);
+        uint4 b = make_uint4(0, 0, 0, 0);
+        if (two) b = gather16(src2 + head + 16 * c);
+        *reinterpret_cast<uint4 *>(dst + head + 16 * c) = make_uint4(f.vec(a.x, b.x), f.vec(a.y, b.y), f.vec(a.z, b.z), f.vec(a.w, b.w));
+    }
+    for (uint32_t i = head + 16 * body + lane; i < n; i += W) dst[i] = f.one(src[i], two ? src2[i] : (uint8_t)0);
+}
+
 // Emit one surviving read: def \n seq \n + \n qual \n (write_read, fastq.cpp:127-138) with the
 // mutations trim_read leaves behind.  `plain`: the record is canonical, untrimmed and untouched,
 // so the output is its raw bytes.
@@ -249,21 +295,13 @@ __device__ __forceinline__ void write_trimmed(uint8_t *dst, const uint8_t *raw, 
     else {
         copy_span<W>(dst, raw + rc.hdr, hl, lane);
         if (lane == 0) dst[hl] = '\n';
+        // G -> N below --replace_to_N_q (trim.cpp:390-403); the terminal-N mask only covers 'N' bases, never a 'G'
         if (o.replace_q == 0) copy_span<W>(dst + s0, sp + lo, wl, lane);
-        else {
-            for (uint32_t i = lane; i < wl; i += W) {          // G -> N below --replace_to_N_q (trim.cpp:390-403)
-                const uint32_t p = lo + i;
-                uint32_t ch = sp[p];
-                if (ch == 'G') {
-                    const int qc = (p < lead || p >= trail) ? o.in_off : (int)qp[p];
-                    if (max(0, qc - o.in_off) < (int)o.replace_q) ch = 'N';
-                }
-                dst[s0 + i] = (uint8_t)ch;
-            }
-        }
+        else xf_span<W>(dst + s0, sp + lo, reinterpret_cast<const uint8_t *>(qp) + lo, wl, lane, XfLowG(o.in_off, o.replace_q));
     }
     if (lane < 3) dst[s1 + lane] = lane == 1 ? '+' : '\n';
     if (!masked && !requal) copy_span<W>(dst + q0, raw + rc.qual + lo, wl, lane);
+    else if (!masked) xf_span<W>(dst + q0, raw + rc.qual + lo, nullptr, wl, lane, XfRequal(o.in_off, o.out_off));
     else {
         for (uint32_t i = lane; i < wl; i += W) {
             const uint32_t p = lo + i;

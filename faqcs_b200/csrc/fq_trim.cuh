@@ -396,6 +396,7 @@ struct LaneRead {
     uint32_t cnt_n;         // N / n
     uint32_t lead, trail;   // terminal-N mask bounds
     uint32_t run_whole;     // longest 'N' run of the whole read (0 if fewer than -n 'N's)
+    uint32_t lowg;          // 'G' below --replace_to_N_q in the whole read
     bool done;              // already fully processed (generic path) or out of range
 };
 
@@ -489,6 +490,7 @@ struct ReadSummary {
     uint32_t ac, tg;        // 16-bit fields: A | C << 16, T | G << 16
     uint32_t n;             // N / n
     uint32_t lead, trail, run;
+    uint32_t lowg;          // 'G' below --replace_to_N_q in the whole read (0 when the option is off)
 };
 
 template <int K>
@@ -530,6 +532,14 @@ __device__ __forceinline__ void phase1_body(const KernelCtx &kc, uint32_t (&c)[K
     out.lead = 0;
     out.trail = len;
     out.run = 0;
+    out.lowg = 0;
+    if (o.replace_q > 0) {                          // candidates of the G -> N replacement (trim.cpp:389-403) in the whole read
+        const int below = o.in_off + (int)o.replace_q;          // quality_score(q) < replace_q  <=>  q < in_off + replace_q
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) cnt += __popc(__ballot_sync(0xffffffffu, c[k] == 'G' && (int)(signed char)q[k] < below));
+        out.lowg = cnt;
+    }
     if (acgt != len) {                              // something else than A, C, G, T (any case) in the read (warp-uniform)
         uint32_t n_any = 0;
 #pragma unroll
@@ -581,8 +591,9 @@ __device__ __forceinline__ void phase1_body(const KernelCtx &kc, uint32_t (&c)[K
 }
 
 // Cooperative pass over one read for the "removed" histograms.
-//   mode 0: positions OUTSIDE the window -> rem hists; returns their class counts / quality sum;
-//           with --replace_to_N_q also counts the G->N candidates INSIDE the window.
+//   mode 0: positions OUTSIDE the window -> rem hists; returns their class counts / quality sum and, with
+//           --replace_to_N_q, the G->N candidates among them (phase 1 counted those of the whole read); chunks that
+//           lie inside the window are skipped unless the largest quality inside is asked for (max_qv >= 0).
 //   mode 1: positions INSIDE the window -> rem hists (read turned out invalid).
 //   mode 2: G->N positions inside the window of a valid read: leave column G, enter column N.
 __device__ __forceinline__ void removed_pass(const KernelCtx &kc, int mode, const uint8_t *sp, const signed char *qp, uint32_t len,
@@ -599,7 +610,7 @@ __device__ __forceinline__ void removed_pass(const KernelCtx &kc, int mode, cons
         const uint32_t p = b + lane;
         // skip chunks that cannot contain work
         const bool chunk_inside = b >= lo && b + 32 <= lo + wl;
-        if (mode == 0 && chunk_inside && o.replace_q == 0 && max_qv < 0) continue;
+        if (mode == 0 && chunk_inside && max_qv < 0) continue;
         if (mode != 0 && (b + 32 <= lo || b >= lo + wl)) continue;
         if (p >= len) continue;
         const bool inside = p >= lo && p < lo + wl;
@@ -608,15 +619,14 @@ __device__ __forceinline__ void removed_pass(const KernelCtx &kc, int mode, cons
         if (p < lead || p >= trail) qc = o.in_off;
         const int qv = max(0, qc - o.in_off);
         const uint32_t code = H.lut()[c] >> 28;
-        const bool lowg = inside && o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q;
+        const bool lowg_any = o.replace_q > 0 && c == 'G' && qv < (int)o.replace_q;
+        const bool lowg = inside && lowg_any;
         if (mode == 0) {
             if (!inside) {
                 sum += qc;
                 if (code < 5) pk += 1u << (5 * code);
-            } else {
-                lowg_cnt += lowg;
-                mq = max(mq, qv);
-            }
+                lowg_cnt += lowg_any;               // candidates OUTSIDE the window: the caller knows the read's total
+            } else mq = max(mq, qv);
         }
         const bool to_rem = (mode == 0 && !inside) || (mode == 1 && inside);
         if (to_rem) {
@@ -940,7 +950,7 @@ __device__ __forceinline__ void trim_group(const KernelCtx &kc, uint32_t mate, u
     LaneRead me;
     me.done = lane >= n_here;
     me.rc = my_rc;
-    me.sum_q = 0; me.cnt_ac = 0; me.cnt_tg = 0; me.cnt_n = 0; me.lead = 0; me.trail = me.rc.len; me.run_whole = 0;
+    me.sum_q = 0; me.cnt_ac = 0; me.cnt_tg = 0; me.cnt_n = 0; me.lead = 0; me.trail = me.rc.len; me.run_whole = 0; me.lowg = 0;
     uint32_t g_off5 = 0, g_lenflags = 0;          // verdict of a read that took the generic path
 
     // ---- phase 1: cooperative per-base pass, read by read
@@ -969,6 +979,7 @@ __device__ __forceinline__ void trim_group(const KernelCtx &kc, uint32_t mate, u
             phase1_body<KP>(kc, c, q, len, rs);
             max_sum = max(max_sum, rs.sum_q);
             if (lane == j) { me.sum_q = rs.sum_q; me.cnt_ac = rs.ac; me.cnt_tg = rs.tg; }
+            if (o.replace_q > 0 && lane == j) me.lowg = rs.lowg;
             if (rs.n && lane == j) { me.cnt_n = rs.n; me.lead = rs.lead; me.trail = rs.trail; me.run_whole = rs.run; }
             continue;
         }
@@ -1000,6 +1011,7 @@ __device__ __forceinline__ void trim_group(const KernelCtx &kc, uint32_t mate, u
         }
         max_sum = max(max_sum, rs.sum_q);
         if (lane == j) { me.sum_q = rs.sum_q; me.cnt_ac = rs.ac; me.cnt_tg = rs.tg; }
+            if (o.replace_q > 0 && lane == j) me.lowg = rs.lowg;
         if (rs.n && lane == j) { me.cnt_n = rs.n; me.lead = rs.lead; me.trail = rs.trail; me.run_whole = rs.run; }
     }
     const bool bad_sum = max_sum >= kBadQual / 2;
@@ -1040,12 +1052,12 @@ __device__ __forceinline__ void trim_group(const KernelCtx &kc, uint32_t mate, u
         w = lane_window(kc, mate, r, len, qa);
     }
 
-    // ---- phase 3a: cooperative pass over the bases outside the window (and G->N candidates / max quality inside)
-    uint32_t w_atc = me.cnt_ac, w_gn = me.cnt_tg, n_lowg = 0;
+    // ---- phase 3a: cooperative pass over the bases outside the window (and, when a re-encoding can overflow, the max quality inside)
+    uint32_t w_atc = me.cnt_ac, w_gn = me.cnt_tg, n_lowg = me.lowg;      // G -> N candidates: those of the whole read, minus the cut ones
     int sum_w = me.sum_q, max_qv = 0;
     {
         const bool partial = !me.done && (w.lo > 0 || w.lo + w.wl < len);
-        const bool want = !me.done && (partial || ((o.replace_q > 0 || need_max) && w.ret));
+        const bool want = !me.done && (partial || (need_max && w.ret));
         uint32_t todo = __ballot_sync(0xffffffffu, want);
         while (todo) {
             const int j = __ffs(todo) - 1;
@@ -1062,7 +1074,7 @@ __device__ __forceinline__ void trim_group(const KernelCtx &kc, uint32_t mate, u
                 w_atc -= r_atc;            // fields never borrow: removed counts <= totals per class
                 w_gn -= r_gn;
                 sum_w -= r_sum;
-                n_lowg = nl;
+                n_lowg -= nl;
                 max_qv = mq;
             }
         }
