@@ -263,6 +263,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=500_000, help="sample size of the cpu_baseline leg")
     ap.add_argument("--ref-pairs", type=int, default=500_000, help="pairs per step of --impl reference (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--read-length", type=int, default=150, help="c2 recipe at another read length (profiling only; the headline is 150)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 is the headline config (BASELINE configs[1]); the others are the parity configs, for profiling only")
     args = ap.parse_args()
@@ -299,7 +300,8 @@ def main():
     nb = max(1, args.batches_per_step)
     from faqcs_b200.api import BUILTIN_ADAPTERS, MODE_HARD, POLYA_ADAPTER
     gen = {"c2": synth.c2, "c3": synth.c3, "c4": synth.c4, "c5": synth.c5}[args.workload]
-    w = gen(args.block_pairs, start=rank * args.block_pairs)
+    w = gen(args.block_pairs, start=rank * args.block_pairs, L=args.read_length) if args.workload == "c2" and args.read_length != 150 \
+        else gen(args.block_pairs, start=rank * args.block_pairs)
     paired = w.r2 is not None
     d_r1 = torch.from_numpy(w.r1).to(dev).repeat(reps)
     d_r2 = torch.from_numpy(w.r2).to(dev).repeat(reps) if paired else torch.zeros(16, dtype=torch.uint8, device=dev)
@@ -523,6 +525,8 @@ def main():
         rl = float(one["filter_stats"][2]) / max(float(one["filter_stats"][1]), 1.0)
         if args.workload != "c2":
             cfg["workload"] = args.workload + " (parity config, not the headline)"
+        elif args.read_length != 150:
+            cfg["workload"] = "c2 recipe at read length %d (profiling only, not the headline)" % args.read_length
         cfg.update({"read_length": rl, "bytes_in_per_batch": n1 + n2, "bytes_out_per_batch": sum(out_bytes),
                     "gbases_per_s": rl * value / 1e9, "l2": "inputs (%.0f MB per device batch) exceed the 126 MB L2" % ((n1 + n2) / 1e6),
                     "reads_total": int(st.filter_stats[1]), "reads_kept": int(st.filter_stats[3]),

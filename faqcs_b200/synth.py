@@ -158,10 +158,9 @@ def _inject_adapters(rng, s: np.ndarray, primers: List[Tuple[str, str]], mate: i
         s[i, :p.size] = p
 
 
-def c2(n_pairs: int, seed: int = SEEDS["C2"], start: int = 0) -> Workload:
-    """configs[1]: 2x150 PE, ASCII-33, default trim + filters + full stats."""
+def c2(n_pairs: int, seed: int = SEEDS["C2"], start: int = 0, L: int = 150) -> Workload:
+    """configs[1]: 2x150 PE, ASCII-33, default trim + filters + full stats (other L: the same recipe at another read length)."""
     rng = np.random.default_rng(seed + start)
-    L = 150
     mates = []
     for mate in (1, 2):
         q = _qualities(rng, n_pairs, L, 30, 40, 0.12, 3.0, 2, 41, 0.10, 59)
