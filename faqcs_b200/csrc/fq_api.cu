@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -162,6 +163,24 @@ fq_status fail(fq_ctx *c, fq_status code, const std::string &msg)
 uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 // (Re)allocate the stats block for at least `rows` position rows, keeping the contents.
+// The dynamic shared-memory limit of a kernel is state of the device's (primary) CUDA context, shared by every fq_ctx on
+// that device -- and contexts on one device run on different host threads.  It is therefore raised ONCE per kernel and
+// device to the opt-in maximum and never lowered: a per-launch value would race with the other context's launch.
+cudaError_t allow_dynamic_smem(fq_ctx *ctx, const void *kernel)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, bool> done;
+    std::lock_guard<std::mutex> lk(mu);
+    bool &d = done[std::make_pair(ctx->device, kernel)];
+    if (d) return cudaSuccess;
+    cudaFuncAttributes fa{};
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - fa.sharedSizeBytes));      // static + dynamic <= opt-in
+    if (e == cudaSuccess) d = true;
+    return e;
+}
+
 __global__ void __launch_bounds__(256) k_merge_stats(unsigned long long *dst, unsigned long long *src, size_t n, uint32_t *dst_rows, uint32_t *src_rows)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -537,6 +556,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         aa.first_index = first_record_index;
         aa.end_index = is_final ? first_record_index + n : ~0ull;
         // shared memory plan: offsets, codes, [adapter bit planes], per warp read codes + mask (+ read planes)
+        const size_t smem_cap = ctx->smem_optin - 2048;          // the kernel also has 1 KiB of static shared memory
         const uint32_t mask_words = (max_len + 31) >> 5;
         uint32_t plane_words = 0, has_gap = 0, rpad = 1;
         for (uint32_t j = 0; j < ctx->aset.n; ++j) {
@@ -560,8 +580,8 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         }
         const size_t per_warp_sweep = 16 * ((size_t)mask_words + 2 * rpad) + 4 * (((size_t)ctx->aset.n + 31) / 32) + (((size_t)n_seg + 3) & ~(size_t)3);
         const size_t fixed_sweep = 40 * (size_t)n_seg + 16 + 8 + 4 * (((size_t)ctx->aset.n + 31) / 32);          // + alignment, + unswept bits, + origin / longest
-        aa.use_planes = base_fixed + (size_t)plane_words * 4 + 4 * per_warp_planes <= ctx->smem_optin ? 1 : 0;
-        aa.sweep = aa.use_planes && n_seg && base_fixed + (size_t)plane_words * 4 + fixed_sweep + 4 * (per_warp_planes + per_warp_sweep) <= ctx->smem_optin ? 1 : 0;
+        aa.use_planes = base_fixed + (size_t)plane_words * 4 + 4 * per_warp_planes <= smem_cap ? 1 : 0;
+        aa.sweep = aa.use_planes && n_seg && base_fixed + (size_t)plane_words * 4 + fixed_sweep + 4 * (per_warp_planes + per_warp_sweep) <= smem_cap ? 1 : 0;
         aa.n_seg = aa.sweep ? n_seg : 0;
         aa.sweep_pure = sweep_pure;
         aa.plane_words = aa.use_planes ? plane_words : 0;
@@ -569,10 +589,10 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         const size_t fixed = base_fixed + (size_t)aa.plane_words * 4 + (aa.sweep ? fixed_sweep : 0);
         const size_t per_warp = (aa.use_planes ? per_warp_planes : per_warp_plain) + (aa.sweep ? per_warp_sweep : 0);
         int warps = 8;
-        while (warps > 1 && fixed + warps * per_warp > ctx->smem_optin) warps >>= 1;
+        while (warps > 1 && fixed + warps * per_warp > smem_cap) warps >>= 1;
         const size_t smem = fixed + warps * per_warp;
-        if (smem > ctx->smem_optin) return fail(ctx, FQ_ERR_ARG, "adapter set + read length exceed shared memory");
-        CK(cudaFuncSetAttribute(k_adapter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > smem_cap) return fail(ctx, FQ_ERR_ARG, "adapter set + read length exceed shared memory");
+        CK(allow_dynamic_smem(ctx, reinterpret_cast<const void *>(k_adapter)));
         int per_sm = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adapter, warps * 32, smem));
         const int grid = std::max(1, std::min<int>((n * n_mates + warps - 1) / warps, ctx->sm_count * std::max(per_sm, 1)));
@@ -613,7 +633,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
         const int ksel = rows < max_len ? 0 : max_len <= 128 ? 4 : max_len <= 160 ? 5 : 0;
         const TrimKernel kern = plain ? (ksel == 4 ? (TrimKernel)k_trim<4, true> : ksel == 5 ? (TrimKernel)k_trim<5, true> : (TrimKernel)k_trim<0, true>)
                                       : (ksel == 4 ? (TrimKernel)k_trim<4, false> : ksel == 5 ? (TrimKernel)k_trim<5, false> : (TrimKernel)k_trim<0, false>);
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(allow_dynamic_smem(ctx, reinterpret_cast<const void *>(kern)));
         const int threads = kTrimThreads;
         int per_sm = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -688,7 +708,7 @@ fq_status process_common(fq_ctx *ctx, const uint8_t *d_r1, size_t n1, const uint
     if (!o.qc_only && !pieces) {
         using EmitKernel = void (*)(const EmitArgs, const DevOpts);
         const EmitKernel kern = (!o.replace_q && o.in_off == o.out_off) ? (EmitKernel)k_emit<true> : (EmitKernel)k_emit<false>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem));
+        CK(allow_dynamic_smem(ctx, reinterpret_cast<const void *>(kern)));
         kern<<<ea.n_tiles, kTile, kEmitSmem, ctx->stream>>>(ea, o);
         ctx->launches++;
     }
