@@ -20,6 +20,17 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     batch = None if kw.get("filter_adapter") else (int(rng.choice([0, 257])) or None)
     try:
         both(r1, r2, lambda: Options(**kw), batch_records=batch)
+        # pieces mode and the pipelined entry points (submit / run / wait) on the same input: same streams, same statistics
+        sg, st_g = both(r1, r2, lambda: Options(**kw), batch_records=None, check_results=False)
+        with Engine(Options(**kw)) as pc:
+            pc.set_output_pieces(True)
+            pc.autodetect(r1, r2)
+            t = pc.submit(r1, r2, 0, True)
+            pc.run(t)
+            res = pc.wait(t)
+            ex = res.expand(r1, r2)
+            assert [bytes(x) for x in ex] == [bytes(x) for x in sg], "pieces (pipelined) differ from byte mode"
+            assert not pc.stats().diff(st_g), "statistics of the pieces run differ"
         # k-mer rarefaction over the same reads (one batch; k and the sampling cadence vary)
         k = int(rng.choice([2, 5, 11, 21, 31]))
         split = int(rng.choice([100, 400, 100000]))
