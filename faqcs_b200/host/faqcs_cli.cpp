@@ -655,7 +655,7 @@ static void write_all(int fd, const uint8_t *p, size_t n)
     }
 }
 // --gz_out: one batch of a stream as BGZF members (<= 0xff00 bytes of text each, SAM specification 4.1), deflated by
-// kIoThreads threads into per-thread buffers and written in order.  Concatenated members are a valid gzip file; the empty
+// several threads into per-thread buffers and written in order.  Concatenated members are a valid gzip file; the empty
 // end-of-file member is written when the stream is closed.
 static void bgzf_member(vector<uint8_t> &out, z_stream &zs, const uint8_t *p, size_t n)
 {
@@ -680,7 +680,7 @@ static void write_bgzf(int fd, const uint8_t *p, size_t n)
 {
     constexpr size_t kBlock = 0xff00;
     const size_t blocks = (n + kBlock - 1) / kBlock;
-    const int nt = (int)max<size_t>(1, min<size_t>(kIoThreads, blocks / 8));
+    const int nt = (int)max<size_t>(1, min<size_t>((size_t)inflate_threads(), blocks / 8));      // deflate is the slow side: as many threads as the readers get
     vector<vector<uint8_t>> part(nt);
     vector<int> bad(nt, 0);
     vector<thread> th;
