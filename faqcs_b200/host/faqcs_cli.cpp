@@ -10,6 +10,7 @@
 #include <getopt.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/uio.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -618,6 +619,7 @@ struct Run {
     fq_options fopt{};
     uint64_t records_done = 0, batches_done = 0;
     bool first_batch = true;
+    bool pieces_mode = false;       // streams come back as pieces of the input buffers + literal bytes (fq_set_output_pieces)
     explicit Run(Cli &opt) : o(opt) {}
     void check(fq_status st, fq_ctx *c = nullptr) { if (st != FQ_OK) throw string(fq_last_error(c ? c : ctx)); }
     // the other devices' contexts, once the quality offset is known (A1 runs once, before sharding: SURVEY 8(e))
@@ -630,6 +632,7 @@ struct Run {
             fq_ctx *c = nullptr;
             if (fq_create(&f, o.devices[ctxs.size()], &c) != FQ_OK) throw string(fq_last_error(nullptr));
             ctxs.push_back(c);
+            if (pieces_mode) check(fq_set_output_pieces(c, 1), c);
         }
     }
     void set_quality_everywhere(int q) { for (fq_ctx *c : ctxs) check(fq_set_quality(c, q), c); }
@@ -738,6 +741,78 @@ static void write_mapped(int fd, const uint8_t *p, size_t n)
     lseek(fd, base + (off_t)n, SEEK_SET);
 }
 
+// Pieces mode (fq_set_output_pieces): a stream of one batch is a list of pieces of the batch's own input buffers plus the
+// literal bytes of the records that changed; only those crossed the PCIe link on the way back.  The file range is reserved and
+// mapped like write_mapped's; kIoThreads threads copy disjoint runs of pieces (a first pass gives every run its offset).
+static void write_pieces(int fd, const fq_out_piece *pc, size_t n_pc, const uint8_t *const src[3], size_t total)
+{
+    if (total == 0) return;
+    struct stat st;
+    const off_t base = lseek(fd, 0, SEEK_CUR);
+    const bool mappable = base >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size == base && total >= (size_t)kIoThreads &&
+                          posix_fallocate(fd, base, (off_t)total) == 0;
+    uint8_t *dst = nullptr;
+    void *m = MAP_FAILED;
+    size_t map_len = 0;
+    if (mappable) {
+        const long page = sysconf(_SC_PAGESIZE);
+        const off_t map_off = base / page * page;
+        map_len = (size_t)(base - map_off) + total;
+        m = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, map_off);
+        if (m == MAP_FAILED) { if (ftruncate(fd, base) != 0) throw "I/O error while writing the trimmed reads"; }
+        else dst = (uint8_t *)m + (base - map_off);
+    }
+    if (!dst) {                                   // pipes, odd files: gather the pieces with writev
+        vector<iovec> iov;
+        iov.reserve(1024);
+        auto flush = [&] {
+            size_t done = 0;
+            while (done < iov.size()) {
+                ssize_t w = writev(fd, iov.data() + done, (int)min<size_t>(iov.size() - done, 1024));
+                if (w < 0) { if (errno == EINTR) continue; throw "I/O error while writing the trimmed reads"; }
+                while (w > 0 && done < iov.size()) {
+                    if ((size_t)w >= iov[done].iov_len) { w -= (ssize_t)iov[done].iov_len; ++done; }
+                    else { iov[done].iov_base = (uint8_t *)iov[done].iov_base + w; iov[done].iov_len -= (size_t)w; w = 0; }
+                }
+            }
+            iov.clear();
+        };
+        for (size_t k = 0; k < n_pc; ++k) {
+            iov.push_back(iovec{(void *)(src[pc[k].source] + pc[k].offset), pc[k].length});
+            if (iov.size() == 1024) flush();
+        }
+        flush();
+        return;
+    }
+    const int nt = kIoThreads;
+    size_t part_bytes[kIoThreads] = {0};
+    {
+        vector<thread> th;
+        for (int t = 0; t < nt; ++t) {
+            auto job = [&, t] { size_t b = 0; for (size_t k = n_pc * t / nt; k < n_pc * (t + 1) / nt; ++k) b += pc[k].length; part_bytes[t] = b; };
+            if (t + 1 < nt) th.emplace_back(job); else job();
+        }
+        for (thread &x : th) x.join();
+    }
+    size_t start[kIoThreads + 1] = {0};
+    for (int t = 0; t < nt; ++t) start[t + 1] = start[t] + part_bytes[t];
+    const bool consistent = start[nt] == total;
+    if (consistent) {
+        vector<thread> th;
+        for (int t = 0; t < nt; ++t) {
+            auto job = [&, t] {
+                uint8_t *d = dst + start[t];
+                for (size_t k = n_pc * t / nt; k < n_pc * (t + 1) / nt; ++k) { memcpy(d, src[pc[k].source] + pc[k].offset, pc[k].length); d += pc[k].length; }
+            };
+            if (t + 1 < nt) th.emplace_back(job); else job();
+        }
+        for (thread &x : th) x.join();
+    }
+    munmap(m, map_len);
+    if (!consistent) throw "pieces of a stream do not add up to its size";
+    lseek(fd, base + (off_t)total, SEEK_SET);
+}
+
 static double now_s() { return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // process_paired (FaQCs.cpp:153-538) / process_unpaired (:540-757): read -> GPU -> four ordered writers.
@@ -767,8 +842,12 @@ static void process(Run &R, bool paired)
         if (!o.trimmed_discard_file.empty()) fout[3] = open_out(o.trimmed_discard_file, "discarded sequences");
     }
     const size_t cap = o.batch_mb << 20;
-    uint8_t *buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [slot][mate], pinned
-    for (int k = 0; k < 2; ++k)
+    // Pieces mode: the writers copy most output bytes out of the batch's own INPUT buffers, so a buffer cycles through
+    // read -> GPU -> write before it is filled again: three slots instead of two.
+    const bool pieces_mode = R.pieces_mode;
+    const int n_slots = pieces_mode ? 3 : 2;
+    uint8_t *buf[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};      // [slot][mate], pinned
+    for (int k = 0; k < n_slots; ++k)
         for (int m = 0; m < n_mates; ++m)
             if (!(buf[k][m] = (uint8_t *)fq_host_alloc(cap))) throw "unable to allocate pinned host memory";
     // Q3 and the k-mer rarefaction curve (points are taken where trim() calls end): keep batches on 32768-record boundaries
@@ -787,6 +866,7 @@ static void process(Run &R, bool paired)
         for (int m = 0; m < n_mates; ++m) post_fill(0, m, 0);
         uint64_t first_index = 0, pending_ticket = 0;
         fq_ctx *pending_ctx = nullptr;
+        const uint8_t *pending_src[2] = {nullptr, nullptr};
         bool have_pending = false;
         auto drain = [&](fq_ctx *c, uint64_t ticket) {
             fq_batch_out out;
@@ -797,10 +877,16 @@ static void process(Run &R, bool paired)
                     const size_t n = out.bytes[s];
                     const int fd = fout[s];
                     const bool gz = o.gz_out;
-                    writers[s].post([fd, p, n, gz] { if (gz) write_bgzf(fd, p, n); else write_mapped(fd, p, n); });
+                    if (pieces_mode) {
+                        const fq_out_piece *pc = out.pieces[s];
+                        const size_t n_pc = out.n_pieces[s];
+                        const uint8_t *s0 = pending_src[0], *s1 = pending_src[1];
+                        writers[s].post([fd, pc, n_pc, s0, s1, p, n] { const uint8_t *const src3[3] = {s0, s1, p}; write_pieces(fd, pc, n_pc, src3, n); });
+                    } else writers[s].post([fd, p, n, gz] { if (gz) write_bgzf(fd, p, n); else write_mapped(fd, p, n); });
                 }
         };
-        for (int slot = 0;; slot ^= 1) {
+        for (int slot = 0;; slot = (slot + 1) % n_slots) {
+            const int next = (slot + 1) % n_slots;
             double t0 = now_s();
             for (int m = 0; m < n_mates; ++m) readers[m].wait_idle();
             t_read += now_s() - t0;
@@ -825,12 +911,15 @@ static void process(Run &R, bool paired)
                 if (o.kmer_rarefaction && nrec % FQ_REF_BATCH) throw "--kmer_rarefaction needs batches of at least 32768 records: raise --batch_mb";
                 use1 = offset_after_line(buf[slot][0], n1, filled[0].lines, 4 * nrec);
                 if (paired) use2 = offset_after_line(buf[slot][1], n2, filled[1].lines, 4 * nrec);
-                // the tails open the next batch; its buffers are free (their batch has been run)
-                memcpy(buf[slot ^ 1][0], buf[slot][0] + use1, n1 - use1);
-                post_fill(slot ^ 1, 0, n1 - use1);
+                // the tails open the next batch; its buffers are free (their batch has been run -- and, in pieces mode, written:
+                // the writers of the batch that used them read their pieces from these buffers)
+                if (pieces_mode)
+                    for (Worker &w : writers) w.wait_idle();
+                memcpy(buf[next][0], buf[slot][0] + use1, n1 - use1);
+                post_fill(next, 0, n1 - use1);
                 if (paired) {
-                    memcpy(buf[slot ^ 1][1], buf[slot][1] + use2, n2 - use2);
-                    post_fill(slot ^ 1, 1, n2 - use2);
+                    memcpy(buf[next][1], buf[slot][1] + use2, n2 - use2);
+                    post_fill(next, 1, n2 - use2);
                 }
             }
             if (R.first_batch) {
@@ -887,6 +976,8 @@ static void process(Run &R, bool paired)
                 t_gpu += now_s() - t0;
                 pending_ticket = ticket;
                 pending_ctx = c;
+                pending_src[0] = p1;
+                pending_src[1] = p2;
                 have_pending = true;
                 first_index += pc.nrec;
             }
@@ -903,7 +994,7 @@ static void process(Run &R, bool paired)
     if (timing)
         cerr << "[timing] waiting for readers " << t_read << " s, cut/autodetect " << t_cut << " s, submit+run+wait " << t_gpu
              << " s, waiting for writers " << t_write_wait << " s" << endl;
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
         for (int m = 0; m < 2; ++m) fq_host_free(buf[k][m]);
     for (int s = 0; s < 4; ++s)
         if (fout[s] >= 0) {
@@ -1120,6 +1211,9 @@ int main(int argc, char *argv[])
         R.ctx = ctx;
         R.ctxs.push_back(ctx);
         R.fopt = f;
+        // plain output files: most bytes are written straight from the input buffers (FAQCS_B200_CLI_BYTES=1: byte streams)
+        R.pieces_mode = !o.gz_out && !o.qc_only && getenv("FAQCS_B200_CLI_BYTES") == nullptr;
+        if (R.pieces_mode) R.check(fq_set_output_pieces(ctx, 1));
         if (o.has_paired()) {
             process(R, true);
             R.check(fq_kmer_end_pass(ctx));        // FaQCs.cpp:518-537
