@@ -406,8 +406,10 @@ __global__ void __launch_bounds__(256, FQ_ADAPTER_MIN_CTAS) k_adapter(const Adap
             const int n_windows = ((int)L + S + 31) >> 5;
             const SweepCtx sc{rx, rstride, s_seg, s_segp, s_seginfo, s_wbound, s_cand, a.n_seg, lane, S, n_windows, full, a.sweep_pure != 0};
             const bool fast = full && a.sweep_pure;
-            if (fast)
+            if (fast) {
                 for (uint32_t w = lane; w < (a.n_seg + 31) >> 5; w += 32) s_segflag[w] = 0;
+                __syncwarp();           // lane 0 ORs into these words
+            }
             if (n_windows <= 5) sweep_windows<5>(sc, 0, s_segflag);
             else
                 for (int w0 = 0; w0 < n_windows; w0 += 6) sweep_windows<6>(sc, w0, s_segflag);
