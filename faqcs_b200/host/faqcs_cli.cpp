@@ -778,6 +778,7 @@ static void write_pieces(int fd, const fq_out_piece *pc, size_t n_pc, const uint
             iov.clear();
         };
         for (size_t k = 0; k < n_pc; ++k) {
+            if (pc[k].source > 2) throw "pieces of a stream do not add up to its size";
             iov.push_back(iovec{(void *)(src[pc[k].source] + pc[k].offset), pc[k].length});
             if (iov.size() == 1024) flush();
         }
@@ -789,7 +790,11 @@ static void write_pieces(int fd, const fq_out_piece *pc, size_t n_pc, const uint
     {
         vector<thread> th;
         for (int t = 0; t < nt; ++t) {
-            auto job = [&, t] { size_t b = 0; for (size_t k = n_pc * t / nt; k < n_pc * (t + 1) / nt; ++k) b += pc[k].length; part_bytes[t] = b; };
+            auto job = [&, t] {
+                size_t b = 0;
+                for (size_t k = n_pc * t / nt; k < n_pc * (t + 1) / nt; ++k) b += pc[k].source < 3 ? pc[k].length : total + 1;     // unknown source: fail below
+                part_bytes[t] = b;
+            };
             if (t + 1 < nt) th.emplace_back(job); else job();
         }
         for (thread &x : th) x.join();

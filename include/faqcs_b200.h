@@ -330,8 +330,8 @@ fq_status fq_merge_stats(fq_ctx *dst, fq_ctx *src);
 float     fq_last_allreduce_ms(const fq_ctx *ctx);
 
 /*
- * k-mer rarefaction (--kmer_rarefaction with --qc_only).  Replaces update_kmer (trim.cpp:887-931, called from
- * trim_read, trim.cpp:260-262), the sampling block at the end of trim() (trim.cpp:157-185) and the end-of-pass code of
+ * k-mer rarefaction (--kmer_rarefaction).  Replaces update_kmer (trim.cpp:887-931, called from
+ * trim_read: on the raw read under --qc_only, trim.cpp:260-262, on what is left of a surviving read otherwise, trim.cpp:545-547), the sampling block at the end of trim() (trim.cpp:157-185) and the end-of-pass code of
  * process_paired / process_unpaired (FaQCs.cpp:518-537, 737-756).  The canonical k-mers of the raw reads go to a hash table
  * in device memory while the curve is being collected (one table per pass over an input, as in the reference); the points
  * of the curve are taken where the reference takes them -- at the end of the trim() call (32768 reads of one mate) whose
@@ -340,7 +340,8 @@ float     fq_last_allreduce_ms(const fq_ctx *ctx);
  *   fq_kmer_enable    once, before the first batch: k (Options::kmer, 2..31), Options::split_size, Options::num_subsample
  *                     (already doubled where the reference doubles it, options.cpp:506-523)
  *   fq_kmer_end_pass  after the last batch of an input (paired files, then the unpaired file)
- *   fq_kmer_results   PlotInfo::kmer_rarefaction and PlotInfo::kmer_frequency_histogram (what plot.cpp:683-733 prints)
+ *   fq_kmer_results   PlotInfo::kmer_rarefaction and PlotInfo::kmer_frequency_histogram (what plot.cpp:683-733 prints);
+ *                     the view's pointers belong to the context and stay valid until its next fq_kmer_* call
  */
 typedef struct fq_rarefaction {
     uint64_t num_seq;          /* TOTAL_NUMBER when the point was taken */
