@@ -127,7 +127,7 @@ struct fq_ctx {
         uint32_t pass_counted = 0;                 // calls [0, pass_counted) fed the table
         std::vector<std::pair<uint32_t, uint64_t>> pass_points;   // (call, TOTAL_NUMBER): distinct / total filled in at the end of the pass
         unsigned long long cap = 0, occupied_bound = 0;
-        DevBuf d_keys, d_count, d_first, d_call_total, d_call_distinct, d_small, d_big, d_scalars;
+        DevBuf d_slots, d_call_total, d_call_distinct, d_small, d_big, d_scalars;
         std::vector<uint64_t> flat;                // fq_kmer_view::frequency
     } kmer;
 
@@ -387,7 +387,7 @@ fq_status map_device_error(fq_ctx *ctx, const BatchInfo &hi)
 // ---- k-mer rarefaction: host side of fq_kmer.cuh ---------------------------------------------------------
 KmerTable kmer_table_of(fq_ctx::Kmer &K)
 {
-    return KmerTable{K.d_keys.as<unsigned long long>(), K.d_count.as<uint32_t>(), K.d_first.as<uint32_t>(), K.cap - 1};
+    return KmerTable{K.d_slots.as<KmerSlot>(), K.cap - 1};
 }
 
 // (Re)allocate the table for at least `slots` slots (a power of two), keeping its entries.
@@ -397,17 +397,15 @@ fq_status kmer_resize(fq_ctx *ctx, unsigned long long slots)
     unsigned long long cap = 1ull << 20;
     while (cap < slots) cap <<= 1;
     if (cap <= K.cap) return FQ_OK;
-    DevBuf nk, nc, nf;
-    CK(nk.ensure(cap * 8));
-    CK(nc.ensure(cap * 4));
-    CK(nf.ensure(cap * 4));
-    KmerTable to{nk.as<unsigned long long>(), nc.as<uint32_t>(), nf.as<uint32_t>(), cap - 1};
+    DevBuf ns;
+    CK(ns.ensure(cap * sizeof(KmerSlot)));
+    KmerTable to{ns.as<KmerSlot>(), cap - 1};
     k_kmer_clear<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(to);
     if (K.cap) k_kmer_rehash<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(kmer_table_of(K), to);
     ctx->launches += K.cap ? 2 : 1;
     CK(cudaStreamSynchronize(ctx->stream));
-    K.d_keys.release(); K.d_count.release(); K.d_first.release();
-    K.d_keys = nk; K.d_count = nc; K.d_first = nf;
+    K.d_slots.release();
+    K.d_slots = ns;
     K.cap = cap;
     return FQ_OK;
 }
@@ -852,7 +850,7 @@ void fq_destroy(fq_ctx *ctx)
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     ctx->d_tile.release(); ctx->d_info.release(); ctx->d_stats.release(); ctx->d_rows.release();
     ctx->d_adp_codes.release(); ctx->d_adp_off.release(); ctx->d_adp_or.release();
-    for (DevBuf *b : {&ctx->kmer.d_keys, &ctx->kmer.d_count, &ctx->kmer.d_first, &ctx->kmer.d_call_total, &ctx->kmer.d_call_distinct, &ctx->kmer.d_small,
+    for (DevBuf *b : {&ctx->kmer.d_slots, &ctx->kmer.d_call_total, &ctx->kmer.d_call_distinct, &ctx->kmer.d_small,
                       &ctx->kmer.d_big, &ctx->kmer.d_scalars}) b->release();
     ctx->h_stats.release();
     if (ctx->h_info) cudaFreeHost(ctx->h_info);

@@ -8,7 +8,7 @@
 // distinct k-mers, k-mer instances) (trim.cpp:157-185); at the end of the pass it turns the table into a histogram of
 // counts (FaQCs.cpp:518-521, 737-740).
 //
-// Here the table is an open-addressing hash table in HBM (64-bit keys, linear probing).  Every slot also remembers the
+// Here the table is an open-addressing hash table in HBM (16-byte slots, linear probing).  Every slot also remembers the
 // FIRST trim() call that produced its k-mer, and every call its number of instances, so all points of the curve follow from
 // the final table: distinct(c) = #{slots first seen in a call <= c}, total(c) = sum of instances of the calls <= c.
 // One thread walks one read with the same rolling update as the reference.
@@ -21,10 +21,13 @@ constexpr unsigned long long kKmerEmpty = ~0ull;
 constexpr uint32_t kKmerMaxCalls = 1u << 16;         // trim() calls of one pass while the curve is collected
 constexpr uint32_t kKmerSmallCounts = 1u << 16;      // counts below this go to a dense histogram, larger ones to a list
 
+struct KmerSlot {                   // 16 bytes: key, count and first call of a k-mer share one 32-byte sector
+    unsigned long long key;         // canonical k-mer or kKmerEmpty
+    uint32_t count;
+    uint32_t first_call;            // smallest call index that inserted the k-mer
+};
 struct KmerTable {
-    unsigned long long *keys;       // [cap] canonical k-mer or kKmerEmpty
-    uint32_t *count;                // [cap]
-    uint32_t *first_call;           // [cap] smallest call index that inserted the k-mer
+    KmerSlot *slots;                // [cap]
     unsigned long long cap_mask;    // cap - 1 (cap is a power of two)
 };
 
@@ -52,10 +55,13 @@ __device__ __forceinline__ void kmer_insert(const KmerTable &T, unsigned long lo
 {
     unsigned long long slot = kmer_hash(key) & T.cap_mask;
     for (;;) {
-        const unsigned long long prev = atomicCAS(&T.keys[slot], kKmerEmpty, key);
+        KmerSlot *const p = &T.slots[slot];
+        // most k-mers of real data are already in the table: look before claiming (a key never changes once it is set)
+        unsigned long long prev = *reinterpret_cast<volatile unsigned long long *>(&p->key);
+        if (prev == kKmerEmpty) prev = atomicCAS(&p->key, kKmerEmpty, key);
         if (prev == kKmerEmpty || prev == key) {
-            atomicAdd(&T.count[slot], 1u);
-            atomicMin(&T.first_call[slot], call);
+            atomicAdd(&p->count, 1u);
+            if (call < *reinterpret_cast<volatile uint32_t *>(&p->first_call)) atomicMin(&p->first_call, call);
             return;
         }
         slot = (slot + 1) & T.cap_mask;
@@ -115,9 +121,7 @@ __global__ void __launch_bounds__(256) k_kmer(const KmerArgs a)
 __global__ void __launch_bounds__(256) k_kmer_clear(KmerTable T)
 {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= T.cap_mask; i += (unsigned long long)gridDim.x * blockDim.x) {
-        T.keys[i] = kKmerEmpty;
-        T.count[i] = 0;
-        T.first_call[i] = 0xffffffffu;
+        T.slots[i] = KmerSlot{kKmerEmpty, 0u, 0xffffffffu};
     }
 }
 
@@ -125,14 +129,14 @@ __global__ void __launch_bounds__(256) k_kmer_clear(KmerTable T)
 __global__ void __launch_bounds__(256) k_kmer_rehash(KmerTable from, KmerTable to)
 {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= from.cap_mask; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long key = from.keys[i];
-        if (key == kKmerEmpty) continue;
-        unsigned long long slot = kmer_hash(key) & to.cap_mask;
+        const KmerSlot e = from.slots[i];
+        if (e.key == kKmerEmpty) continue;
+        unsigned long long slot = kmer_hash(e.key) & to.cap_mask;
         for (;;) {
-            const unsigned long long prev = atomicCAS(&to.keys[slot], kKmerEmpty, key);
+            const unsigned long long prev = atomicCAS(&to.slots[slot].key, kKmerEmpty, e.key);
             if (prev == kKmerEmpty) {
-                to.count[slot] = from.count[i];
-                to.first_call[slot] = from.first_call[i];
+                to.slots[slot].count = e.count;
+                to.slots[slot].first_call = e.first_call;
                 break;
             }
             slot = (slot + 1) & to.cap_mask;
@@ -146,9 +150,10 @@ __global__ void __launch_bounds__(256) k_kmer_summarize(KmerTable T, unsigned lo
 {
     unsigned long long mine = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= T.cap_mask; i += (unsigned long long)gridDim.x * blockDim.x) {
-        if (T.keys[i] == kKmerEmpty) continue;
+        const KmerSlot e = T.slots[i];
+        if (e.key == kKmerEmpty) continue;
         ++mine;
-        const uint32_t c = T.count[i], f = T.first_call[i];
+        const uint32_t c = e.count, f = e.first_call;
         if (f < kKmerMaxCalls) atomicAdd(&call_distinct[f], 1ull);
         if (c < kKmerSmallCounts) atomicAdd(&small_hist[c], 1ull);
         else {
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(256) k_kmer_count(KmerTable T, unsigned long l
 {
     unsigned long long mine = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= T.cap_mask; i += (unsigned long long)gridDim.x * blockDim.x)
-        mine += T.keys[i] != kKmerEmpty;
+        mine += T.slots[i].key != kKmerEmpty;
 #pragma unroll
     for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_distinct, mine);
