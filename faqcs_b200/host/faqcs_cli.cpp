@@ -14,6 +14,8 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include "pgzip.hpp"
+
 #include <algorithm>
 #include <cerrno>
 #include <chrono>
@@ -400,10 +402,10 @@ static size_t count_newlines(const uint8_t *buf, size_t n)
 // Plain files are read with read(2) straight into the pinned batch buffer; gzip input (magic 1f 8b) goes
 // through zlib like the reference's reader (fastq.cpp:8-30) -- except blocked gzip (BGZF: bgzip, bcl-convert, samtools),
 // whose members carry their compressed size in the header and are inflated by several threads at once.
-static int inflate_threads()      // per input file: half the cores, at most 16
+static int g_input_files = 2;      // files read at the same time (two mates, or one file of unpaired reads)
+static int inflate_threads()      // per input file: the cores divided among the files, 2 .. 32
 {
-    static const int v = (int)min(16u, max(2u, thread::hardware_concurrency() / 2));
-    return v;
+    return (int)min(32u, max(2u, thread::hardware_concurrency() / (unsigned)max(1, g_input_files)));
 }
 
 // A BGZF member at p[0..avail): its total size, or 0 if the bytes are not a complete BGZF header (RFC 1952 member with
@@ -441,9 +443,139 @@ struct Source {
             csize = st.st_size;
             return true;
         }
-        if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b) return open_zlib();
+        if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b) {
+            // ordinary gzip: several threads enter the deflate stream at block boundaries (pgzip.hpp); FAQCS_B200_PGZIP=0: one zlib stream
+            const char *e = getenv("FAQCS_B200_PGZIP");
+            // (FAQCS_B200_PGZIP_MIN / _PIECE / _SPAN: smallest file, smallest piece, bytes per round -- the tests shrink them)
+            const char *m = getenv("FAQCS_B200_PGZIP_MIN"), *pc = getenv("FAQCS_B200_PGZIP_PIECE"), *sp = getenv("FAQCS_B200_PGZIP_SPAN");
+            if (pc) pz_min_piece = (size_t)strtoull(pc, nullptr, 10);
+            if (sp) pz_span = (size_t)strtoull(sp, nullptr, 10);
+            if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= (off_t)(m ? strtoull(m, nullptr, 10) : (4u << 20)) && !(e && e[0] == '0')) {
+                pgzip = true;
+                csize = st.st_size;
+                pz_window.assign(pgz::kWin, 0);
+                return true;
+            }
+            return open_zlib();
+        }
         detect_sliced();
         return true;
+    }
+    // ---- ordinary gzip, inflated by several threads (pgzip.hpp) ----
+    bool pgzip = false, pz_in_member = false;
+    size_t pz_bit = 0;                    // first undecoded bit of the member's deflate stream, relative to byte cpos
+    size_t pz_window_len = 0;             // valid bytes at the end of pz_window (output of this member so far, at most 32 KiB)
+    vector<uint8_t> pz_window;            // the last 32 KiB of output
+    deque<pgz::Bytes> pz_pend;            // decoded pieces not yet handed out (the front one from pz_pend_off on)
+    size_t pz_pend_off = 0;
+    size_t pz_span = 0;                   // compressed bytes looked at per round
+    size_t pz_min_piece = 256u << 10;     // a thread gets at least this much compressed data
+    uint32_t pz_crc = 0;
+    uint64_t pz_isize = 0;
+    void pz_read(size_t want)
+    {
+        cbuf.resize(want);
+        for (size_t done = 0; done < want;) {
+            const ssize_t got = pread(fd, cbuf.data() + done, want - done, cpos + (off_t)done);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) throw "fastq.cpp:next_read: Unable to read header";
+            done += (size_t)got;
+        }
+    }
+    // the header of the member at cpos (RFC 1952); false: no further member (end of file, or bytes that are not gzip: ignored as gzread does)
+    bool pz_member_header()
+    {
+        const size_t want = (size_t)min<off_t>(csize - cpos, 1 << 16);
+        if (want < 18) return false;
+        pz_read(want);
+        const uint8_t *h = cbuf.data();
+        if (h[0] != 0x1f || h[1] != 0x8b) return false;
+        if (h[2] != 8 || (h[3] & 0xe0)) throw "fastq.cpp:next_read: Unable to read header";
+        size_t p = 10;
+        if (h[3] & 4) { if (p + 2 > want) return false; p += 2 + (h[p] | (size_t)h[p + 1] << 8); }
+        if (h[3] & 8) { while (p < want && h[p]) ++p; ++p; }
+        if (h[3] & 16) { while (p < want && h[p]) ++p; ++p; }
+        if (h[3] & 2) p += 2;
+        if (p >= want) throw "fastq.cpp:next_read: Unable to read header";
+        cpos += (off_t)p;
+        pz_bit = 0;
+        pz_window_len = 0;
+        pz_crc = (uint32_t)crc32(0L, Z_NULL, 0);
+        pz_isize = 0;
+        pz_in_member = true;
+        return true;
+    }
+    // one round: more decoded bytes into pz_pend (or eof)
+    void pz_produce()
+    {
+        if (!pz_in_member && (cpos >= csize || !pz_member_header())) { eof = true; return; }
+        const int threads = inflate_threads();
+        if (!pz_span) pz_span = max<size_t>((size_t)threads * (2u << 20), 8u << 20);
+        for (;;) {
+            const size_t want = (size_t)min<off_t>(csize - cpos, (off_t)pz_span);
+            pz_read(want);
+            pgz::Result R = pgz::inflate_parallel(cbuf.data(), want, pz_bit, pz_window, pz_window_len, threads, pz_min_piece);
+            if (R.error) throw "fastq.cpp:next_read: Unable to read header";
+            size_t total = 0;
+            for (const pgz::Piece &pc : R.pieces) total += pc.out.size();
+            if (total == 0 && !R.stream_end) {
+                // not one whole block in this span: look at more of the file, or the stream is cut short
+                if ((off_t)want >= csize - cpos) throw "fastq.cpp:next_read: Unable to read header";
+                pz_span *= 2;
+                continue;
+            }
+            // CRC-32 of the pieces in parallel, combined in order (RFC 1952 trailer)
+            vector<uint32_t> crcs(R.pieces.size());
+            {
+                vector<thread> th;
+                for (size_t q = 0; q < R.pieces.size(); ++q)
+                    th.emplace_back([&, q] {
+                        uLong c = crc32(0L, Z_NULL, 0);
+                        const pgz::Bytes &o = R.pieces[q].out;
+                        for (size_t at = 0; at < o.size(); at += 1u << 30) c = crc32(c, o.data() + at, (uInt)min<size_t>(o.size() - at, 1u << 30));
+                        crcs[q] = (uint32_t)c;
+                    });
+                for (thread &x : th) x.join();
+            }
+            for (size_t q = 0; q < R.pieces.size(); ++q) {
+                pz_crc = (uint32_t)crc32_combine(pz_crc, crcs[q], (z_off_t)R.pieces[q].out.size());
+                if (R.pieces[q].out.size()) pz_pend.push_back(std::move(R.pieces[q].out));
+            }
+            pz_isize += total;
+            pz_window_len = min(pgz::kWin, pz_window_len + total);
+            cpos += (off_t)(R.end_bit >> 3);
+            pz_bit = R.end_bit & 7;
+            if (R.stream_end) {
+                if (csize - cpos < 8) throw "fastq.cpp:next_read: Unable to read header";
+                uint8_t t[8];
+                if (pread(fd, t, 8, cpos) != 8) throw "fastq.cpp:next_read: Unable to read header";
+                const uint32_t crc = t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+                const uint32_t isz = t[4] | (uint32_t)t[5] << 8 | (uint32_t)t[6] << 16 | (uint32_t)t[7] << 24;
+                if (crc != pz_crc || isz != (uint32_t)pz_isize) throw "fastq.cpp:next_read: Unable to read header";
+                cpos += 8;
+                pz_in_member = false;
+            }
+            return;
+        }
+    }
+    size_t fill_pgzip(uint8_t *buf, size_t have, size_t cap, size_t *new_lines)
+    {
+        size_t n = have;
+        while (n < cap) {
+            if (pz_pend.empty()) {
+                if (eof) break;
+                pz_produce();           // sets eof when the file holds no further member
+                continue;
+            }
+            const pgz::Bytes &front = pz_pend.front();
+            const size_t take = min(cap - n, front.size() - pz_pend_off);
+            memcpy(buf + n, front.data() + pz_pend_off, take);
+            pz_pend_off += take;
+            n += take;
+            if (pz_pend_off == front.size()) { pz_pend.pop_front(); pz_pend_off = 0; }
+        }
+        *new_lines += count_newlines(buf + have, n - have);
+        return n;
     }
     bool open_zlib()
     {
@@ -541,6 +673,7 @@ struct Source {
     {
         size_t n = have;
         if (bgzf) return fill_bgzf(buf, have, cap, new_lines);
+        if (pgzip) return fill_pgzip(buf, have, cap, new_lines);
         if (sliced) {
             const size_t want = (size_t)min<off_t>((off_t)(cap - have), size - pos);
             const int nt = want >= io_slice_min() && want >= (size_t)kIoThreads ? kIoThreads : 1;
@@ -828,6 +961,7 @@ static void process(Run &R, bool paired)
     Cli &o = R.o;
     const bool timing = getenv("FAQCS_B200_TIMING") != nullptr;
     const int n_mates = paired ? 2 : 1;
+    g_input_files = n_mates;
     Source src[2];
     if (paired) {
         if (!src[0].open(o.input_read1_file)) { cerr << "Unable to open " << o.input_read1_file << " for loading read one sequences" << endl; throw "I/O error"; }

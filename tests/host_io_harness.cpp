@@ -14,6 +14,7 @@ int main(int argc, char **argv)
         if (mode == "read") {
             Source s;
             if (!s.open(argv[2])) return 2;
+            const bool was_pgzip = s.pgzip, was_bgzf = s.bgzf;
             const size_t cap = (size_t)atoi(argv[4]) << 10;
             std::vector<uint8_t> buf(cap);
             FILE *f = fopen(argv[3], "wb");
@@ -28,7 +29,7 @@ int main(int argc, char **argv)
                 ++fills;
             }
             fclose(f);
-            printf("fills %zu lines %zu\n", fills, total_lines);
+            printf("fills %zu lines %zu mode %s\n", fills, total_lines, was_pgzip ? "pgzip" : was_bgzf ? "bgzf" : s.gz ? "zlib" : "plain");
             return 0;
         }
         if (mode == "write") {

@@ -327,3 +327,28 @@ def test_keep_unpaired_appends_the_single_end_pass():
     gz = run_cli_only({"-1": ("r1.fq", w.r1), "-2": ("r2.fq", w.r2), "-u": ("u.fq", u.r1)}, ["--keep_unpaired", "--gz_out"])
     assert gzip.decompress(gz["QC.unpaired.trimmed.fastq.gz"]) == want
     assert gzip.decompress(gz["QC.1.trimmed.fastq.gz"]) == both["QC.1.trimmed.fastq"]
+
+
+def test_ordinary_gzip_inputs_are_inflated_in_parallel():
+    """Ordinary gzip input of some size: several threads enter the deflate stream at block boundaries
+    (faqcs_b200/host/pgzip.hpp); mate 2 as two concatenated members.  Same files as the reference reading the same .gz."""
+    w = synth.c2(70000)
+    tmp = tempfile.mkdtemp(prefix="faqcs_pgz_")
+    try:
+        d2 = bytes(w.r2)
+        cut = d2.index(b"\n@", len(d2) // 3) + 1
+        z1, z2 = gzip.compress(bytes(w.r1), 6), gzip.compress(d2[:cut], 9) + gzip.compress(d2[cut:], 1)
+        assert len(z1) > (4 << 20) and len(z2) > (4 << 20)
+        p1, p2 = os.path.join(tmp, "r1.fastq.gz"), os.path.join(tmp, "r2.fastq.gz")
+        open(p1, "wb").write(z1)
+        open(p2, "wb").write(z2)
+        outs = {}
+        for tag, exe, more in (("ref", refcli.REF_BIN, []), ("gpu", CLI, ["--batch_mb", "9"])):
+            out = os.path.join(tmp, tag)
+            p = subprocess.run([exe, "-d", out, "-t", "2", "--debug", "-1", p1, "-2", p2, "--discard"] + more, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                               preexec_fn=lambda: signal.signal(signal.SIGPIPE, signal.SIG_IGN))
+            assert p.returncode == 0, (tag, p.stderr.decode(errors="replace")[-600:])
+            outs[tag] = {n: open(os.path.join(out, n), "rb").read() for n in sorted(os.listdir(out)) if not n.endswith(".pdf")}
+        assert_same_files(outs)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)

@@ -77,3 +77,60 @@ def test_blocked_gzip_writer_round_trips(harness, fastq, tmp_path):
     back = tmp_path / "back.bin"                      # and through the driver's own parallel reader
     p = subprocess.run([harness, "read", str(dst), str(back), "2048"], capture_output=True)
     assert p.returncode == 0 and back.read_bytes() == fastq
+
+
+# ---- ordinary gzip, inflated by several threads (faqcs_b200/host/pgzip.hpp) -----------------------------------------------
+@pytest.fixture(scope="module")
+def big_fastq():
+    return bytes(synth.c2(40000).r1)          # 13.6 MB: its gzip is above the 4 MiB below which the reader stays with zlib
+
+
+def _shape(d, name):
+    """(gzip bytes, what they inflate to) -- only the requested one is built."""
+    import numpy as np
+    tiny = b"@x\nACGT\n+\nIIII\n"
+    if name.startswith("level"):
+        return gzip.compress(d, int(name[5:])), d
+    if name == "two_members":
+        return gzip.compress(d[:6_000_000], 6) + gzip.compress(d[6_000_000:], 1), d
+    if name == "member_then_tiny_member":
+        return gzip.compress(d, 6) + gzip.compress(tiny, 6), d + tiny
+    if name == "trailing_zeros":
+        return gzip.compress(d, 6) + b"\0" * 100, d
+    if name == "full_flush_inside":
+        co = zlib.compressobj(6, zlib.DEFLATED, 31)
+        return co.compress(d[:7_000_000]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(d[7_000_000:]) + co.flush(), d
+    if name == "incompressible":                  # stored blocks: nothing to enter, one thread inflates it all
+        rnd = np.random.default_rng(1).integers(0, 256, size=6_000_000, dtype=np.uint8).tobytes()
+        return gzip.compress(rnd, 6), rnd
+    if name == "stored_level0":
+        return gzip.compress(d[:8_000_000], 0), d[:8_000_000]
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("shape", ["level1", "level6", "level9", "two_members", "member_then_tiny_member", "trailing_zeros", "full_flush_inside",
+                                   "incompressible", "stored_level0"])
+def test_parallel_gzip_reader_delivers_the_file(harness, big_fastq, tmp_path, shape):
+    z, want = _shape(big_fastq, shape)
+    src, dst = tmp_path / "in.gz", tmp_path / "out.bin"
+    src.write_bytes(z)
+    for buffer_kib, env in ((3000, {}), (65536, {}), (65536, {"FAQCS_B200_PGZIP": "0"})):
+        p = subprocess.run([harness, "read", str(src), str(dst), str(buffer_kib)], capture_output=True, env=dict(os.environ, **env))
+        assert p.returncode == 0, p.stderr.decode()
+        assert dst.read_bytes() == want
+        assert (b"mode zlib" if env else b"mode pgzip") in p.stdout
+
+
+def test_parallel_gzip_reader_rejects_damage(harness, big_fastq, tmp_path):
+    z = bytearray(gzip.compress(big_fastq, 6))
+    for where, what in ((len(z) // 2, "a flipped byte in the deflate stream"), (len(z) - 6, "a wrong CRC-32"), (len(z) - 2, "a wrong length")):
+        bad = bytearray(z)
+        bad[where] ^= 0x41
+        src = tmp_path / "bad.gz"
+        src.write_bytes(bytes(bad))
+        p = subprocess.run([harness, "read", str(src), str(tmp_path / "out.bin"), "65536"], capture_output=True)
+        assert p.returncode == 5 and b"Unable to read" in p.stderr, what
+    src = tmp_path / "cut.gz"
+    src.write_bytes(bytes(z[:len(z) * 2 // 3]))                          # truncated file
+    p = subprocess.run([harness, "read", str(src), str(tmp_path / "out.bin"), "65536"], capture_output=True)
+    assert p.returncode == 5
