@@ -196,13 +196,14 @@ inline Result inflate_parallel(const uint8_t *comp, size_t n, size_t start_bit, 
     const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, (n - (start_bit >> 3)) / std::max<size_t>(min_piece, 64)));   // >= 256 KiB per piece
     std::vector<size_t> start(T, ~(size_t)0);
     start[0] = start_bit;
-    const size_t span = (total_bits - start_bit) / T;
+    // the first piece knows its window and is inflated once, the others twice: it gets two shares of the span
+    const size_t span = (total_bits - start_bit) / (T + 1);
     {   // 1. entry points of the pieces
         std::vector<std::thread> th;
         for (int i = 1; i < T; ++i)
             // (blocks of a FASTQ file are tens of KiB of compressed data: a piece whose first quarter holds no entry point is left
             // to the piece in front of it)
-            th.emplace_back([&, i] { start[i] = find_block_start(comp, n, (start_bit + span * i + 7) & ~(size_t)7, start_bit + span * i + span / 4, D.A); });
+            th.emplace_back([&, i] { start[i] = find_block_start(comp, n, (start_bit + span * (i + 1) + 7) & ~(size_t)7, start_bit + span * (i + 1) + span / 4, D.A); });
         for (auto &t : th) t.join();
     }
     std::vector<int> idx;           // pieces with an entry point, in order
