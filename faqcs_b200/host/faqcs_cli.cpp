@@ -519,8 +519,17 @@ struct Source {
             size_t total = 0;
             for (const pgz::Piece &pc : R.pieces) total += pc.out.size();
             if (total == 0 && !R.stream_end) {
-                // not one whole block in this span: look at more of the file, or the stream is cut short
-                if ((off_t)want >= csize - cpos) throw "fastq.cpp:next_read: Unable to read header";
+                // not one whole block in this span: look at more of the file -- or the file is cut short: what one zlib stream
+                // still gets out of it is handed out and the input ends there, as it does for gzread / gzgets (fastq.cpp:8-30)
+                if ((off_t)want >= csize - cpos) {
+                    pgz::Bytes tail;
+                    if (!pgz::inflate_truncated_tail(cbuf.data(), want, pz_bit, pz_window.data() + (pgz::kWin - pz_window_len), pz_window_len, tail))
+                        throw "fastq.cpp:next_read: Unable to read header";
+                    if (tail.size()) pz_pend.push_back(std::move(tail));
+                    cpos = csize;
+                    pz_in_member = false;
+                    return;
+                }
                 pz_span *= 2;
                 continue;
             }
@@ -546,7 +555,7 @@ struct Source {
             cpos += (off_t)(R.end_bit >> 3);
             pz_bit = R.end_bit & 7;
             if (R.stream_end) {
-                if (csize - cpos < 8) throw "fastq.cpp:next_read: Unable to read header";
+                if (csize - cpos < 8) { cpos = csize; pz_in_member = false; return; }      // the file ends inside the trailer: cut short, as above
                 uint8_t t[8];
                 if (pread(fd, t, 8, cpos) != 8) throw "fastq.cpp:next_read: Unable to read header";
                 const uint32_t crc = t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;

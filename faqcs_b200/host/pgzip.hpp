@@ -148,6 +148,39 @@ inline End inflate_from(const uint8_t *comp, size_t n, size_t start_bit, size_t 
     return result;
 }
 
+// What one zlib stream still gets out of a deflate stream that is cut short (a truncated file): everything up to the last
+// byte present, as gzread hands it out before it reports the end of the file.  False: the data are not deflate data.
+inline bool inflate_truncated_tail(const uint8_t *comp, size_t n, size_t start_bit, const uint8_t *dict, size_t dict_len, Bytes &out)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    size_t byte = start_bit >> 3;
+    const int k = (int)(start_bit & 7);
+    bool ok = true;
+    if (dict_len) ok = inflateSetDictionary(&zs, dict, (uInt)dict_len) == Z_OK;
+    if (ok && k && byte < n) { ok = inflatePrime(&zs, 8 - k, comp[byte] >> k) == Z_OK; ++byte; }
+    zs.next_in = const_cast<uint8_t *>(comp + std::min(byte, n));
+    zs.avail_in = (uInt)(n - std::min(byte, n));
+    out.n = 0;
+    out.reserve(std::max<size_t>(6 * n, 1u << 16));
+    size_t produced = 0;
+    while (ok) {
+        if (produced == out.cap) { out.n = produced; out.reserve(out.cap + out.cap / 2); }
+        zs.next_out = out.data() + produced;
+        const size_t room = std::min<size_t>(out.cap - produced, 1u << 30);
+        zs.avail_out = (uInt)room;
+        const int rc = inflate(&zs, Z_SYNC_FLUSH);
+        produced += room - zs.avail_out;
+        if (rc == Z_STREAM_END) break;
+        if (rc == Z_BUF_ERROR || (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0)) break;      // the input is used up
+        if (rc != Z_OK) { ok = false; break; }
+    }
+    inflateEnd(&zs);
+    out.n = ok ? produced : 0;
+    return ok;
+}
+
 // First bit at or after `from_bit` (and before `limit_bit`) where a dynamic block starts and two blocks inflate cleanly.
 inline size_t find_block_start(const uint8_t *comp, size_t n, size_t from_bit, size_t limit_bit, const uint8_t *dict)
 {

@@ -130,7 +130,19 @@ def test_parallel_gzip_reader_rejects_damage(harness, big_fastq, tmp_path):
         src.write_bytes(bytes(bad))
         p = subprocess.run([harness, "read", str(src), str(tmp_path / "out.bin"), "65536"], capture_output=True)
         assert p.returncode == 5 and b"Unable to read" in p.stderr, what
-    src = tmp_path / "cut.gz"
-    src.write_bytes(bytes(z[:len(z) * 2 // 3]))                          # truncated file
-    p = subprocess.run([harness, "read", str(src), str(tmp_path / "out.bin"), "65536"], capture_output=True)
-    assert p.returncode == 5
+
+
+def test_parallel_gzip_reader_on_a_truncated_file(harness, big_fastq, tmp_path):
+    """A gzip file that is cut short: gzread / gzgets (the reference's reader, fastq.cpp:8-30) hand out everything up to the last
+    byte present and then report the end of the file; the parallel reader must deliver exactly the same bytes."""
+    z = gzip.compress(big_fastq, 6)
+    for cut in (len(z) * 2 // 3, len(z) - 1000, len(z) - 4):
+        src = tmp_path / "cut.gz"
+        src.write_bytes(z[:cut])
+        got = []
+        for env in ({}, {"FAQCS_B200_PGZIP": "0"}):
+            p = subprocess.run([harness, "read", str(src), str(tmp_path / "out.bin"), "65536"], capture_output=True, env=dict(os.environ, **env))
+            assert p.returncode == 0, p.stderr.decode()
+            assert (b"mode zlib" if env else b"mode pgzip") in p.stdout
+            got.append((tmp_path / "out.bin").read_bytes())
+        assert got[0] == got[1] and big_fastq.startswith(got[0]) and len(got[0]) > len(big_fastq) // 2
