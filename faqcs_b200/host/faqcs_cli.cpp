@@ -470,6 +470,7 @@ struct Source {
     size_t pz_pend_off = 0;
     size_t pz_span = 0;                   // compressed bytes looked at per round
     size_t pz_min_piece = 256u << 10;     // a thread gets at least this much compressed data
+    int pz_solo_rounds = 0;               // rounds left in which no entry points are looked for
     uint32_t pz_crc = 0;
     uint64_t pz_isize = 0;
     void pz_read(size_t want)
@@ -514,7 +515,12 @@ struct Source {
         for (;;) {
             const size_t want = (size_t)min<off_t>(csize - cpos, (off_t)pz_span);
             pz_read(want);
-            pgz::Result R = pgz::inflate_parallel(cbuf.data(), want, pz_bit, pz_window, pz_window_len, threads, pz_min_piece);
+            // a stream without entry points (stored or fixed blocks, blocks larger than a piece) is left to one thread for a few
+            // rounds instead of being searched again and again
+            const int use = pz_solo_rounds > 0 ? 1 : threads;
+            if (pz_solo_rounds > 0) --pz_solo_rounds;
+            pgz::Result R = pgz::inflate_parallel(cbuf.data(), want, pz_bit, pz_window, pz_window_len, use, pz_min_piece);
+            if (use > 1 && R.pieces.size() == 1 && !R.error) pz_solo_rounds = 8;
             if (R.error) throw "fastq.cpp:next_read: Unable to read header";
             size_t total = 0;
             for (const pgz::Piece &pc : R.pieces) total += pc.out.size();
