@@ -921,7 +921,7 @@ __device__ __forceinline__ void process_generic(const KernelCtx &kc, uint32_t ma
 // ---------------------------------------------------------------------------------------------
 // trim_group: trim_read (trim.cpp:225-551) for the 32 reads r0 .. r0+31 of one mate, by one warp.
 // Returns, in the lane that owns read r0 + lane, the verdict {offset_5, length | flags << 24}
-// (length 0 = invalid).  KSEL / PLAIN: see k_trim_emit (fq_fused.cuh).
+// (length 0 = invalid).  KSEL / PLAIN: see k_trim below.
 // ---------------------------------------------------------------------------------------------
 #ifndef FQ_TRIM_THREADS
 #define FQ_TRIM_THREADS 1024
